@@ -1,0 +1,205 @@
+/*
+ * tfrecomm.h -- C ABI of libtfrecomm.so: the B200 (sm_100a) implementation of TF-recomm's
+ * matrix-factorization train step.
+ *
+ * The reference (jilljenn/TF-recomm) has NO FFI/plugin boundary of its own: it is Python that
+ * builds a TensorFlow 1.x graph (ops.py) and drives it with sess.run (svd_train_val.py:70-72).
+ * The boundary a drop-in must honour is therefore that Python surface (kept by tf-recomm_b200/ops.py,
+ * dataio.py, session.py); this C ABI is what sits directly below it and replaces the TensorFlow
+ * runtime.  Each entry point cites the reference lines (into /root/reference) whose arithmetic it
+ * replaces; "TF:" cites TensorFlow 1.x by file name.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only. Every pointer is a DEVICE pointer unless its name ends in _host.
+ *  - The caller owns all memory (tables, optimizer slots, workspaces); the library never allocates
+ *    device memory.  `stream` is a cudaStream_t passed as void*.  All calls are asynchronous on
+ *    `stream` and capturable in a CUDA graph (no host sync, no allocation).
+ *  - Return 0 on success, negative tfr_status on error; tfr_last_error() gives the message
+ *    (thread-local).  There is no CPU fallback anywhere: without a CUDA device every compute entry
+ *    point returns TFR_ERR_CUDA.
+ *  - ids are int32 row indices; tables are fp32, row-major, contiguous: feat[rows][dim].
+ */
+#ifndef TFRECOMM_H_
+#define TFRECOMM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFR_ABI_VERSION 1
+
+typedef enum {
+  TFR_OK = 0,
+  TFR_ERR_INVALID = -1, /* bad argument (null pointer, negative size, unsupported dim) */
+  TFR_ERR_CUDA = -2,    /* a CUDA runtime call failed; see tfr_last_error()            */
+  TFR_ERR_WORKSPACE = -3 /* workspace too small                                         */
+} tfr_status;
+
+/* Model-variant flags. 0 = README model (README.md:31-39, doc/graph_svd.png): plain dot, squared
+ * error, L2 on the gathered embeddings, Adam.  The fork as written is all four bits set. */
+enum {
+  TFR_ABS_ITEM = 1,        /* ops.py:44     tf.abs(feat_items) in the dot                 */
+  TFR_LOSS_SIGMOID_CE = 2, /* ops.py:125-126 summed sigmoid cross-entropy on the logits    */
+  TFR_REG_BIAS = 4,        /* ops.py:85-89  L2 on the gathered biases as well              */
+  TFR_OPT_SGD = 8          /* ops.py:145    GradientDescentOptimizer (scatter_sub, no Adam) */
+};
+/* var_list bits (ops.py:118,147-149; adaptive_test.py:28 trains the user side only) */
+enum { TFR_VAR_MU = 1, TFR_VAR_UB = 2, TFR_VAR_UF = 4, TFR_VAR_IB = 8, TFR_VAR_IF = 16, TFR_VAR_ALL = 31 };
+
+const char* tfr_last_error(void);
+int tfr_abi_version(void);
+/* Number of SMs of the current device (148 on B200), or negative status. */
+int tfr_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer scalars kept in DEVICE memory so that a captured graph can be replayed every step.
+ * Replaces the non-table state of TF AdamOptimizer (TF: adam.py _create_slots/_prepare/_finish):
+ * beta1_power/beta2_power advance by one fp32 multiply per step AFTER the applies; lr_t is
+ * recomputed at the start of each step as lr*sqrt(1-beta2_power)/(1-beta1_power) (A.4).
+ * The caller allocates sizeof(tfr_opt_scalars) device bytes and fills it with tfr_opt_init.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  float lr, reg, beta1, beta2, eps;
+  float beta1_power, beta2_power, lr_t;
+  float one_minus_beta1, one_minus_beta2; /* fp32(1)-fp32(beta), as TF computes them */
+  int32_t flags, var_mask;
+  int64_t global_step;   /* svd_train_val.py:48 tf.train.get_or_create_global_step()        */
+  int64_t batch_cursor;  /* next batch index into a device-resident index stream (see below) */
+  double se_sum;         /* sum over the last step's batch of (rate - infer)^2, float64 like
+                            svd_train_val.py:104 (np.power(train_rates - train_infer, 2))   */
+  float g_mu;            /* last step's d cost / d bias_global (sum_b e_b)                   */
+  float pad_;
+  double* se_ring;       /* optional device ring: se_ring[global_step % se_ring_len] = se_sum, so the
+                            driver's trailing-window train RMSE (svd_train_val.py:59,104,108) needs one
+                            read per epoch instead of one per step                            */
+  int64_t se_ring_len;
+} tfr_opt_scalars;
+
+int tfr_opt_init(tfr_opt_scalars* opt_dev, float lr, float reg, float beta1, float beta2, float eps,
+                 int32_t flags, int32_t var_mask, void* stream);
+int tfr_opt_set_se_ring(tfr_opt_scalars* opt_dev, double* se_ring, int64_t se_ring_len, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The five variables of ops.py:8-12,29-32 and their Adam slots (TF: adam.py zeros_like slots).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t user_num, item_num, dim, pad_;
+  float* mu;        /* bias_global   []      ops.py:8  */
+  float* user_bias; /* user_bias     [U]     ops.py:9  */
+  float* item_bias; /* item_bias     [I]     ops.py:11 */
+  float* user_feat; /* user_features [U,dim] ops.py:29 */
+  float* item_feat; /* item_features [I,dim] ops.py:31 */
+  float *m_mu, *v_mu, *m_ub, *v_ub, *m_ib, *v_ib, *m_uf, *v_uf, *m_if, *v_if; /* null in SGD mode */
+  uint8_t* user_touched; /* [U] all zero between steps: rows of this step's IndexedSlices      */
+  uint8_t* item_touched; /* [I]                                                                */
+} tfr_svd_tables;
+
+/* ---- forward only: replaces sess.run([logits, infer]) at svd_train_val.py:121-122 -----------
+ * gathers ops.py:13-14,37-38; logits = ((sum_k u*v' + mu) + b_u) + b_i ops.py:44-47;
+ * head ops.py:76-78 (fork: infer = round(sigmoid(logits)); README: infer = logits).
+ * logits / infer may be null.  B = 0 is a no-op. */
+int tfr_svd_forward(const tfr_svd_tables* t, const int32_t* users, const int32_t* items, int64_t B,
+                    int32_t flags, float* logits, float* infer, void* stream);
+
+/* ---- batch assembly: replaces dataio.ShuffleIterator.next (dataio.py:114-117) on the device ---
+ * cols_* are the training columns resident in HBM; row_index holds the pre-drawn MT19937
+ * `np.random.randint(0, N, B)` stream for many steps (generated on the host so that it is the
+ * reference's stream).  Batch k = rows row_index[k*B .. k*B+B).  If batch_index < 0 the batch
+ * number is read from opt->batch_cursor (graph replay).  Also marks users/items in the touched
+ * maps and computes lr_t for this step. */
+int tfr_svd_batch_assemble(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* col_user,
+                           const int32_t* col_item, const float* col_rate, const int64_t* row_index,
+                           int64_t batch_index, int64_t B, int32_t* users, int32_t* items, float* rates,
+                           void* stream);
+
+/* ---- dedup: replaces TF optimizer.py::_deduplicate_indexed_slices (tf.unique + unsorted_segment_sum)
+ * Stable LSD radix sort of (id, position): sorted_ids ascending, sorted_pos = original positions,
+ * ascending inside each run of equal ids (so a run lists one id's occurrences in BATCH ORDER).
+ * Two independent problems (user ids, item ids) are sorted by ONE cooperative launch.
+ * n may be 0.  max_id_* = number of rows of the table (exclusive upper bound of ids). */
+int64_t tfr_dedup_workspace_bytes(int64_t n);
+int tfr_dedup_sort_pairs(const int32_t* ids_a, int64_t max_id_a, int32_t* sorted_ids_a, int32_t* sorted_pos_a,
+                         const int32_t* ids_b, int64_t max_id_b, int32_t* sorted_ids_b, int32_t* sorted_pos_b,
+                         int64_t n, void* workspace, int64_t workspace_bytes, void* stream);
+/* tf.unique's own outputs from the sorted pairs (parity/debug API, not on the hot step):
+ * uniq[0..n_uniq) in order of FIRST OCCURRENCE, idx[b] = position of ids[b] in uniq, *n_uniq_dev.
+ * scratch: n int32. */
+int tfr_unique_first_occurrence(const int32_t* sorted_ids, const int32_t* sorted_pos, int64_t n,
+                                int32_t* uniq, int32_t* idx, int32_t* n_uniq_dev, int32_t* scratch,
+                                void* stream);
+
+/* ---- full train step: replaces sess.run([train_op, logits, infer]) at svd_train_val.py:70-72 ----
+ * forward + d cost/d logits (ops.py:124-126) -> dedup -> per-row summed gradients (loss + reg*L2 on
+ * the gathered rows, ops.py:81-89,140) -> TF sparse Adam over the WHOLE tables (A.4) / dense Adam on
+ * bias_global (A.5), or scatter_sub SGD (ops.py:145).  logits/infer come from the PRE-update tables
+ * (A.7).  users/items/rates are the assembled batch (device).  Advances opt->global_step,
+ * beta powers and batch_cursor; leaves the touched maps zeroed. */
+int64_t tfr_svd_step_workspace_bytes(int64_t B, int32_t dim);
+/* flags / var_mask must equal what tfr_opt_init was given (the host copy selects the launches, the
+ * device copy drives the kernels).  side_stream (optional, may be null) lets the streaming pass over
+ * the rows outside the slice overlap the forward/sort/segment-sum chain. */
+int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
+                       const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
+                       int32_t flags, int32_t var_mask, void* workspace, int64_t workspace_bytes, void* stream,
+                       void* side_stream);
+
+/* Pieces of the step, exported for parity tests and for callers that schedule them themselves. */
+typedef struct { /* carved out of the step workspace by tfr_svd_step_carve */
+  float* err;           /* [B] d cost / d logits                                     */
+  float* partials;      /* [TFR_MAX_PARTIALS] per-CTA sums of err                    */
+  double* se_partials;  /* [TFR_MAX_PARTIALS] per-CTA sums of (rate-infer)^2         */
+  int32_t *su_ids, *su_pos, *si_ids, *si_pos; /* sorted (id,pos) for users / items   */
+  float *gsum_uf, *gsum_if; /* [B,dim] summed gradient of the run whose head is at sorted index k */
+  float *gsum_ub, *gsum_ib; /* [B]                                                  */
+  float *cont_uf, *cont_if, *tail_uf, *tail_if; /* [n_tiles,dim] cross-tile partial sums */
+  float *cont_ub, *cont_ib, *tail_ub, *tail_ib; /* [n_tiles]                          */
+  void* sort_ws; int64_t sort_ws_bytes;
+  int32_t tile, n_tiles;
+} tfr_svd_step_ws;
+#define TFR_MAX_PARTIALS 1024
+int tfr_svd_step_carve(void* workspace, int64_t workspace_bytes, int64_t B, int32_t dim, tfr_svd_step_ws* out);
+/* forward + error: writes logits, infer, ws.err, partial sums (deterministic two-stage reduction). */
+int tfr_svd_fwd_err(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
+                    const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
+                    const tfr_svd_step_ws* ws, void* stream);
+/* marks touched rows + computes lr_t (what tfr_svd_batch_assemble does for a device-assembled batch) */
+int tfr_svd_mark_touched(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
+                         const int32_t* items, int64_t B, void* stream);
+/* ordered segment sums of the per-occurrence gradients (never materialised): for every run of equal
+ * ids in the sorted pairs, gsum[head k] = sum in batch order of (e_b*partner_row + reg*own_row). */
+int tfr_svd_segment_grads(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
+                          const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, void* stream);
+/* TF sparse Adam over a whole table, rows NOT marked touched (pure decay + step), one streaming pass. */
+int tfr_adam_stream_untouched(float* var, float* m, float* v, int64_t rows, int32_t width,
+                              const uint8_t* touched, const tfr_opt_scalars* opt, void* stream);
+/* ... and the rows of this step's slice: var/m/v[sorted_ids[k]] for every run head k, gradient gsum[k]. */
+int tfr_adam_touched(float* var, float* m, float* v, int32_t width, const int32_t* sorted_ids, int64_t n,
+                     const float* gsum, const tfr_opt_scalars* opt, void* stream);
+/* SGD: var[sorted_ids[k]] -= gsum[k] for run heads (gsum already holds sum of lr*g, ops.py:145). */
+int tfr_sgd_apply(float* var, int32_t width, const int32_t* sorted_ids, int64_t n, const float* gsum,
+                  void* stream);
+/* end of step: dense Adam/SGD on bias_global from the err partials (A.5), advance beta powers and
+ * counters (TF: adam.py::_finish), clear the touched maps. */
+int tfr_svd_finish_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
+                        const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, int32_t n_partials,
+                        void* stream);
+
+/* ---- FM forward: replaces forward.py:21-22 `fma` ---------------------------------------------
+ * yhat[r] = w0 + sum_i W_i x_i + 0.5 * sum_f ((sum_i V_if x_i)^2 - sum_i V_if^2 x_i^2) on CSR rows
+ * (indptr int64 [n+1], indices int32, data fp32).  sums (optional) receives sum_i V_if x_i [n,dim]. */
+int tfr_fm_forward(int64_t n_rows, const int64_t* indptr, const int32_t* indices, const float* data,
+                   const float* w0, const float* W, const float* V, int32_t dim, float* yhat, float* sums,
+                   void* stream);
+
+/* ---- CUDA-graph helpers (thin wrappers so that a ctypes host needs no CUDA bindings) ------------ */
+int tfr_graph_begin_capture(void* stream);
+int tfr_graph_end_capture(void* stream, void** graph_exec_out);
+int tfr_graph_launch(void* graph_exec, void* stream);
+int tfr_graph_destroy(void* graph_exec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFRECOMM_H_ */

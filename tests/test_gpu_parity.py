@@ -1,0 +1,395 @@
+"""GPU parity tests: the CUDA path (through the C ABI of include/tfrecomm.h) against the CPU oracle on the same
+seeded inputs.  Bar (BASELINE.json north_star): bit-exact id dedup / segment indexing; per-step parameters within
+1e-5 relative (fp32).  Run with `pytest -m gpu` on the B200 box.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import np_oracle
+from tf_recomm_b200 import _lib, init
+from tf_recomm_b200.engine import TABLE_NAMES, SvdEngine
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5   # north_star: per-step parameters within 1e-5 relative (fp32)
+ATOL = 2e-7   # absolute floor for entries near zero (tables are O(1e-2), updates O(lr))
+
+
+def zipf_ids(rng, n, size, a=1.0):
+    p = 1.0 / np.arange(1, n + 1) ** a
+    p /= p.sum()
+    return rng.permutation(n)[rng.choice(n, size=size, p=p)].astype(np.int32)
+
+
+def make_batch(rng, U, I, B, binary=False):
+    users = zipf_ids(rng, U, B, 0.6)
+    items = zipf_ids(rng, I, B, 1.0)
+    rates = rng.integers(0, 2, B).astype(np.float32) if binary else rng.integers(1, 6, B).astype(np.float32)
+    return users, items, rates
+
+
+def both(U, I, d, lr, reg, flags=0, var_mask=31, seed=1, bias_init="truncated_normal"):
+    tabs = init.init_tables(U, I, d, seed=seed, bias_init=bias_init)
+    eng = SvdEngine(U, I, d, lr, reg, flags=flags, var_mask=var_mask, tables=tabs)
+    orc = oracle.SvdOracle(tabs["mu"], tabs["user_bias"], tabs["item_bias"], tabs["user_feat"], tabs["item_feat"],
+                           lr, reg, flags=flags, var_mask=var_mask)
+    return eng, orc
+
+
+def assert_state_close(eng, orc, what=""):
+    got = eng.get_tables()
+    for n in TABLE_NAMES:
+        ref = getattr(orc, n)
+        np.testing.assert_allclose(got[n].reshape(ref.shape), ref, rtol=RTOL, atol=ATOL, err_msg="%s %s" % (what, n))
+        if not eng.sgd:
+            for s in ("m_", "v_"):
+                np.testing.assert_allclose(got[s + n].reshape(ref.shape), orc.slots[s + n], rtol=RTOL, atol=1e-12,
+                                           err_msg="%s %s%s" % (what, s, n))
+
+
+@pytest.mark.parametrize("d", [1, 4, 15, 20, 33, 64, 128, 256])
+@pytest.mark.parametrize("flags", [0, _lib.FORK_FLAGS])
+def test_forward_parity(d, flags):
+    rng = np.random.default_rng(d)
+    U, I, B = 301, 157, 1237
+    eng, orc = both(U, I, d, 1e-3, 0.05, flags=flags)
+    users, items, _ = make_batch(rng, U, I, B)
+    logits, infer = eng.forward(users, items)
+    ref_logits, ref_infer = orc.forward(users, items)
+    np.testing.assert_allclose(logits.cpu().numpy(), ref_logits, rtol=RTOL, atol=1e-6)
+    if flags:
+        # round(sigmoid(x)) may flip only where sigmoid is within float error of 0.5
+        diff = infer.cpu().numpy() != ref_infer
+        assert np.all(np.abs(ref_logits[diff]) < 1e-5)
+    else:
+        np.testing.assert_allclose(infer.cpu().numpy(), ref_infer, rtol=RTOL, atol=1e-6)
+
+
+def test_forward_empty_and_single():
+    eng, orc = both(10, 7, 15, 1e-3, 0.05)
+    logits, infer = eng.forward(np.zeros(0, np.int32), np.zeros(0, np.int32))
+    assert logits.numel() == 0 and infer.numel() == 0
+    logits, _ = eng.forward(np.array([9], np.int32), np.array([6], np.int32))
+    np.testing.assert_allclose(logits.cpu().numpy(), orc.forward([9], [6])[0], rtol=RTOL, atol=1e-6)
+
+
+def gpu_sort(ids_a, max_a, ids_b=None, max_b=1):
+    L = _lib.load()
+    n = len(ids_a)
+    dev = torch.device("cuda")
+    a = torch.from_numpy(np.ascontiguousarray(ids_a, np.int32)).to(dev)
+    b = torch.from_numpy(np.ascontiguousarray(ids_b, np.int32)).to(dev) if ids_b is not None else None
+    out = [torch.empty(max(n, 1), dtype=torch.int32, device=dev) for _ in range(4)]
+    nbytes = L.tfr_dedup_workspace_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.tfr_dedup_sort_pairs(a.data_ptr(), max_a, out[0].data_ptr(), out[1].data_ptr(),
+                                      b.data_ptr() if b is not None else None, max_b,
+                                      out[2].data_ptr() if b is not None else None,
+                                      out[3].data_ptr() if b is not None else None, n, ws.data_ptr(), nbytes, st))
+    torch.cuda.synchronize()
+    return [o[:n] for o in out]
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 511, 512, 513, 1000, 10000, 65536, 200001])
+def test_dedup_sort_bit_exact(n):
+    """Stable sort of (id, position): equals numpy's stable argsort bit for bit; both problems in one launch."""
+    rng = np.random.default_rng(n)
+    max_a, max_b = 162541, 3952
+    ids_a = zipf_ids(rng, max_a, n, 0.8)
+    ids_b = zipf_ids(rng, max_b, n, 1.1)
+    sa, pa, sb, pb = gpu_sort(ids_a, max_a, ids_b, max_b)
+    for ids, s, p in ((ids_a, sa, pa), (ids_b, sb, pb)):
+        order = np.argsort(ids, kind="stable").astype(np.int32)
+        assert np.array_equal(p.cpu().numpy(), order)
+        assert np.array_equal(s.cpu().numpy(), ids[order])
+
+
+@pytest.mark.parametrize("max_id", [1, 2, 255, 256, 257, 65536, 100_000_000])
+def test_dedup_sort_id_ranges(max_id):
+    """1..4 radix passes (ids up to 1e8 = config 5), all-equal ids, already-sorted and reversed inputs."""
+    rng = np.random.default_rng(5)
+    n = 5000
+    for ids in (rng.integers(0, max_id, n).astype(np.int32), np.full(n, max_id - 1, np.int32),
+                np.sort(rng.integers(0, max_id, n)).astype(np.int32),
+                np.sort(rng.integers(0, max_id, n))[::-1].astype(np.int32)):
+        s, p, _, _ = gpu_sort(ids, max_id)
+        order = np.argsort(ids, kind="stable").astype(np.int32)
+        assert np.array_equal(p.cpu().numpy(), order)
+        assert np.array_equal(s.cpu().numpy(), ids[order])
+
+
+@pytest.mark.parametrize("n", [1, 7, 64, 1000, 65536])
+def test_unique_first_occurrence_bit_exact(n):
+    """tf.unique semantics (first-occurrence order, idx) recovered from the sorted pairs: bit-exact vs oracle."""
+    L = _lib.load()
+    rng = np.random.default_rng(n + 3)
+    max_id = 3952
+    ids = zipf_ids(rng, max_id, n, 1.0)
+    s, p, _, _ = gpu_sort(ids, max_id)
+    dev = s.device
+    uniq = torch.empty(n, dtype=torch.int32, device=dev)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    scratch = torch.empty(n, dtype=torch.int32, device=dev)
+    nu = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(L.tfr_unique_first_occurrence(s.data_ptr(), p.data_ptr(), n, uniq.data_ptr(), idx.data_ptr(),
+                                             nu.data_ptr(), scratch.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream))
+    ref_uniq, ref_idx = oracle.unique_first_occurrence(ids)
+    k = int(nu.item())
+    assert k == len(ref_uniq)
+    assert np.array_equal(uniq[:k].cpu().numpy(), ref_uniq)
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+
+
+@pytest.mark.parametrize("d,B", [(15, 1000), (20, 777), (128, 4096), (4, 100), (33, 257)])
+@pytest.mark.parametrize("flags", [0, _lib.FORK_FLAGS])
+def test_segment_grads_vs_oracle(d, B, flags):
+    """Summed per-row gradients at run heads == oracle's tf.unique + unsorted_segment_sum of per-occurrence grads."""
+    L = _lib.load()
+    rng = np.random.default_rng(d * 1000 + B)
+    U, I = 211, 97
+    eng, orc = both(U, I, d, 5e-3, 0.01, flags=flags)
+    users, items, rates = make_batch(rng, U, I, B, binary=bool(flags))
+    du, di, dr = eng._dev_i32(users), eng._dev_i32(items), eng._dev_f32(rates)
+    ws = eng.step_ws(B)
+    st = torch.cuda.current_stream().cuda_stream
+    logits = torch.empty(B, device="cuda")
+    infer = torch.empty(B, device="cuda")
+    tp = C.byref(eng.tables_struct)
+    _lib.check(L.tfr_svd_mark_touched(tp, eng.opt.data_ptr(), du.data_ptr(), di.data_ptr(), B, st))
+    _lib.check(L.tfr_svd_fwd_err(tp, eng.opt.data_ptr(), du.data_ptr(), di.data_ptr(), dr.data_ptr(), B,
+                                 logits.data_ptr(), infer.data_ptr(), C.byref(ws), st))
+    _lib.check(L.tfr_dedup_sort_pairs(du.data_ptr(), U, ws.su_ids, ws.su_pos, di.data_ptr(), I, ws.si_ids, ws.si_pos,
+                                      B, ws.sort_ws, ws.sort_ws_bytes, st))
+    _lib.check(L.tfr_svd_segment_grads(tp, eng.opt.data_ptr(), du.data_ptr(), di.data_ptr(), B, C.byref(ws), st))
+    torch.cuda.synchronize()
+
+    wbase = eng.workspace(B)
+    base_ptr = wbase.data_ptr()
+
+    def ws_arr(ptr, count, dtype):
+        off = ptr - base_ptr
+        nbytes = count * np.dtype(dtype).itemsize
+        return wbase[off:off + nbytes].cpu().numpy().view(dtype)
+
+    g = orc.grads(users, items, rates)
+    lr = np.float32(5e-3)
+    scale = lr if flags & _lib.OPT_SGD else np.float32(1)
+    np.testing.assert_allclose(ws_arr(ws.err, B, np.float32), g["err"], rtol=RTOL, atol=1e-6)
+    for side, ids, gf, gb, sid_p, gs_p, gsb_p in (("user", users, g["g_uf"], g["g_ub"], ws.su_ids, ws.gsum_uf, ws.gsum_ub),
+                                                  ("item", items, g["g_if"], g["g_ib"], ws.si_ids, ws.gsum_if, ws.gsum_ib)):
+        sid = ws_arr(sid_p, B, np.int32)
+        gs = ws_arr(gs_p, B * d, np.float32).reshape(B, d)
+        gsb = ws_arr(gsb_p, B, np.float32)
+        heads = np.flatnonzero(np.r_[True, sid[1:] != sid[:-1]])
+        uq, idx = oracle.unique_first_occurrence(ids)
+        ref = oracle.segment_sum(gf * scale, idx, len(uq))
+        refb = oracle.segment_sum(gb * scale, idx, len(uq))
+        assert len(heads) == len(uq)                      # bit-exact: number of unique ids
+        assert np.array_equal(np.sort(uq), sid[heads])    # bit-exact: the unique id set
+        slot_of = {int(u): k for k, u in enumerate(uq)}
+        perm = np.array([slot_of[int(i)] for i in sid[heads]])
+        np.testing.assert_allclose(gs[heads], ref[perm], rtol=RTOL, atol=1e-7, err_msg=side)
+        np.testing.assert_allclose(gsb[heads], refb[perm], rtol=RTOL, atol=1e-6, err_msg=side)
+
+
+@pytest.mark.parametrize("U,I,d,B,steps", [(50, 30, 15, 64, 25), (301, 157, 20, 500, 10), (6040, 3952, 15, 1000, 10),
+                                           (2000, 1000, 128, 4096, 6), (97, 61, 33, 200, 8)])
+def test_train_step_parity_readme_adam(U, I, d, B, steps):
+    """README model: squared error + L2 on gathered embeddings + TF sparse Adam (whole-table decay)."""
+    rng = np.random.default_rng(U + d)
+    eng, orc = both(U, I, d, 1e-3, 0.05)
+    for s in range(steps):
+        users, items, rates = make_batch(rng, U, I, B)
+        logits, infer = eng.train_step(users, items, rates)
+        ref_logits, ref_infer = orc.train_step(users, items, rates)
+        np.testing.assert_allclose(logits.cpu().numpy(), ref_logits, rtol=RTOL, atol=1e-6, err_msg="step %d" % s)
+        np.testing.assert_allclose(infer.cpu().numpy(), ref_infer, rtol=RTOL, atol=1e-6)
+        assert_state_close(eng, orc, "step %d" % s)
+    sc = eng.opt_scalars()
+    assert sc.global_step == steps == orc.global_step
+    assert sc.beta1_power == pytest.approx(orc.s.beta1_power, rel=0, abs=0)   # same fp32 multiply chain
+    assert sc.beta2_power == pytest.approx(orc.s.beta2_power, rel=0, abs=0)
+    assert int(eng.user_touched.sum()) == 0 and int(eng.item_touched.sum()) == 0
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_two_stream_schedule_same_result(overlap):
+    rng = np.random.default_rng(3)
+    U, I, d, B = 3000, 1500, 128, 2048
+    eng, orc = both(U, I, d, 1e-3, 0.05)
+    eng.overlap = overlap
+    for s in range(5):
+        users, items, rates = make_batch(rng, U, I, B)
+        eng.train_step(users, items, rates)
+        orc.train_step(users, items, rates)
+    assert_state_close(eng, orc, "overlap=%s" % overlap)
+
+
+def test_train_step_parity_fork_sgd():
+    """The fork as written: abs item factors, sigmoid-CE, bias L2, SGD scatter_sub (ops.py:44,85-89,125,145)."""
+    rng = np.random.default_rng(11)
+    U, I, d, B = 120, 80, 20, 256
+    eng, orc = both(U, I, d, 5e-3, 0.01, flags=_lib.FORK_FLAGS)
+    for s in range(12):
+        users, items, rates = make_batch(rng, U, I, B, binary=True)
+        logits, infer = eng.train_step(users, items, rates)
+        ref_logits, ref_infer = orc.train_step(users, items, rates)
+        np.testing.assert_allclose(logits.cpu().numpy(), ref_logits, rtol=RTOL, atol=2e-6, err_msg="step %d" % s)
+        assert_state_close(eng, orc, "fork step %d" % s)
+
+
+def test_train_step_fork_loss_with_adam():
+    rng = np.random.default_rng(12)
+    U, I, d, B = 120, 80, 15, 256
+    flags = _lib.ABS_ITEM | _lib.LOSS_SIGMOID_CE | _lib.REG_BIAS
+    eng, orc = both(U, I, d, 5e-3, 0.01, flags=flags)
+    for s in range(8):
+        users, items, rates = make_batch(rng, U, I, B, binary=True)
+        eng.train_step(users, items, rates)
+        orc.train_step(users, items, rates)
+        assert_state_close(eng, orc, "fork+adam step %d" % s)
+
+
+def test_var_list_user_side_only():
+    """var_list=[user_bias, user_features] (adaptive_test.py:28): item side and bias_global must not move."""
+    rng = np.random.default_rng(13)
+    U, I, d, B = 90, 40, 15, 128
+    mask = _lib.VAR_UB | _lib.VAR_UF
+    eng, orc = both(U, I, d, 1e-2, 0.01, var_mask=mask)
+    before = eng.get_tables()
+    for s in range(5):
+        users, items, rates = make_batch(rng, U, I, B)
+        eng.train_step(users, items, rates)
+        orc.train_step(users, items, rates)
+    after = eng.get_tables()
+    for n in ("mu", "item_bias", "item_feat"):
+        assert np.array_equal(before[n], after[n])
+    assert_state_close(eng, orc, "var_list")
+
+
+def test_untouched_rows_keep_moving():
+    """TF IndexedSlices Adam decays m/v and steps var over the WHOLE table: a row touched once keeps moving."""
+    U, I, d = 40, 20, 15
+    eng, orc = both(U, I, d, 1e-2, 0.0)
+    u0 = np.array([3, 3, 5], np.int32); i0 = np.array([1, 2, 1], np.int32); r0 = np.array([4, 2, 5], np.float32)
+    eng.train_step(u0, i0, r0); orc.train_step(u0, i0, r0)
+    row3 = eng.get_tables()["user_feat"][3].copy()
+    u1 = np.array([7], np.int32); i1 = np.array([9], np.int32); r1 = np.array([3], np.float32)
+    eng.train_step(u1, i1, r1); orc.train_step(u1, i1, r1)
+    assert not np.array_equal(row3, eng.get_tables()["user_feat"][3])
+    assert_state_close(eng, orc, "untouched")
+
+
+def test_duplicate_heavy_batches():
+    """All occurrences hit one user / one item; runs far longer than a 32-entry tile."""
+    rng = np.random.default_rng(17)
+    U, I, d, B = 10, 6, 128, 3000
+    eng, orc = both(U, I, d, 1e-3, 0.05)
+    users = np.full(B, 4, np.int32)
+    items = rng.integers(0, 2, B).astype(np.int32)
+    rates = rng.integers(1, 6, B).astype(np.float32)
+    eng.train_step(users, items, rates)
+    orc.train_step(users, items, rates)
+    assert_state_close(eng, orc, "hot rows")
+
+
+def test_stream_graph_matches_host_fed():
+    """Device-resident data + pre-drawn index stream + ONE captured CUDA graph per step == host-fed steps."""
+    rng = np.random.default_rng(19)
+    U, I, d, B, N, steps = 500, 300, 15, 200, 5000, 7
+    cu = zipf_ids(rng, U, N, 0.5); ci = zipf_ids(rng, I, N, 1.0); cr = rng.integers(1, 6, N).astype(np.float32)
+    row_index = rng.integers(0, N, steps * B)
+    eng_a, orc = both(U, I, d, 1e-3, 0.05)
+    eng_b, _ = both(U, I, d, 1e-3, 0.05)
+    eng_c, _ = both(U, I, d, 1e-3, 0.05)
+    for e in (eng_b, eng_c):
+        e.set_train_data(cu, ci, cr)
+        e.set_index_stream(row_index, B)
+        e.set_se_ring(steps)
+    eng_b.run_stream_steps(steps, use_graph=True)
+    eng_c.run_stream_steps(steps, use_graph=False)
+    se_ref = []
+    for s in range(steps):
+        rows = row_index[s * B:(s + 1) * B]
+        out = eng_a.train_step_host(cu[rows].astype(np.float64), ci[rows].astype(np.float64), cr[rows].astype(np.float64))
+        ref_logits, ref_infer = orc.train_step(cu[rows], ci[rows], cr[rows])
+        np.testing.assert_allclose(out[1], ref_infer, rtol=RTOL, atol=1e-6)
+        se_ref.append(np.sum((cr[rows].astype(np.float64) - ref_infer.astype(np.float64)) ** 2))
+    torch.cuda.synchronize()
+    ta, tb, tc = eng_a.get_tables(), eng_b.get_tables(), eng_c.get_tables()
+    for n in ta:
+        assert np.array_equal(ta[n], tb[n]), n    # same kernels, same order: bit-identical
+        assert np.array_equal(ta[n], tc[n]), n
+    assert eng_b.global_step == steps
+    np.testing.assert_allclose(eng_b.se_ring.cpu().numpy(), np.array(se_ref), rtol=1e-5)
+
+
+def test_fm_forward_golden_and_oracle(golden_dir):
+    """FM forward: the golden vector produced by the reference's own `fma` (forward.py:21-22) and the C oracle."""
+    import os
+    L = _lib.load()
+    z = np.load(os.path.join(golden_dir, "fm_forward.npz"))
+    dev = torch.device("cuda")
+    for V in (z["V"], np.random.default_rng(0).standard_normal((40, 20)) * 0.1, np.random.default_rng(1).standard_normal((40, 128)) * 0.1):
+        indptr = torch.from_numpy(z["indptr"]).to(dev)
+        indices = torch.from_numpy(z["indices"]).to(dev)
+        data = torch.from_numpy(z["data"]).to(dev)
+        W = torch.from_numpy(z["W"].astype(np.float32)).to(dev)
+        Vd = torch.from_numpy(np.ascontiguousarray(V, np.float32)).to(dev)
+        w0 = torch.from_numpy(z["mu"].astype(np.float32).reshape(1)).to(dev)
+        n = len(z["indptr"]) - 1
+        y = torch.empty(n, device=dev)
+        _lib.check(L.tfr_fm_forward(n, indptr.data_ptr(), indices.data_ptr(), data.data_ptr(), w0.data_ptr(),
+                                    W.data_ptr(), Vd.data_ptr(), Vd.shape[1], y.data_ptr(), None,
+                                    torch.cuda.current_stream().cuda_stream))
+        ref = oracle.fm_forward(z["indptr"], z["indices"], z["data"], z["mu"], z["W"], V)
+        np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+        if V is z["V"]:
+            np.testing.assert_allclose(y.cpu().numpy(), z["y"], rtol=1e-5, atol=1e-6)
+
+
+# ---- BASELINE.json full sizes: size-independent properties -----------------------------------------------
+def test_full_size_config4_properties():
+    """ML-25M shape (162541 x 62423, d=128, B=65536): sortedness + permutation of the dedup, idempotence,
+    touched maps cleared, lr=0 leaves var unchanged while m,v decay exactly, and the device-drawn step equals a
+    second engine fed the same batch (determinism)."""
+    U, I, d, B = 162541, 62423, 128, 65536
+    rng = np.random.default_rng(23)
+    users = zipf_ids(rng, U, B, 0.7); items = zipf_ids(rng, I, B, 1.0)
+    rates = rng.integers(1, 6, B).astype(np.float32)
+    sa, pa, sb, pb = gpu_sort(users, U, items, I)
+    for ids, s, p in ((users, sa, pa), (items, sb, pb)):
+        s_, p_ = s.cpu().numpy(), p.cpu().numpy()
+        assert np.all(np.diff(s_) >= 0)                                  # sortedness
+        assert np.array_equal(np.sort(p_), np.arange(B))                  # a permutation
+        assert np.array_equal(ids[p_], s_)                                # consistent pairs
+        same = s_[1:] == s_[:-1]
+        assert np.all(p_[1:][same] > p_[:-1][same])                       # batch order inside a run
+        s2, _, _, _ = gpu_sort(s_, U)
+        assert np.array_equal(s2.cpu().numpy(), s_)                       # idempotence
+        assert len(np.unique(ids)) == int(np.sum(np.r_[True, ~same]))     # n_uniq
+    engs = [SvdEngine(U, I, d, 1e-3, 0.05, device_init_seed=7) for _ in range(2)]
+    for e in engs:
+        for _ in range(2):
+            e.train_step(users, items, rates)
+    a, b = engs[0].get_tables(), engs[1].get_tables()
+    for n in a:
+        assert np.array_equal(a[n], b[n]), n                              # deterministic, run to run
+    assert int(engs[0].user_touched.sum()) == 0 and int(engs[0].item_touched.sum()) == 0
+    # linearity-type property of the whole-table pass: with lr = 0, var is unchanged and m, v of rows outside
+    # the slice are exactly m*beta1, v*beta2
+    e0 = SvdEngine(U, I, d, 0.0, 0.05, device_init_seed=7)
+    e0.train_step(users, items, rates)
+    t1 = e0.get_tables()
+    e0.train_step(users[:1], items[:1], rates[:1])
+    t2 = e0.get_tables()
+    assert np.array_equal(t1["user_feat"], t2["user_feat"])
+    keep = np.ones(U, bool); keep[users[0]] = False
+    assert np.array_equal(t2["m_user_feat"][keep], t1["m_user_feat"][keep] * np.float32(0.9))
+    assert np.array_equal(t2["v_user_feat"][keep], t1["v_user_feat"][keep] * np.float32(0.999))

@@ -1,0 +1,7 @@
+"""tf-recomm_b200: B200 (sm_100a) implementation of TF-recomm's matrix-factorization train step.
+
+The directory name carries a hyphen (repo convention); import it as `tf_recomm_b200` through the alias module
+at the repo root.  Submodules: _lib (ctypes binding of libtfrecomm.so), engine (device state + step calls),
+ops / dataio / config / session (host-side mirror of the reference's Python surface), init, synthetic.
+"""
+__all__ = ["_lib", "engine", "init"]

@@ -1,0 +1,117 @@
+"""ctypes binding of libtfrecomm.so (include/tfrecomm.h).  No torch types cross this boundary: only raw
+device pointers (tensor.data_ptr()), sizes and a cudaStream_t handle.
+
+There is NO fallback: if the shared library is missing or a call fails, TfrError is raised.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libtfrecomm.so")
+
+ABS_ITEM, LOSS_SIGMOID_CE, REG_BIAS, OPT_SGD = 1, 2, 4, 8
+README_FLAGS = 0
+FORK_FLAGS = ABS_ITEM | LOSS_SIGMOID_CE | REG_BIAS | OPT_SGD
+VAR_MU, VAR_UB, VAR_UF, VAR_IB, VAR_IF, VAR_ALL = 1, 2, 4, 8, 16, 31
+MAX_PARTIALS = 1024
+
+vp = C.c_void_p
+i64 = C.c_int64
+i32 = C.c_int32
+f32 = C.c_float
+
+
+class TfrError(RuntimeError):
+    pass
+
+
+class OptScalars(C.Structure):
+    """Mirror of tfr_opt_scalars (device-resident)."""
+    _fields_ = [("lr", f32), ("reg", f32), ("beta1", f32), ("beta2", f32), ("eps", f32),
+                ("beta1_power", f32), ("beta2_power", f32), ("lr_t", f32),
+                ("one_minus_beta1", f32), ("one_minus_beta2", f32),
+                ("flags", i32), ("var_mask", i32),
+                ("global_step", i64), ("batch_cursor", i64), ("se_sum", C.c_double),
+                ("g_mu", f32), ("pad_", f32), ("se_ring", vp), ("se_ring_len", i64)]
+
+
+class SvdTables(C.Structure):
+    """Mirror of tfr_svd_tables (host struct of device pointers, passed by pointer)."""
+    _fields_ = [("user_num", i32), ("item_num", i32), ("dim", i32), ("pad_", i32),
+                ("mu", vp), ("user_bias", vp), ("item_bias", vp), ("user_feat", vp), ("item_feat", vp),
+                ("m_mu", vp), ("v_mu", vp), ("m_ub", vp), ("v_ub", vp), ("m_ib", vp), ("v_ib", vp),
+                ("m_uf", vp), ("v_uf", vp), ("m_if", vp), ("v_if", vp),
+                ("user_touched", vp), ("item_touched", vp)]
+
+
+class StepWs(C.Structure):
+    """Mirror of tfr_svd_step_ws."""
+    _fields_ = [("err", vp), ("partials", vp), ("se_partials", vp),
+                ("su_ids", vp), ("su_pos", vp), ("si_ids", vp), ("si_pos", vp),
+                ("gsum_uf", vp), ("gsum_if", vp), ("gsum_ub", vp), ("gsum_ib", vp),
+                ("cont_uf", vp), ("cont_if", vp), ("tail_uf", vp), ("tail_if", vp),
+                ("cont_ub", vp), ("cont_ib", vp), ("tail_ub", vp), ("tail_ib", vp),
+                ("sort_ws", vp), ("sort_ws_bytes", i64), ("tile", i32), ("n_tiles", i32)]
+
+
+# name -> (restype, argtypes).  Every symbol include/tfrecomm.h declares is listed here; the CPU test
+# suite checks that the library exports all of them.
+_PROTOS = {
+    "tfr_last_error": (C.c_char_p, []),
+    "tfr_abi_version": (C.c_int, []),
+    "tfr_device_sm_count": (C.c_int, []),
+    "tfr_opt_init": (C.c_int, [vp, f32, f32, f32, f32, f32, i32, i32, vp]),
+    "tfr_opt_set_se_ring": (C.c_int, [vp, vp, i64, vp]),
+    "tfr_svd_forward": (C.c_int, [C.POINTER(SvdTables), vp, vp, i64, i32, vp, vp, vp]),
+    "tfr_svd_batch_assemble": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp]),
+    "tfr_dedup_workspace_bytes": (i64, [i64]),
+    "tfr_dedup_sort_pairs": (C.c_int, [vp, i64, vp, vp, vp, i64, vp, vp, i64, vp, i64, vp]),
+    "tfr_unique_first_occurrence": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, vp]),
+    "tfr_svd_step_workspace_bytes": (i64, [i64, i32]),
+    "tfr_svd_train_step": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, i64, vp, vp, i32, i32, vp, i64, vp, vp]),
+    "tfr_svd_step_carve": (C.c_int, [vp, i64, i64, i32, C.POINTER(StepWs)]),
+    "tfr_svd_fwd_err": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, i64, vp, vp, C.POINTER(StepWs), vp]),
+    "tfr_svd_mark_touched": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, vp]),
+    "tfr_svd_segment_grads": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, C.POINTER(StepWs), vp]),
+    "tfr_adam_stream_untouched": (C.c_int, [vp, vp, vp, i64, i32, vp, vp, vp]),
+    "tfr_adam_touched": (C.c_int, [vp, vp, vp, i32, vp, i64, vp, vp, vp]),
+    "tfr_sgd_apply": (C.c_int, [vp, i32, vp, i64, vp, vp]),
+    "tfr_svd_finish_step": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, C.POINTER(StepWs), i32, vp]),
+    "tfr_fm_forward": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
+    "tfr_graph_begin_capture": (C.c_int, [vp]),
+    "tfr_graph_end_capture": (C.c_int, [vp, C.POINTER(vp)]),
+    "tfr_graph_launch": (C.c_int, [vp, vp]),
+    "tfr_graph_destroy": (C.c_int, [vp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library; raise loudly if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise TfrError(
+            "libtfrecomm.so is not built (%s). Run `python __graft_entry__.py build` (nvcc, sm_100a). "
+            "There is no CPU fallback for this path." % SO_PATH)
+    L = C.CDLL(SO_PATH)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    if L.tfr_abi_version() != 1:
+        raise TfrError("libtfrecomm.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc < 0:
+        raise TfrError("libtfrecomm: %s (status %d)" % (load().tfr_last_error().decode(), rc))
+    return rc
+
+
+def exported_symbols():
+    return sorted(_PROTOS)

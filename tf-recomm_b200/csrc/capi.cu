@@ -1,0 +1,206 @@
+// C-ABI glue: error reporting, workspace carving, the full train step (the sequence that replaces one
+// sess.run([train_op, logits, infer]) of svd_train_val.py:70-72) and CUDA-graph helpers.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace tfr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  cached = n;
+  return n;
+}
+
+int fwd_err_n_partials(int dim, int64_t B);
+
+}  // namespace tfr
+
+using namespace tfr;
+
+extern "C" const char* tfr_last_error(void) { return g_err; }
+extern "C" int tfr_abi_version(void) { return TFR_ABI_VERSION; }
+
+extern "C" int tfr_device_sm_count(void) {
+  int dev = 0, n = 0;
+  TFR_CUDA(cudaGetDevice(&dev));
+  TFR_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  return n;
+}
+
+__global__ void set_se_ring_kernel(tfr_opt_scalars* opt, double* ring, int64_t len) {
+  opt->se_ring = ring;
+  opt->se_ring_len = len;
+}
+
+extern "C" int tfr_opt_set_se_ring(tfr_opt_scalars* opt_dev, double* se_ring, int64_t se_ring_len, void* stream) {
+  TFR_CHECK_ARG(opt_dev && se_ring_len >= 0);
+  set_se_ring_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(opt_dev, se_ring, se_ring_len);
+  TFR_LAUNCH_CHECK();
+  return TFR_OK;
+}
+
+// ---- step workspace ---------------------------------------------------------------------------------
+static constexpr int kTile = 32;
+
+static int64_t carve(char* base, int64_t B, int32_t dim, tfr_svd_step_ws* o) {
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const int64_t n_tiles = (B + kTile - 1) / kTile;
+  tfr_svd_step_ws w;
+  memset(&w, 0, sizeof(w));
+  w.err = (float*)take(B * 4);
+  w.partials = (float*)take(TFR_MAX_PARTIALS * 4);
+  w.se_partials = (double*)take(TFR_MAX_PARTIALS * 8);
+  w.su_ids = (int32_t*)take(B * 4);
+  w.su_pos = (int32_t*)take(B * 4);
+  w.si_ids = (int32_t*)take(B * 4);
+  w.si_pos = (int32_t*)take(B * 4);
+  w.gsum_uf = (float*)take(B * (int64_t)dim * 4);
+  w.gsum_if = (float*)take(B * (int64_t)dim * 4);
+  w.gsum_ub = (float*)take(B * 4);
+  w.gsum_ib = (float*)take(B * 4);
+  w.cont_uf = (float*)take(n_tiles * dim * 4);
+  w.cont_if = (float*)take(n_tiles * dim * 4);
+  w.tail_uf = (float*)take(n_tiles * dim * 4);
+  w.tail_if = (float*)take(n_tiles * dim * 4);
+  w.cont_ub = (float*)take(n_tiles * 4);
+  w.cont_ib = (float*)take(n_tiles * 4);
+  w.tail_ub = (float*)take(n_tiles * 4);
+  w.tail_ib = (float*)take(n_tiles * 4);
+  w.sort_ws_bytes = tfr_dedup_workspace_bytes(B);
+  w.sort_ws = take(w.sort_ws_bytes);
+  w.tile = kTile;
+  w.n_tiles = (int32_t)n_tiles;
+  if (o) *o = w;
+  return off;
+}
+
+extern "C" int64_t tfr_svd_step_workspace_bytes(int64_t B, int32_t dim) {
+  if (B <= 0 || dim <= 0) return TFR_ERR_INVALID;
+  return carve(nullptr, B, dim, nullptr) + 256;
+}
+
+extern "C" int tfr_svd_step_carve(void* workspace, int64_t workspace_bytes, int64_t B, int32_t dim,
+                                  tfr_svd_step_ws* out) {
+  TFR_CHECK_ARG(workspace && out && B > 0 && dim > 0);
+  if (workspace_bytes < tfr_svd_step_workspace_bytes(B, dim)) {
+    set_error("step workspace too small: %lld < %lld", (long long)workspace_bytes,
+              (long long)tfr_svd_step_workspace_bytes(B, dim));
+    return TFR_ERR_WORKSPACE;
+  }
+  char* base = reinterpret_cast<char*>(align_up((int64_t)(uintptr_t)workspace, 256));
+  carve(base, B, dim, out);
+  return TFR_OK;
+}
+
+// ---- the step ------------------------------------------------------------------------------------------
+// Fork/join events for the two-stream schedule (streaming pass over the untouched rows overlaps the
+// forward -> sort -> segment-sum chain, which only touches this step's slice rows).
+static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+
+extern "C" int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
+                                  const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
+                                  int32_t flags, int32_t var_mask, void* workspace, int64_t workspace_bytes,
+                                  void* stream, void* side_stream) {
+  TFR_CHECK_ARG(t && opt && users && items && rates && B > 0 && t->dim > 0);
+  // flags / var_mask repeat what the caller gave tfr_opt_init: the device copy drives the kernels, the
+  // host copy selects which launches are issued (var_list: untrained tables get no launch at all).
+  const bool sgd = flags & TFR_OPT_SGD;
+  TFR_CHECK_ARG(sgd || (t->m_uf && t->v_uf && t->m_if && t->v_if && t->m_ub && t->v_ub && t->m_ib && t->v_ib &&
+                        t->m_mu && t->v_mu));
+  tfr_svd_step_ws ws;
+  int rc = tfr_svd_step_carve(workspace, workspace_bytes, B, t->dim, &ws);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t side = (cudaStream_t)side_stream;
+  const int dim = t->dim;
+
+  if (!sgd && side) {
+    if (!g_ev_fork) {
+      TFR_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+      TFR_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+    }
+    TFR_CUDA(cudaEventRecord(g_ev_fork, st));
+    TFR_CUDA(cudaStreamWaitEvent(side, g_ev_fork, 0));
+  }
+  cudaStream_t pass_st = (!sgd && side) ? side : st;
+
+  if ((rc = tfr_svd_fwd_err(t, opt, users, items, rates, B, logits, infer, &ws, st))) return rc;
+  if ((rc = tfr_dedup_sort_pairs(users, t->user_num, ws.su_ids, ws.su_pos, items, t->item_num, ws.si_ids, ws.si_pos,
+                                 B, ws.sort_ws, ws.sort_ws_bytes, st)))
+    return rc;
+  if ((rc = tfr_svd_segment_grads(t, opt, users, items, B, &ws, st))) return rc;
+
+  if (!sgd) {
+    // whole-table decay + step over the rows outside this step's slice (reads only touched maps + tables)
+    if ((var_mask & TFR_VAR_UF) && (rc = tfr_adam_stream_untouched(t->user_feat, t->m_uf, t->v_uf, t->user_num, dim, t->user_touched, opt, pass_st))) return rc;
+    if ((var_mask & TFR_VAR_IF) && (rc = tfr_adam_stream_untouched(t->item_feat, t->m_if, t->v_if, t->item_num, dim, t->item_touched, opt, pass_st))) return rc;
+    if ((var_mask & TFR_VAR_UB) && (rc = tfr_adam_stream_untouched(t->user_bias, t->m_ub, t->v_ub, t->user_num, 1, t->user_touched, opt, pass_st))) return rc;
+    if ((var_mask & TFR_VAR_IB) && (rc = tfr_adam_stream_untouched(t->item_bias, t->m_ib, t->v_ib, t->item_num, 1, t->item_touched, opt, pass_st))) return rc;
+    if ((var_mask & TFR_VAR_UF) && (rc = tfr_adam_touched(t->user_feat, t->m_uf, t->v_uf, dim, ws.su_ids, B, ws.gsum_uf, opt, st))) return rc;
+    if ((var_mask & TFR_VAR_IF) && (rc = tfr_adam_touched(t->item_feat, t->m_if, t->v_if, dim, ws.si_ids, B, ws.gsum_if, opt, st))) return rc;
+    if ((var_mask & TFR_VAR_UB) && (rc = tfr_adam_touched(t->user_bias, t->m_ub, t->v_ub, 1, ws.su_ids, B, ws.gsum_ub, opt, st))) return rc;
+    if ((var_mask & TFR_VAR_IB) && (rc = tfr_adam_touched(t->item_bias, t->m_ib, t->v_ib, 1, ws.si_ids, B, ws.gsum_ib, opt, st))) return rc;
+    if (side) {
+      TFR_CUDA(cudaEventRecord(g_ev_join, side));
+      TFR_CUDA(cudaStreamWaitEvent(st, g_ev_join, 0));
+    }
+  } else {
+    if ((var_mask & TFR_VAR_UF) && (rc = tfr_sgd_apply(t->user_feat, dim, ws.su_ids, B, ws.gsum_uf, st))) return rc;
+    if ((var_mask & TFR_VAR_IF) && (rc = tfr_sgd_apply(t->item_feat, dim, ws.si_ids, B, ws.gsum_if, st))) return rc;
+    if ((var_mask & TFR_VAR_UB) && (rc = tfr_sgd_apply(t->user_bias, 1, ws.su_ids, B, ws.gsum_ub, st))) return rc;
+    if ((var_mask & TFR_VAR_IB) && (rc = tfr_sgd_apply(t->item_bias, 1, ws.si_ids, B, ws.gsum_ib, st))) return rc;
+  }
+  return tfr_svd_finish_step(t, opt, users, items, B, &ws, fwd_err_n_partials(dim, B), st);
+}
+
+// ---- CUDA graphs ------------------------------------------------------------------------------------------
+extern "C" int tfr_graph_begin_capture(void* stream) {
+  TFR_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeRelaxed));
+  return TFR_OK;
+}
+
+extern "C" int tfr_graph_end_capture(void* stream, void** graph_exec_out) {
+  TFR_CHECK_ARG(graph_exec_out);
+  cudaGraph_t graph = nullptr;
+  TFR_CUDA(cudaStreamEndCapture((cudaStream_t)stream, &graph));
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    set_error("cudaGraphInstantiate -> %s", cudaGetErrorString(e));
+    return TFR_ERR_CUDA;
+  }
+  *graph_exec_out = (void*)exec;
+  return TFR_OK;
+}
+
+extern "C" int tfr_graph_launch(void* graph_exec, void* stream) {
+  TFR_CHECK_ARG(graph_exec);
+  TFR_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+  return TFR_OK;
+}
+
+extern "C" int tfr_graph_destroy(void* graph_exec) {
+  if (graph_exec) TFR_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+  return TFR_OK;
+}

@@ -1,0 +1,119 @@
+// Shared device/host helpers for libtfrecomm (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tfrecomm.h"
+
+namespace tfr {
+
+void set_error(const char* fmt, ...);
+int sm_count();
+
+#define TFR_CHECK_ARG(cond)                                                        \
+  do {                                                                             \
+    if (!(cond)) {                                                                 \
+      tfr::set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, #cond);    \
+      return TFR_ERR_INVALID;                                                      \
+    }                                                                              \
+  } while (0)
+
+#define TFR_CUDA(expr)                                                             \
+  do {                                                                             \
+    cudaError_t e__ = (expr);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      tfr::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+      return TFR_ERR_CUDA;                                                         \
+    }                                                                              \
+  } while (0)
+
+#define TFR_LAUNCH_CHECK() TFR_CUDA(cudaGetLastError())
+
+// ---- explicit-rounding fp32 arithmetic: every TensorFlow op is its own rounding, never an FMA ----
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
+
+// ---- cache-hinted 128-bit / 32-bit accesses ---------------------------------------------------
+// Streaming table data (the Adam pass reads and writes every byte exactly once per step): .cs =
+// cache-streaming (evict-first), so the pass does not push the batch's gathered rows out of L2.
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float ld_stream_f1(const float* p) {
+  float r;
+  asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f1(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+// Gathered rows: read-only path.  Safe because no kernel that gathers also writes the tables (they are
+// only written by the Adam kernels of the previous step), and the rows are re-read from L2 by the
+// segment-sum and the slice-row update.
+__device__ __forceinline__ float4 ld_gather_f4(const float4* p) {
+  float4 r;
+  asm("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_gather_f1(const float* p) {
+  float r;
+  asm("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
+// lane-group (L = 1..32, power of two) butterfly sum; every lane of the group gets the total.
+template <int L>
+__device__ __forceinline__ float group_sum(float x) {
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) x = add_rn(x, __shfl_xor_sync(0xffffffffu, x, o, L));
+  return x;
+}
+
+// TF: tf.sigmoid (Eigen scalar_logistic_op) = 1/(1+exp(-x)); tf.round = round-half-to-even.
+__device__ __forceinline__ float sigmoid_tf(float x) { return div_rn(1.0f, add_rn(1.0f, expf(-x))); }
+
+// d cost / d logits.  README: l2_loss(infer-rate) -> x - z (ops.py:124).
+// fork: sigmoid_cross_entropy_with_logits (ops.py:125), autodiff of TF's relu(x)-x*z+log1p(exp(-|x|)).
+__device__ __forceinline__ float dloss(int flags, float x, float z) {
+  if (!(flags & TFR_LOSS_SIGMOID_CE)) return sub_rn(x, z);
+  const bool cond = x >= 0.0f;
+  const float n = cond ? -x : x;
+  const float t = expf(n);
+  const float sgm = mul_rn(div_rn(1.0f, add_rn(1.0f, t)), t);
+  const float g = sub_rn(cond ? 1.0f : 0.0f, z);
+  return add_rn(g, cond ? -sgm : sgm);
+}
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// lane-group geometry for a row of `dim` floats: VEC = 4 when rows are 16-byte aligned (dim % 4 == 0),
+// else scalar; L = lanes cooperating on one row (power of two <= 32).
+struct RowGeom {
+  int vec, lanes;
+};
+inline RowGeom row_geom(int dim) {
+  RowGeom g;
+  g.vec = (dim % 4 == 0) ? 4 : 1;
+  int units = dim / g.vec;
+  int l = 1;
+  while (l < units && l < 32) l <<= 1;
+  g.lanes = l;
+  return g;
+}
+
+}  // namespace tfr

@@ -1,0 +1,252 @@
+// K3a: stable LSD radix sort of (id, position) pairs -- the "sort" half of the sort/segment-reduce that
+// replaces TF optimizer.py::_deduplicate_indexed_slices (tf.unique + tf.unsorted_segment_sum; SURVEY
+// A.3, reached from ops.py:144/148 through Optimizer.minimize).
+//
+// One cooperative launch sorts TWO independent key arrays (the batch's user ids and item ids): the
+// first half of the grid owns problem A, the second half problem B, and both advance through the
+// 8-bit digit passes in lock step with grid-wide barriers.  Per pass: (a) per-CTA digit histogram of
+// the CTA's contiguous chunk, (b) grid barrier, (c) every CTA derives its own scatter bases from all
+// histograms (digit-exclusive scan + counts of lower CTAs), (d) stable scatter tile by tile: inside a
+// warp equal digits are ranked with __match_any_sync, across warps by a per-digit walk over the 16
+// warps' counters.  Because positions start as 0..n-1 and every pass is stable, equal ids end up in
+// ascending position = batch order, which is what makes the segment sums reproduce
+// unsorted_segment_sum's in-order adds.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace tfr {
+
+constexpr int SORT_THREADS = 512;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int RADIX = 256;
+constexpr int SORT_MAX_BPP = 64;  // CTAs per problem; 2*64 <= 148 SMs keeps the grid co-resident
+
+struct SortProblem {
+  const int32_t* in_ids;
+  int32_t* out_ids;
+  int32_t* out_pos;
+  int32_t* tmp_ids;
+  int32_t* tmp_pos;
+  int64_t n;
+};
+
+__global__ void __launch_bounds__(SORT_THREADS) dedup_sort_kernel(SortProblem pa, SortProblem pb, int bpp, int n_passes,
+                                                                  uint32_t* __restrict__ hist_g) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t s_wc[SORT_WARPS][RADIX];
+  __shared__ uint32_t s_base[RADIX];
+  __shared__ uint32_t s_scan[RADIX / 32];
+
+  const int prob = blockIdx.x / bpp;
+  const int blk = blockIdx.x % bpp;
+  const SortProblem p = prob ? pb : pa;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  int64_t chunk = (p.n + bpp - 1) / bpp;
+  chunk = (chunk + SORT_THREADS - 1) / SORT_THREADS * SORT_THREADS;
+  const int64_t begin = min((int64_t)blk * chunk, p.n);
+  const int64_t end = min(begin + chunk, p.n);
+  uint32_t* my_hist = hist_g + ((size_t)prob * bpp + blk) * RADIX;
+
+  for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_wc[0][0])[i] = 0;
+
+  for (int pass = 0; pass < n_passes; ++pass) {
+    const int shift = pass * 8;
+    // ping-pong so that the LAST pass lands in out_*
+    const bool to_out = ((n_passes - 1 - pass) & 1) == 0;
+    const int32_t* src_ids = pass == 0 ? p.in_ids : (to_out ? p.tmp_ids : p.out_ids);
+    const int32_t* src_pos = pass == 0 ? nullptr : (to_out ? p.tmp_pos : p.out_pos);
+    int32_t* dst_ids = to_out ? p.out_ids : p.tmp_ids;
+    int32_t* dst_pos = to_out ? p.out_pos : p.tmp_pos;
+
+    // (a) histogram of my chunk
+    if (tid < RADIX) s_base[tid] = 0;
+    __syncthreads();
+    for (int64_t i0 = begin; i0 < end; i0 += SORT_THREADS) {
+      const int64_t i = i0 + tid;
+      const bool valid = i < end;
+      const uint32_t digit = valid ? (((uint32_t)src_ids[i] >> shift) & 255u) : 256u;
+      const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+      if (valid && (peers & lt_mask) == 0) atomicAdd(&s_base[digit], __popc(peers));
+    }
+    __syncthreads();
+    if (tid < RADIX) my_hist[tid] = s_base[tid];
+    grid.sync();
+
+    // (c) my scatter bases: exclusive scan over digits of the problem-wide totals + lower CTAs' counts
+    uint32_t tot = 0, mine = 0;
+    if (tid < RADIX) {
+      const uint32_t* h = hist_g + (size_t)prob * bpp * RADIX + tid;
+      for (int b = 0; b < bpp; ++b) {
+        const uint32_t c = h[(size_t)b * RADIX];
+        if (b < blk) mine += c;
+        tot += c;
+      }
+      uint32_t incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      if (lane == 31) s_scan[warp] = incl;
+      tot = incl - tot;  // exclusive within the warp
+    }
+    __syncthreads();
+    if (tid < RADIX) {
+      uint32_t off = 0;
+      for (int w = 0; w < warp; ++w) off += s_scan[w];
+      s_base[tid] = tot + off + mine;
+    }
+    __syncthreads();
+
+    // (d) stable scatter, tile by tile
+    for (int64_t i0 = begin; i0 < end; i0 += SORT_THREADS) {
+      const int64_t i = i0 + tid;
+      const bool valid = i < end;
+      const int32_t key = valid ? src_ids[i] : 0;
+      const int32_t pos = valid ? (src_pos ? src_pos[i] : (int32_t)i) : 0;
+      const uint32_t digit = valid ? (((uint32_t)key >> shift) & 255u) : 256u;
+      const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+      const uint32_t lrank = __popc(peers & lt_mask);
+      const bool leader = valid && lrank == 0;
+      if (leader) s_wc[warp][digit] = __popc(peers);
+      __syncthreads();
+      if (tid < RADIX) {
+        uint32_t run = s_base[tid];
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+          const uint32_t c = s_wc[w][tid];
+          if (c) { s_wc[w][tid] = run; run += c; }
+        }
+        s_base[tid] = run;
+      }
+      __syncthreads();
+      if (valid) {
+        const uint32_t d = s_wc[warp][digit] + lrank;
+        dst_ids[d] = key;
+        dst_pos[d] = pos;
+      }
+      __syncwarp();
+      if (leader) s_wc[warp][digit] = 0;
+    }
+    grid.sync();
+  }
+}
+
+// tf.unique outputs from the sorted pairs (parity API; single CTA, not on the hot step).
+__global__ void __launch_bounds__(1024) unique_first_occurrence_kernel(const int32_t* __restrict__ sid,
+                                                                       const int32_t* __restrict__ spos, int64_t n,
+                                                                       int32_t* __restrict__ uniq,
+                                                                       int32_t* __restrict__ idx,
+                                                                       int32_t* __restrict__ n_uniq_dev,
+                                                                       int32_t* __restrict__ scratch) {
+  __shared__ int32_t s_warp[32];
+  __shared__ int32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t b = tid; b < n; b += 1024) scratch[b] = 0;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  // is_first[b] = 1 where b is the first occurrence of its id (= the position of a run head)
+  for (int64_t k = tid; k < n; k += 1024)
+    if (k == 0 || sid[k] != sid[k - 1]) scratch[spos[k]] = 1;
+  __syncthreads();
+  // exclusive scan over batch positions -> rank in first-occurrence order
+  for (int64_t b0 = 0; b0 < n; b0 += 1024) {
+    const int64_t b = b0 + tid;
+    const int32_t x = b < n ? scratch[b] : 0;
+    int32_t incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int32_t off = s_carry;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (b < n) scratch[b] = off + incl - x;
+    __syncthreads();
+    if (tid == 1023) s_carry = off + incl;
+    __syncthreads();
+  }
+  if (tid == 0) *n_uniq_dev = s_carry;
+  // every run head labels its run
+  for (int64_t k = tid; k < n; k += 1024) {
+    if (k == 0 || sid[k] != sid[k - 1]) {
+      const int32_t id = sid[k];
+      const int32_t r = scratch[spos[k]];
+      uniq[r] = id;
+      for (int64_t j = k; j < n && sid[j] == id; ++j) idx[spos[j]] = r;
+    }
+  }
+}
+
+static int bits_for(int64_t max_id) {
+  int bits = 1;
+  while (bits < 32 && ((int64_t)1 << bits) < max_id) ++bits;
+  return bits;
+}
+
+}  // namespace tfr
+
+using namespace tfr;
+
+static int sort_bpp(int64_t n) {
+  int64_t bpp = (n + 2047) / 2048;
+  if (bpp < 1) bpp = 1;
+  if (bpp > SORT_MAX_BPP) bpp = SORT_MAX_BPP;
+  return (int)bpp;
+}
+
+extern "C" int64_t tfr_dedup_workspace_bytes(int64_t n) {
+  if (n < 0) return TFR_ERR_INVALID;
+  return align_up(2 * SORT_MAX_BPP * RADIX * (int64_t)sizeof(uint32_t), 256) + 4 * align_up(n * 4, 256) + 256;
+}
+
+extern "C" int tfr_dedup_sort_pairs(const int32_t* ids_a, int64_t max_id_a, int32_t* sorted_ids_a,
+                                    int32_t* sorted_pos_a, const int32_t* ids_b, int64_t max_id_b,
+                                    int32_t* sorted_ids_b, int32_t* sorted_pos_b, int64_t n, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  TFR_CHECK_ARG(n >= 0 && n < ((int64_t)1 << 31));
+  if (n == 0) return TFR_OK;
+  TFR_CHECK_ARG(ids_a && sorted_ids_a && sorted_pos_a && workspace && max_id_a > 0);
+  TFR_CHECK_ARG(!ids_b || (sorted_ids_b && sorted_pos_b && max_id_b > 0));
+  if (workspace_bytes < tfr_dedup_workspace_bytes(n)) {
+    set_error("dedup workspace too small: %lld < %lld", (long long)workspace_bytes,
+              (long long)tfr_dedup_workspace_bytes(n));
+    return TFR_ERR_WORKSPACE;
+  }
+  char* w = reinterpret_cast<char*>(align_up((int64_t)(uintptr_t)workspace, 256));
+  uint32_t* hist = reinterpret_cast<uint32_t*>(w);
+  w += align_up(2 * SORT_MAX_BPP * RADIX * (int64_t)sizeof(uint32_t), 256);
+  const int64_t seg = align_up(n * 4, 256);
+  SortProblem pa{ids_a, sorted_ids_a, sorted_pos_a, (int32_t*)w, (int32_t*)(w + seg), n};
+  SortProblem pb{ids_b, sorted_ids_b, sorted_pos_b, (int32_t*)(w + 2 * seg), (int32_t*)(w + 3 * seg), ids_b ? n : 0};
+  int bits = bits_for(max_id_a);
+  if (ids_b && bits_for(max_id_b) > bits) bits = bits_for(max_id_b);
+  int n_passes = (bits + 7) / 8;
+  int bpp = sort_bpp(n);
+  void* args[] = {&pa, &pb, &bpp, &n_passes, &hist};
+  TFR_CUDA(cudaLaunchCooperativeKernel((const void*)dedup_sort_kernel, dim3(2 * bpp), dim3(SORT_THREADS), args, 0,
+                                       (cudaStream_t)stream));
+  return TFR_OK;
+}
+
+extern "C" int tfr_unique_first_occurrence(const int32_t* sorted_ids, const int32_t* sorted_pos, int64_t n,
+                                           int32_t* uniq, int32_t* idx, int32_t* n_uniq_dev, int32_t* scratch,
+                                           void* stream) {
+  TFR_CHECK_ARG(n >= 0 && n_uniq_dev);
+  if (n == 0) {
+    TFR_CUDA(cudaMemsetAsync(n_uniq_dev, 0, sizeof(int32_t), (cudaStream_t)stream));
+    return TFR_OK;
+  }
+  TFR_CHECK_ARG(sorted_ids && sorted_pos && uniq && idx && scratch);
+  unique_first_occurrence_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sorted_ids, sorted_pos, n, uniq, idx, n_uniq_dev,
+                                                                     scratch);
+  TFR_LAUNCH_CHECK();
+  return TFR_OK;
+}

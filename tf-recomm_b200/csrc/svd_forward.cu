@@ -1,0 +1,235 @@
+// K0 batch assembly, K1 forward (eval), K2 forward + d cost/d logits (train).
+//
+// Reference arithmetic replaced here (file:line into /root/reference):
+//   dataio.py:114-117   ShuffleIterator.next: rows = inputs[randint ids]           -> batch_assemble_kernel
+//   ops.py:13-14,37-38  four embedding_lookup gathers                               -> row loads below
+//   ops.py:44-47        logits = ((sum_k u*v' + mu) + b_u) + b_i                     -> svd_logit
+//   ops.py:76-78        fork head: infer = round(sigmoid(logits)); README: logits   -> head()
+//   ops.py:124-126      d cost/d logits (squared error / sigmoid-CE)                 -> tfr::dloss
+//
+// Layout: warp lanes are split in groups of L lanes, one group per batch row; a lane owns VEC
+// consecutive floats of the row per pass (128-bit loads when dim % 4 == 0).  Two rows per group are
+// in flight to double the outstanding gathers.  Products and adds are separate fp32 roundings
+// (tf.multiply then tf.reduce_sum), the lane-group butterfly fixes the reduction order.
+#include "common.cuh"
+
+namespace tfr {
+
+template <int VEC, int L>
+__device__ __forceinline__ float row_dot(const float* __restrict__ pu, const float* __restrict__ qi, int dim,
+                                         int lane, bool abs_item) {
+  float acc = 0.0f;
+  if (VEC == 4) {
+    const float4* pu4 = reinterpret_cast<const float4*>(pu);
+    const float4* qi4 = reinterpret_cast<const float4*>(qi);
+    const int n4 = dim >> 2;
+    for (int k = lane; k < n4; k += L) {
+      const float4 a = ld_gather_f4(pu4 + k);
+      float4 b = ld_gather_f4(qi4 + k);
+      if (abs_item) { b.x = fabsf(b.x); b.y = fabsf(b.y); b.z = fabsf(b.z); b.w = fabsf(b.w); }
+      acc = add_rn(acc, mul_rn(a.x, b.x));
+      acc = add_rn(acc, mul_rn(a.y, b.y));
+      acc = add_rn(acc, mul_rn(a.z, b.z));
+      acc = add_rn(acc, mul_rn(a.w, b.w));
+    }
+  } else {
+    for (int k = lane; k < dim; k += L) {
+      const float a = ld_gather_f1(pu + k);
+      float b = ld_gather_f1(qi + k);
+      if (abs_item) b = fabsf(b);
+      acc = add_rn(acc, mul_rn(a, b));
+    }
+  }
+  return group_sum<L>(acc);
+}
+
+__device__ __forceinline__ float head(int flags, float x) {
+  return (flags & TFR_LOSS_SIGMOID_CE) ? rintf(sigmoid_tf(x)) : x;
+}
+
+// TRAIN = false: eval forward.  TRAIN = true: also err[b], per-CTA partial sums of err and of the
+// float64 squared error (svd_train_val.py:104).
+template <int VEC, int L, bool TRAIN>
+__global__ void __launch_bounds__(256) svd_forward_kernel(tfr_svd_tables t, const tfr_opt_scalars* __restrict__ opt,
+                                                          const int32_t* __restrict__ users,
+                                                          const int32_t* __restrict__ items,
+                                                          const float* __restrict__ rates, int64_t B, int flags_arg,
+                                                          float* __restrict__ logits, float* __restrict__ infer,
+                                                          float* __restrict__ err, float* __restrict__ partials,
+                                                          double* __restrict__ se_partials) {
+  constexpr int GPW = 32 / L;  // groups per warp
+  const int lane = threadIdx.x & (L - 1);
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / L;
+  const int flags = TRAIN ? opt->flags : flags_arg;
+  const bool abs_item = flags & TFR_ABS_ITEM;
+  const int dim = t.dim;
+  const float mu = *t.mu;
+  float err_acc = 0.0f;
+  double se_acc = 0.0;
+
+  // all lanes of a warp iterate the same number of times (shuffles inside row_dot need full warps)
+  const int64_t warp_first = group - (group % GPW);
+  for (int64_t b0 = warp_first; b0 < B; b0 += 2 * n_groups) {
+    const int64_t ba = b0 + (group % GPW), bb = ba + n_groups;
+    const bool va = ba < B, vb = bb < B;
+    const int32_t ua = va ? users[ba] : 0, ia = va ? items[ba] : 0;
+    const int32_t ub = vb ? users[bb] : 0, ib = vb ? items[bb] : 0;
+    const float xa0 = row_dot<VEC, L>(t.user_feat + (size_t)ua * dim, t.item_feat + (size_t)ia * dim, dim, lane, abs_item);
+    const float xb0 = row_dot<VEC, L>(t.user_feat + (size_t)ub * dim, t.item_feat + (size_t)ib * dim, dim, lane, abs_item);
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const bool valid = h ? vb : va;
+        if (!valid) continue;
+        const int64_t b = h ? bb : ba;
+        const int32_t u = h ? ub : ua, i = h ? ib : ia;
+        float x = add_rn(h ? xb0 : xa0, mu);               // ops.py:45
+        x = add_rn(x, ld_gather_f1(t.user_bias + u));      // ops.py:46
+        x = add_rn(x, ld_gather_f1(t.item_bias + i));      // ops.py:47
+        const float inf = head(flags, x);
+        if (logits) logits[b] = x;
+        if (infer) infer[b] = inf;
+        if (TRAIN) {
+          const float z = rates[b];
+          const float e = dloss(flags, x, z);
+          err[b] = e;
+          err_acc = add_rn(err_acc, e);
+          const double dse = (double)z - (double)inf;
+          se_acc += dse * dse;
+        }
+      }
+    }
+  }
+  if (TRAIN) {
+    // fixed-order block reduction: group leaders -> shared -> thread 0 sums sequentially.
+    __shared__ float s_err[256];
+    __shared__ double s_se[256];
+    s_err[threadIdx.x] = (lane == 0) ? err_acc : 0.0f;
+    s_se[threadIdx.x] = (lane == 0) ? se_acc : 0.0;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float a = 0.0f;
+      double d = 0.0;
+      for (int j = threadIdx.x; j < 256; j += 32) { a = add_rn(a, s_err[j]); d += s_se[j]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a = add_rn(a, __shfl_xor_sync(0xffffffffu, a, o));
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+      }
+      if (threadIdx.x == 0) { partials[blockIdx.x] = a; se_partials[blockIdx.x] = d; }
+    }
+  }
+}
+
+// lr_t = lr*sqrt(1-beta2_power)/(1-beta1_power), three fp32 roundings (TF: adam.py _apply_sparse_shared)
+__device__ __forceinline__ void begin_step_scalars(tfr_opt_scalars* opt) {
+  float tt = sqrt_rn(sub_rn(1.0f, opt->beta2_power));
+  tt = mul_rn(opt->lr, tt);
+  opt->lr_t = div_rn(tt, sub_rn(1.0f, opt->beta1_power));
+}
+
+__global__ void __launch_bounds__(256) batch_assemble_kernel(tfr_svd_tables t, tfr_opt_scalars* opt,
+                                                             const int32_t* __restrict__ col_user,
+                                                             const int32_t* __restrict__ col_item,
+                                                             const float* __restrict__ col_rate,
+                                                             const int64_t* __restrict__ row_index, int64_t batch_index,
+                                                             int64_t B, int32_t* __restrict__ users,
+                                                             int32_t* __restrict__ items, float* __restrict__ rates) {
+  const int64_t batch = batch_index >= 0 ? batch_index : opt->batch_cursor;
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    int32_t u, i;
+    if (row_index) {
+      const int64_t row = row_index[batch * B + b];
+      u = col_user[row];
+      i = col_item[row];
+      rates[b] = col_rate[row];
+      users[b] = u;
+      items[b] = i;
+    } else {
+      u = users[b];
+      i = items[b];
+    }
+    t.user_touched[u] = 1;
+    t.item_touched[i] = 1;
+  }
+  if (b == 0) begin_step_scalars(opt);
+}
+
+template <bool TRAIN>
+static int launch_forward(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
+                          const int32_t* items, const float* rates, int64_t B, int flags, float* logits, float* infer,
+                          float* err, float* partials, double* se_partials, int* n_partials_out, cudaStream_t st) {
+  const RowGeom g = row_geom(t->dim);
+  const int64_t rows_per_cta = 256 / g.lanes * 2;
+  int64_t grid = (B + rows_per_cta - 1) / rows_per_cta;
+  const int64_t cap = TRAIN ? TFR_MAX_PARTIALS : (int64_t)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  if (n_partials_out) *n_partials_out = (int)grid;
+#define TFR_FWD_CASE(V, LL)                                                                                     \
+  if (g.vec == V && g.lanes == LL) {                                                                            \
+    svd_forward_kernel<V, LL, TRAIN><<<(unsigned)grid, 256, 0, st>>>(*t, opt, users, items, rates, B, flags, logits, \
+                                                                     infer, err, partials, se_partials);        \
+    TFR_LAUNCH_CHECK();                                                                                          \
+    return TFR_OK;                                                                                               \
+  }
+  TFR_FWD_CASE(4, 1) TFR_FWD_CASE(4, 2) TFR_FWD_CASE(4, 4) TFR_FWD_CASE(4, 8) TFR_FWD_CASE(4, 16) TFR_FWD_CASE(4, 32)
+  TFR_FWD_CASE(1, 1) TFR_FWD_CASE(1, 2) TFR_FWD_CASE(1, 4) TFR_FWD_CASE(1, 8) TFR_FWD_CASE(1, 16) TFR_FWD_CASE(1, 32)
+#undef TFR_FWD_CASE
+  set_error("unsupported dim %d", t->dim);
+  return TFR_ERR_INVALID;
+}
+
+int fwd_err_n_partials(int dim, int64_t B) {
+  const RowGeom g = row_geom(dim);
+  const int64_t rows_per_cta = 256 / g.lanes * 2;
+  int64_t grid = (B + rows_per_cta - 1) / rows_per_cta;
+  if (grid > TFR_MAX_PARTIALS) grid = TFR_MAX_PARTIALS;
+  if (grid < 1) grid = 1;
+  return (int)grid;
+}
+
+}  // namespace tfr
+
+using namespace tfr;
+
+extern "C" int tfr_svd_forward(const tfr_svd_tables* t, const int32_t* users, const int32_t* items, int64_t B,
+                               int32_t flags, float* logits, float* infer, void* stream) {
+  TFR_CHECK_ARG(t && t->dim > 0 && B >= 0);
+  if (B == 0) return TFR_OK;
+  TFR_CHECK_ARG(users && items && t->user_feat && t->item_feat && t->user_bias && t->item_bias && t->mu);
+  return launch_forward<false>(t, nullptr, users, items, nullptr, B, flags, logits, infer, nullptr, nullptr, nullptr,
+                               nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int tfr_svd_fwd_err(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
+                               const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
+                               const tfr_svd_step_ws* ws, void* stream) {
+  TFR_CHECK_ARG(t && opt && ws && t->dim > 0 && B > 0 && users && items && rates);
+  return launch_forward<true>(t, opt, users, items, rates, B, 0, logits, infer, ws->err, ws->partials,
+                              ws->se_partials, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int tfr_svd_batch_assemble(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* col_user,
+                                      const int32_t* col_item, const float* col_rate, const int64_t* row_index,
+                                      int64_t batch_index, int64_t B, int32_t* users, int32_t* items, float* rates,
+                                      void* stream) {
+  TFR_CHECK_ARG(t && opt && B > 0 && users && items && rates && col_user && col_item && col_rate && row_index);
+  TFR_CHECK_ARG(t->user_touched && t->item_touched);
+  batch_assemble_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      *t, opt, col_user, col_item, col_rate, row_index, batch_index, B, users, items, rates);
+  TFR_LAUNCH_CHECK();
+  return TFR_OK;
+}
+
+extern "C" int tfr_svd_mark_touched(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
+                                    const int32_t* items, int64_t B, void* stream) {
+  TFR_CHECK_ARG(t && opt && B > 0 && users && items && t->user_touched && t->item_touched);
+  batch_assemble_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      *t, opt, nullptr, nullptr, nullptr, nullptr, 0, B, const_cast<int32_t*>(users), const_cast<int32_t*>(items),
+      nullptr);
+  TFR_LAUNCH_CHECK();
+  return TFR_OK;
+}

@@ -1,0 +1,305 @@
+"""SvdEngine: the device-resident state of the matrix-factorization model and the calls that step it.
+
+It owns what the TensorFlow session owned in the reference (the five variables of ops.py:8-12,29-32, the
+Adam slots, global_step -- svd_train_val.py:47-56) as CUDA tensors, and drives libtfrecomm.so through
+ctypes.  torch is plumbing here (device memory, streams, pinned staging); all arithmetic of the path is in
+the hand-written kernels.  No CPU fallback: constructing an engine without CUDA raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ABS_ITEM, FORK_FLAGS, LOSS_SIGMOID_CE, OPT_SGD, README_FLAGS, REG_BIAS, VAR_ALL, OptScalars, StepWs,
+                   SvdTables, TfrError, check)
+
+TABLE_NAMES = ("mu", "user_bias", "item_bias", "user_feat", "item_feat")
+_SLOT_FIELDS = {"mu": ("m_mu", "v_mu"), "user_bias": ("m_ub", "v_ub"), "item_bias": ("m_ib", "v_ib"),
+                "user_feat": ("m_uf", "v_uf"), "item_feat": ("m_if", "v_if")}
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise TfrError("tf-recomm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback for this path")
+
+
+class SvdEngine:
+    def __init__(self, user_num, item_num, dim, lr, reg, flags=README_FLAGS, var_mask=VAR_ALL, beta1=0.9,
+                 beta2=0.999, eps=1e-8, tables=None, device=None, device_init_seed=None):
+        """tables: dict of numpy arrays (mu, user_bias, item_bias, user_feat, item_feat) to inject; if None the
+        tables are drawn ON THE DEVICE (truncated normal 0.02 / zeros biases) -- for shapes too large to stage
+        through host memory (100M x 128)."""
+        _require_cuda()
+        self.L = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.U, self.I, self.d = int(user_num), int(item_num), int(dim)
+        self.flags, self.var_mask = int(flags), int(var_mask)
+        self.sgd = bool(flags & OPT_SGD)
+        self.hyper = dict(lr=float(lr), reg=float(reg), beta1=float(beta1), beta2=float(beta2), eps=float(eps))
+        dev = self.device
+        with torch.cuda.device(dev):
+            self.t = {}
+            if tables is not None:
+                for n in TABLE_NAMES:
+                    a = np.ascontiguousarray(tables[n], dtype=np.float32)
+                    self.t[n] = torch.from_numpy(a.reshape(-1) if n == "mu" else a).to(dev).contiguous()
+            else:
+                g = torch.Generator(device=dev)
+                g.manual_seed(13575 if device_init_seed is None else int(device_init_seed))
+                self.t["mu"] = torch.zeros(1, device=dev)
+                self.t["user_bias"] = torch.zeros(self.U, device=dev)
+                self.t["item_bias"] = torch.zeros(self.I, device=dev)
+                self.t["user_feat"] = torch.empty(self.U, self.d, device=dev)
+                self.t["item_feat"] = torch.empty(self.I, self.d, device=dev)
+                for n in ("user_feat", "item_feat"):
+                    torch.nn.init.trunc_normal_(self.t[n], mean=0.0, std=0.02, a=-0.04, b=0.04, generator=g)
+            assert self.t["user_feat"].shape == (self.U, self.d) and self.t["item_feat"].shape == (self.I, self.d)
+            self.slots = {}
+            if not self.sgd:
+                for n in TABLE_NAMES:
+                    self.slots["m_" + n] = torch.zeros_like(self.t[n])
+                    self.slots["v_" + n] = torch.zeros_like(self.t[n])
+            self.user_touched = torch.zeros(self.U, dtype=torch.uint8, device=dev)
+            self.item_touched = torch.zeros(self.I, dtype=torch.uint8, device=dev)
+            self.opt = torch.zeros(C.sizeof(OptScalars), dtype=torch.uint8, device=dev)
+            self.side_stream = torch.cuda.Stream(device=dev)
+            self._fill_struct()
+            check(self.L.tfr_opt_init(self.opt.data_ptr(), lr, reg, beta1, beta2, eps, self.flags, self.var_mask,
+                                      self._stream()))
+        self._ws = {}
+        self._stage = {}
+        self._graphs = {}
+        self.data = None
+        self.se_ring = None
+        self.overlap = True
+
+    # ---- plumbing ---------------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _fill_struct(self):
+        s = SvdTables()
+        s.user_num, s.item_num, s.dim = self.U, self.I, self.d
+        s.mu, s.user_bias, s.item_bias = (self.t[n].data_ptr() for n in ("mu", "user_bias", "item_bias"))
+        s.user_feat, s.item_feat = self.t["user_feat"].data_ptr(), self.t["item_feat"].data_ptr()
+        if not self.sgd:
+            for n, (mf, vf) in _SLOT_FIELDS.items():
+                setattr(s, mf, self.slots["m_" + n].data_ptr())
+                setattr(s, vf, self.slots["v_" + n].data_ptr())
+        s.user_touched, s.item_touched = self.user_touched.data_ptr(), self.item_touched.data_ptr()
+        self.tables_struct = s
+
+    def workspace(self, B):
+        ws = self._ws.get(B)
+        if ws is None:
+            nbytes = check(self.L.tfr_svd_step_workspace_bytes(B, self.d))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws[B] = ws
+        return ws
+
+    def step_ws(self, B):
+        ws = self.workspace(B)
+        out = StepWs()
+        check(self.L.tfr_svd_step_carve(ws.data_ptr(), ws.numel(), B, self.d, C.byref(out)))
+        return out
+
+    def _dev_i32(self, a):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=torch.int32).contiguous()
+        # the real iterators yield float64 id columns (dataio.py:103); TF's feed casts by value (A.7)
+        return torch.from_numpy(np.ascontiguousarray(a).astype(np.int32, copy=False)).to(self.device)
+
+    def _dev_f32(self, a):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=torch.float32).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a).astype(np.float32, copy=False)).to(self.device)
+
+    # ---- forward only: sess.run([logits, infer]) at svd_train_val.py:121-122 --------------------------------
+    def forward(self, users, items):
+        users, items = self._dev_i32(users), self._dev_i32(items)
+        B = users.numel()
+        logits = torch.empty(B, dtype=torch.float32, device=self.device)
+        infer = torch.empty(B, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.L.tfr_svd_forward(C.byref(self.tables_struct), users.data_ptr(), items.data_ptr(), B,
+                                         self.flags, logits.data_ptr(), infer.data_ptr(), self._stream()))
+        return logits, infer
+
+    # ---- one train step on a device-resident batch: sess.run([train_op, logits, infer]), :70-72 -------------
+    def train_step(self, users, items, rates, logits=None, infer=None, marked=False):
+        users, items, rates = self._dev_i32(users), self._dev_i32(items), self._dev_f32(rates)
+        B = users.numel()
+        if logits is None:
+            logits = torch.empty(B, dtype=torch.float32, device=self.device)
+        if infer is None:
+            infer = torch.empty(B, dtype=torch.float32, device=self.device)
+        ws = self.workspace(B)
+        with torch.cuda.device(self.device):
+            st = self._stream()
+            if not marked:
+                check(self.L.tfr_svd_mark_touched(C.byref(self.tables_struct), self.opt.data_ptr(), users.data_ptr(),
+                                                  items.data_ptr(), B, st))
+            side = self.side_stream.cuda_stream if (self.overlap and not self.sgd) else None
+            check(self.L.tfr_svd_train_step(C.byref(self.tables_struct), self.opt.data_ptr(), users.data_ptr(),
+                                            items.data_ptr(), rates.data_ptr(), B, logits.data_ptr(),
+                                            infer.data_ptr(), self.flags, self.var_mask, ws.data_ptr(), ws.numel(),
+                                            st, side))
+        return logits, infer
+
+    # ---- host-fed step (the feed_dict path): pinned staging, H2D, step, D2H of the fetched predictions -------
+    def train_step_host(self, users, items, rates, fetch=True):
+        B = len(users)
+        stg = self._stage.get(B)
+        if stg is None:
+            stg = dict(
+                h_ids=torch.empty(2 * B, dtype=torch.int32).pin_memory(),
+                h_rates=torch.empty(B, dtype=torch.float32).pin_memory(),
+                d_ids=torch.empty(2 * B, dtype=torch.int32, device=self.device),
+                d_rates=torch.empty(B, dtype=torch.float32, device=self.device),
+                d_out=torch.empty(2 * B, dtype=torch.float32, device=self.device),
+                h_out=torch.empty(2 * B, dtype=torch.float32).pin_memory())
+            self._stage[B] = stg
+        hi = stg["h_ids"].numpy()
+        hi[:B] = users  # value cast float64 -> int32, like TF feeding an int32 placeholder (A.7)
+        hi[B:] = items
+        stg["h_rates"].numpy()[:] = rates
+        stg["d_ids"].copy_(stg["h_ids"], non_blocking=True)
+        stg["d_rates"].copy_(stg["h_rates"], non_blocking=True)
+        self.train_step(stg["d_ids"][:B], stg["d_ids"][B:], stg["d_rates"], logits=stg["d_out"][:B],
+                        infer=stg["d_out"][B:])
+        if not fetch:
+            return None
+        stg["h_out"].copy_(stg["d_out"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        out = stg["h_out"].numpy()
+        return out[:B].copy(), out[B:].copy()
+
+    h2d_bytes = staticmethod(lambda B: 12 * B)
+    d2h_bytes = staticmethod(lambda B: 8 * B)
+
+    # ---- device-resident training data + pre-drawn index stream (dataio.ShuffleIterator on the device) ------
+    def set_train_data(self, col_user, col_item, col_rate):
+        self.data = dict(user=self._dev_i32(col_user), item=self._dev_i32(col_item), rate=self._dev_f32(col_rate))
+
+    def set_index_stream(self, row_index, B):
+        """row_index: the reference's np.random.randint(0, N, B) draws for consecutive steps, concatenated."""
+        if isinstance(row_index, torch.Tensor):
+            ri = row_index.to(device=self.device, dtype=torch.int64).contiguous()
+        else:
+            ri = torch.from_numpy(np.ascontiguousarray(row_index, dtype=np.int64)).to(self.device)
+        assert ri.numel() % B == 0
+        self.row_index = ri
+        self.stream_B = B
+        self.set_batch_cursor(0)
+
+    def set_batch_cursor(self, k):
+        off = OptScalars.batch_cursor.offset
+        self.opt[off:off + 8].copy_(torch.tensor([k], dtype=torch.int64).view(torch.uint8))
+
+    def set_se_ring(self, n):
+        self.se_ring = torch.zeros(n, dtype=torch.float64, device=self.device)
+        check(self.L.tfr_opt_set_se_ring(self.opt.data_ptr(), self.se_ring.data_ptr(), n, self._stream()))
+
+    def _enqueue_stream_step(self, B, bufs, batch_index=-1):
+        st = self._stream()
+        check(self.L.tfr_svd_batch_assemble(C.byref(self.tables_struct), self.opt.data_ptr(),
+                                            self.data["user"].data_ptr(), self.data["item"].data_ptr(),
+                                            self.data["rate"].data_ptr(), self.row_index.data_ptr(), batch_index, B,
+                                            bufs["users"].data_ptr(), bufs["items"].data_ptr(),
+                                            bufs["rates"].data_ptr(), st))
+        ws = self.workspace(B)
+        side = self.side_stream.cuda_stream if (self.overlap and not self.sgd) else None
+        check(self.L.tfr_svd_train_step(C.byref(self.tables_struct), self.opt.data_ptr(), bufs["users"].data_ptr(),
+                                        bufs["items"].data_ptr(), bufs["rates"].data_ptr(), B,
+                                        bufs["logits"].data_ptr(), bufs["infer"].data_ptr(), self.flags,
+                                        self.var_mask, ws.data_ptr(), ws.numel(), st, side))
+
+    def stream_buffers(self, B):
+        key = ("bufs", B)
+        b = self._stage.get(key)
+        if b is None:
+            dev = self.device
+            b = dict(users=torch.empty(B, dtype=torch.int32, device=dev),
+                     items=torch.empty(B, dtype=torch.int32, device=dev),
+                     rates=torch.empty(B, dtype=torch.float32, device=dev),
+                     logits=torch.empty(B, dtype=torch.float32, device=dev),
+                     infer=torch.empty(B, dtype=torch.float32, device=dev))
+            self._stage[key] = b
+        return b
+
+    def run_stream_steps(self, n_steps, use_graph=True):
+        """Runs n_steps train steps on batches drawn by the device-resident index stream, starting at the
+        current batch_cursor.  With use_graph the whole step (assemble -> ... -> finish) is ONE captured CUDA
+        graph replayed n_steps times: no per-step host work besides the graph launch."""
+        B = self.stream_B
+        bufs = self.stream_buffers(B)
+        with torch.cuda.device(self.device):
+            if not use_graph:
+                for _ in range(n_steps):
+                    self._enqueue_stream_step(B, bufs)
+                return bufs
+            g = self._graphs.get(B)
+            if g is None:
+                self.workspace(B)
+                cap = torch.cuda.Stream(device=self.device)
+                cap.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(cap):
+                    check(self.L.tfr_graph_begin_capture(cap.cuda_stream))
+                    try:
+                        self._enqueue_stream_step(B, bufs)
+                    finally:
+                        exe = C.c_void_p()
+                        rc = self.L.tfr_graph_end_capture(cap.cuda_stream, C.byref(exe))
+                    check(rc)
+                torch.cuda.current_stream(self.device).wait_stream(cap)
+                g = exe
+                self._graphs[B] = g
+            st = self._stream()
+            for _ in range(n_steps):
+                check(self.L.tfr_graph_launch(g, st))
+        return bufs
+
+    # ---- state access ------------------------------------------------------------------------------------
+    def opt_scalars(self):
+        raw = self.opt.cpu().numpy().tobytes()
+        return OptScalars.from_buffer_copy(raw)
+
+    @property
+    def global_step(self):
+        return int(self.opt_scalars().global_step)
+
+    def get_tables(self):
+        out = {n: self.t[n].detach().cpu().numpy().copy() for n in TABLE_NAMES}
+        for k, v in self.slots.items():
+            out[k] = v.detach().cpu().numpy().copy()
+        return out
+
+    def variable(self, name):
+        return self.t[name]
+
+    # ---- checkpoint: tf.train.Saver().save / restore (svd_train_val.py:54,197-198; adaptive_test.py:40) -----
+    def save(self, path):
+        s = self.opt_scalars()
+        arrays = self.get_tables()
+        arrays["__opt__"] = np.array([s.beta1_power, s.beta2_power], np.float32)
+        arrays["__step__"] = np.array([s.global_step], np.int64)
+        arrays["__shape__"] = np.array([self.U, self.I, self.d, self.flags], np.int64)
+        with open(path, "wb") as f:
+            np.savez(f, **arrays)
+
+    def restore(self, path):
+        z = np.load(path)
+        U, I, d, _ = (int(x) for x in z["__shape__"])
+        if (U, I, d) != (self.U, self.I, self.d):
+            raise TfrError("checkpoint shape %s does not match engine %s" % ((U, I, d), (self.U, self.I, self.d)))
+        for n in TABLE_NAMES:
+            self.t[n].copy_(torch.from_numpy(z[n].reshape(self.t[n].shape)))
+            if not self.sgd and ("m_" + n) in z.files:
+                self.slots["m_" + n].copy_(torch.from_numpy(z["m_" + n].reshape(self.t[n].shape)))
+                self.slots["v_" + n].copy_(torch.from_numpy(z["v_" + n].reshape(self.t[n].shape)))
+        for field, val, dt in (("beta1_power", z["__opt__"][0], torch.float32), ("beta2_power", z["__opt__"][1], torch.float32),
+                               ("global_step", z["__step__"][0], torch.int64)):
+            off = getattr(OptScalars, field).offset
+            t = torch.tensor([val], dtype=dt).view(torch.uint8)
+            self.opt[off:off + t.numel()].copy_(t)
