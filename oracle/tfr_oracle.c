@@ -57,15 +57,19 @@ typedef struct {
 
 /* ---- forward: ops.py:13-14,37-38 (gathers), :44-47 (dot + three bias adds), :76-78 (head) -- */
 /* logits[b] = ((sum_k u[b,k]*v'[b,k] + mu) + b_u) + b_i ; v' = |v| when ORC_ABS_ITEM.      */
-/* The reduce_sum order inside TF/Eigen is unspecified; this restatement adds k = 0..d-1.   */
+/* tf.multiply rounds every product to fp32; the ORDER of tf.reduce_sum inside TF/Eigen (a    */
+/* SIMD packet tree) is unspecified, so the restatement returns the order-independent value:   */
+/* the fp32 products summed exactly (double accumulator) and rounded once.  Any fp32 summation */
+/* order, TF's included, lies within a few ulp of it.                                          */
 static inline float orc_logit(const orc_svd_state *s, int32_t u, int32_t i) {
   const int d = s->dim;
   const float *pu = s->user_feat + (size_t)u * d, *qi = s->item_feat + (size_t)i * d;
-  float acc = 0.0f;
+  double dacc = 0.0;
   if (s->flags & ORC_ABS_ITEM)
-    for (int k = 0; k < d; ++k) acc = acc + pu[k] * fabsf(qi[k]);
+    for (int k = 0; k < d; ++k) { float pr = pu[k] * fabsf(qi[k]); dacc += (double)pr; }
   else
-    for (int k = 0; k < d; ++k) acc = acc + pu[k] * qi[k];
+    for (int k = 0; k < d; ++k) { float pr = pu[k] * qi[k]; dacc += (double)pr; }
+  float acc = (float)dacc;
   acc = acc + s->mu[0];         /* ops.py:45 */
   acc = acc + s->user_bias[u];  /* ops.py:46 */
   acc = acc + s->item_bias[i];  /* ops.py:47 */
@@ -179,10 +183,10 @@ ORC_API void orc_svd_grads(const orc_svd_state *s, const int32_t *users, const i
     }
   }
   /* d cost / d bias_global: reduce_sum of the upstream gradient over the batch (A.3).       */
-  /* Eigen's reduction order is unspecified; restated as a sequential fp32 sum.              */
-  float acc = 0.0f;
-  for (int64_t b = 0; b < B; ++b) acc = acc + err_out[b];
-  *g_mu = acc;
+  /* Eigen's reduction order is unspecified: order-independent restatement as for the dot.   */
+  double acc = 0.0;
+  for (int64_t b = 0; b < B; ++b) acc += (double)err_out[b];
+  *g_mu = (float)acc;
 }
 
 /* ---- dedup: TF optimizer.py::_deduplicate_indexed_slices (A.3) --------------------------- */
