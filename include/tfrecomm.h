@@ -75,11 +75,18 @@ typedef struct {
                             driver's trailing-window train RMSE (svd_train_val.py:59,104,108) needs one
                             read per epoch instead of one per step                            */
   int64_t se_ring_len;
+  uint64_t* timeline;    /* optional debug buffer [2][TFR_TL_SLOTS] of %globaltimer ns: earliest block entry and
+                            latest warp exit of every kernel of the step (there is no nsys on the box); null = off */
 } tfr_opt_scalars;
+#define TFR_TL_SLOTS 16
+enum { TFR_TL_ASSEMBLE = 0, TFR_TL_FWD = 1, TFR_TL_SORT = 2, TFR_TL_TILES = 3, TFR_TL_FIXUP = 4, TFR_TL_STREAM_UF = 5,
+       TFR_TL_STREAM_IF = 6, TFR_TL_STREAM_UB = 7, TFR_TL_STREAM_IB = 8, TFR_TL_TOUCHED_U = 9, TFR_TL_TOUCHED_I = 10,
+       TFR_TL_FINISH = 11 };
 
 int tfr_opt_init(tfr_opt_scalars* opt_dev, float lr, float reg, float beta1, float beta2, float eps,
                  int32_t flags, int32_t var_mask, void* stream);
 int tfr_opt_set_se_ring(tfr_opt_scalars* opt_dev, double* se_ring, int64_t se_ring_len, void* stream);
+int tfr_opt_set_timeline(tfr_opt_scalars* opt_dev, uint64_t* timeline, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * The five variables of ops.py:8-12,29-32 and their Adam slots (TF: adam.py zeros_like slots).
@@ -123,6 +130,11 @@ int64_t tfr_dedup_workspace_bytes(int64_t n);
 int tfr_dedup_sort_pairs(const int32_t* ids_a, int64_t max_id_a, int32_t* sorted_ids_a, int32_t* sorted_pos_a,
                          const int32_t* ids_b, int64_t max_id_b, int32_t* sorted_ids_b, int32_t* sorted_pos_b,
                          int64_t n, void* workspace, int64_t workspace_bytes, void* stream);
+/* same, with the step's scalars so that the launch shows up in opt->timeline */
+int tfr_dedup_sort_pairs_tl(const int32_t* ids_a, int64_t max_id_a, int32_t* sorted_ids_a, int32_t* sorted_pos_a,
+                            const int32_t* ids_b, int64_t max_id_b, int32_t* sorted_ids_b, int32_t* sorted_pos_b,
+                            int64_t n, void* workspace, int64_t workspace_bytes, const tfr_opt_scalars* opt,
+                            void* stream);
 /* tf.unique's own outputs from the sorted pairs (parity/debug API, not on the hot step):
  * uniq[0..n_uniq) in order of FIRST OCCURRENCE, idx[b] = position of ids[b] in uniq, *n_uniq_dev.
  * scratch: n int32. */
@@ -138,12 +150,15 @@ int tfr_unique_first_occurrence(const int32_t* sorted_ids, const int32_t* sorted
  * beta powers and batch_cursor; leaves the touched maps zeroed. */
 int64_t tfr_svd_step_workspace_bytes(int64_t B, int32_t dim);
 /* flags / var_mask must equal what tfr_opt_init was given (the host copy selects the launches, the
- * device copy drives the kernels).  side_stream (optional, may be null) lets the streaming pass over
- * the rows outside the slice overlap the forward/sort/segment-sum chain. */
+ * device copy drives the kernels).  side_streams (optional; n_side = 0..3 distinct streams) let independent
+ * parts of the step run concurrently: [0] BULK, low priority: the streaming pass over the rows outside the
+ * slice; [1] CHAIN, high priority: forward -> segment sums -> slice update; [2] SORT, high priority: the id
+ * sort next to the forward.  Fork/join is by events, so the whole step is still capturable as one graph from
+ * `stream`. */
 int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
                        const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
                        int32_t flags, int32_t var_mask, void* workspace, int64_t workspace_bytes, void* stream,
-                       void* side_stream);
+                       void* const* side_streams, int32_t n_side);
 
 /* Pieces of the step, exported for parity tests and for callers that schedule them themselves. */
 typedef struct { /* carved out of the step workspace by tfr_svd_step_carve */
@@ -155,6 +170,7 @@ typedef struct { /* carved out of the step workspace by tfr_svd_step_carve */
   float *gsum_ub, *gsum_ib; /* [B]                                                  */
   float *cont_uf, *cont_if, *tail_uf, *tail_if; /* [n_tiles,dim] cross-tile partial sums */
   float *cont_ub, *cont_ib, *tail_ub, *tail_ib; /* [n_tiles]                          */
+  uint8_t *kind_u, *kind_i;                     /* [n_tiles] tile classes for the fix-up */
   void* sort_ws; int64_t sort_ws_bytes;
   int32_t tile, n_tiles;
 } tfr_svd_step_ws;
@@ -171,13 +187,31 @@ int tfr_svd_mark_touched(const tfr_svd_tables* t, tfr_opt_scalars* opt, const in
  * ids in the sorted pairs, gsum[head k] = sum in batch order of (e_b*partner_row + reg*own_row). */
 int tfr_svd_segment_grads(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
                           const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, void* stream);
-/* TF sparse Adam over a whole table, rows NOT marked touched (pure decay + step), one streaming pass. */
+/* TF sparse Adam (A.4), split in two kernels that together read and write every parameter once per step:
+ * (1) the streaming pass over the rows NOT marked touched (pure decay + step), all tables in ONE launch;
+ * (2) the slice rows: var/m/v[sorted_ids[k]] for every run head k with the summed gradient gsum[k], the
+ *     feature rows and the bias entries of both tables in ONE launch.  SGD (ops.py:145): var -= gsum. */
+typedef struct {
+  float *var, *m, *v;     /* [rows*width], 16-byte aligned */
+  int64_t rows;
+  int32_t width;
+  const uint8_t* touched; /* [rows] */
+} tfr_adam_table;
+int tfr_adam_stream_multi(const tfr_adam_table* tables, int32_t n_tables /* 1..4 */, const tfr_opt_scalars* opt,
+                          int32_t tl_slot, void* stream);
 int tfr_adam_stream_untouched(float* var, float* m, float* v, int64_t rows, int32_t width,
                               const uint8_t* touched, const tfr_opt_scalars* opt, void* stream);
-/* ... and the rows of this step's slice: var/m/v[sorted_ids[k]] for every run head k, gradient gsum[k]. */
+typedef struct {
+  float *var, *m, *v;        /* feature table [rows, width]; null = not in var_list          */
+  float *bvar, *bm, *bv;     /* bias table [rows] sharing the row ids; null = not in var_list  */
+  const int32_t* sorted_ids; /* [n]                                                           */
+  const float* gsum;         /* [n, width] valid at run heads                                  */
+  const float* bgsum;        /* [n]                                                            */
+} tfr_slice_update;
+int tfr_adam_slice_multi(const tfr_slice_update* sides, int32_t n_sides /* 1..2 */, int32_t width, int64_t n,
+                         const tfr_opt_scalars* opt, int32_t sgd, int32_t tl_slot, void* stream);
 int tfr_adam_touched(float* var, float* m, float* v, int32_t width, const int32_t* sorted_ids, int64_t n,
                      const float* gsum, const tfr_opt_scalars* opt, void* stream);
-/* SGD: var[sorted_ids[k]] -= gsum[k] for run heads (gsum already holds sum of lr*g, ops.py:145). */
 int tfr_sgd_apply(float* var, int32_t width, const int32_t* sorted_ids, int64_t n, const float* gsum,
                   void* stream);
 /* end of step: dense Adam/SGD on bias_global from the err partials (A.5), advance beta powers and

@@ -32,7 +32,7 @@ class OptScalars(C.Structure):
                 ("one_minus_beta1", f32), ("one_minus_beta2", f32),
                 ("flags", i32), ("var_mask", i32),
                 ("global_step", i64), ("batch_cursor", i64), ("se_sum", C.c_double),
-                ("g_mu", f32), ("pad_", f32), ("se_ring", vp), ("se_ring_len", i64)]
+                ("g_mu", f32), ("pad_", f32), ("se_ring", vp), ("se_ring_len", i64), ("timeline", vp)]
 
 
 class SvdTables(C.Structure):
@@ -51,7 +51,19 @@ class StepWs(C.Structure):
                 ("gsum_uf", vp), ("gsum_if", vp), ("gsum_ub", vp), ("gsum_ib", vp),
                 ("cont_uf", vp), ("cont_if", vp), ("tail_uf", vp), ("tail_if", vp),
                 ("cont_ub", vp), ("cont_ib", vp), ("tail_ub", vp), ("tail_ib", vp),
+                ("kind_u", vp), ("kind_i", vp),
                 ("sort_ws", vp), ("sort_ws_bytes", i64), ("tile", i32), ("n_tiles", i32)]
+
+
+class AdamTable(C.Structure):
+    """Mirror of tfr_adam_table."""
+    _fields_ = [("var", vp), ("m", vp), ("v", vp), ("rows", i64), ("width", i32), ("touched", vp)]
+
+
+class SliceUpdate(C.Structure):
+    """Mirror of tfr_slice_update."""
+    _fields_ = [("var", vp), ("m", vp), ("v", vp), ("bvar", vp), ("bm", vp), ("bv", vp), ("sorted_ids", vp),
+                ("gsum", vp), ("bgsum", vp)]
 
 
 # name -> (restype, argtypes).  Every symbol include/tfrecomm.h declares is listed here; the CPU test
@@ -62,19 +74,24 @@ _PROTOS = {
     "tfr_device_sm_count": (C.c_int, []),
     "tfr_opt_init": (C.c_int, [vp, f32, f32, f32, f32, f32, i32, i32, vp]),
     "tfr_opt_set_se_ring": (C.c_int, [vp, vp, i64, vp]),
+    "tfr_opt_set_timeline": (C.c_int, [vp, vp, vp]),
     "tfr_svd_forward": (C.c_int, [C.POINTER(SvdTables), vp, vp, i64, i32, vp, vp, vp]),
     "tfr_svd_batch_assemble": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp]),
     "tfr_dedup_workspace_bytes": (i64, [i64]),
     "tfr_dedup_sort_pairs": (C.c_int, [vp, i64, vp, vp, vp, i64, vp, vp, i64, vp, i64, vp]),
+    "tfr_dedup_sort_pairs_tl": (C.c_int, [vp, i64, vp, vp, vp, i64, vp, vp, i64, vp, i64, vp, vp]),
     "tfr_unique_first_occurrence": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, vp]),
     "tfr_svd_step_workspace_bytes": (i64, [i64, i32]),
-    "tfr_svd_train_step": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, i64, vp, vp, i32, i32, vp, i64, vp, vp]),
+    "tfr_svd_train_step": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, i64, vp, vp, i32, i32, vp, i64, vp,
+                                     C.POINTER(vp), i32]),
     "tfr_svd_step_carve": (C.c_int, [vp, i64, i64, i32, C.POINTER(StepWs)]),
     "tfr_svd_fwd_err": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, i64, vp, vp, C.POINTER(StepWs), vp]),
     "tfr_svd_mark_touched": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, vp]),
     "tfr_svd_segment_grads": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, C.POINTER(StepWs), vp]),
     "tfr_adam_stream_untouched": (C.c_int, [vp, vp, vp, i64, i32, vp, vp, vp]),
+    "tfr_adam_stream_multi": (C.c_int, [C.POINTER(AdamTable), i32, vp, i32, vp]),
     "tfr_adam_touched": (C.c_int, [vp, vp, vp, i32, vp, i64, vp, vp, vp]),
+    "tfr_adam_slice_multi": (C.c_int, [C.POINTER(SliceUpdate), i32, i32, i64, vp, i32, i32, vp]),
     "tfr_sgd_apply": (C.c_int, [vp, i32, vp, i64, vp, vp]),
     "tfr_svd_finish_step": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, C.POINTER(StepWs), i32, vp]),
     "tfr_fm_forward": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]),

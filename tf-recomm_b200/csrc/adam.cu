@@ -9,6 +9,9 @@
 // operation keeps TF's rounding order (separate mul/add, correctly rounded sqrt and divide).
 // Also: dense ApplyAdam for bias_global (TF: training_ops.cc, A.5), scatter_sub SGD (ops.py:145) and
 // the end-of-step bookkeeping (TF: adam.py::_finish).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace tfr {
@@ -33,108 +36,201 @@ __device__ __forceinline__ void adam_grad(float& var, float& m, float& v, float 
   var = sub_rn(var, div_rn(mul_rn(k.lr_t, m), add_rn(sqrt_rn(v), k.eps)));
 }
 
-// ---- streaming pass, 128-bit path: width % 4 == 0, so a float4 never straddles two rows --------------
-// Persistent grid (a multiple of the SM count); each thread owns UNROLL float4 triples per trip so
-// that 6*UNROLL 16-byte requests are in flight per thread.  Loads bypass L1 and are evict-first in L2:
-// every byte is touched once per step and must not push the batch's gathered rows out of L2.
-template <typename IdxT, int UNROLL>
-__global__ void __launch_bounds__(512) adam_stream_vec4_kernel(float4* __restrict__ var, float4* __restrict__ m,
-                                                               float4* __restrict__ v, IdxT n4, uint32_t row4,
-                                                               const uint8_t* __restrict__ touched,
-                                                               const tfr_opt_scalars* __restrict__ opt) {
-  const AdamK k = load_k(opt);
-  const IdxT stride = (IdxT)gridDim.x * blockDim.x;
-  for (IdxT q0 = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; q0 < n4; q0 += stride * UNROLL) {
-    bool live[UNROLL];
+// ---- streaming pass over the rows OUTSIDE the step's slice, all tables in ONE launch -------------------
+// One launch, not one per table: a second kernel queued behind the first on the same stream would sit at the
+// head of its hardware queue until the first finishes and block every other stream that shares the queue
+// (measured: forward and sort started 60 us late).  The concatenated tables are cut into units of 4 floats;
+// a thread owns UNROLL units per trip (6*UNROLL 16-byte requests in flight).  For width % 4 == 0 a unit lies
+// in one row (one touched-map byte); otherwise (dim 15, bias tables) each float has its own row and a mixed
+// unit falls back to scalar accesses.  Loads/stores are .cs (evict-first): every byte is touched once per
+// step and must not push the batch's gathered rows out of L2.  The touched-map lookups of trip i+1 are
+// issued before the data loads of trip i, so the dependent byte load never sits in front of them.
+struct StreamTab {
+  float *var, *m, *v;
+  const uint8_t* touched;
+  uint32_t n;        // floats
+  uint32_t width;    // floats per row
+  uint32_t unit_end; // exclusive end of this table's units in the concatenated unit space
+};
+struct StreamArgs {
+  StreamTab t[4];
+  int n_tabs;
+  uint32_t total_units;
+};
+
+__device__ __forceinline__ uint32_t unit_mask(const StreamArgs& a, uint32_t q, int& tab, uint32_t& lu) {
+  // -> 4-bit mask of the unit's floats that are live (in range and in a row outside the slice)
+  if (q >= a.total_units) { tab = 0; lu = 0; return 0u; }
+  tab = 0;
+  uint32_t begin = 0;
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const IdxT q = q0 + (IdxT)u * stride;
-      live[u] = q < n4 && touched[q / row4] == 0;
-    }
-    float4 a[UNROLL], b[UNROLL], c[UNROLL];
+  for (int i = 0; i < 3; ++i)
+    if (tab == i && i + 1 < a.n_tabs && q >= a.t[i].unit_end) { begin = a.t[i].unit_end; tab = i + 1; }
+  lu = q - begin;
+  const StreamTab& t = a.t[tab];
+  const uint32_t e0 = lu * 4u;
+  if ((t.width & 3u) == 0u) return t.touched[e0 / t.width] ? 0u : 0xFu;
+  uint32_t mask = 0;
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const IdxT q = q0 + (IdxT)u * stride;
-      if (live[u]) { a[u] = ld_stream_f4(var + q); b[u] = ld_stream_f4(m + q); c[u] = ld_stream_f4(v + q); }
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      if (!live[u]) continue;
-      const IdxT q = q0 + (IdxT)u * stride;
-      adam_decay(a[u].x, b[u].x, c[u].x, k);
-      adam_decay(a[u].y, b[u].y, c[u].y, k);
-      adam_decay(a[u].z, b[u].z, c[u].z, k);
-      adam_decay(a[u].w, b[u].w, c[u].w, k);
-      st_stream_f4(var + q, a[u]);
-      st_stream_f4(m + q, b[u]);
-      st_stream_f4(v + q, c[u]);
-    }
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t e = e0 + j;
+    if (e < t.n && t.touched[e / t.width] == 0) mask |= 1u << j;
   }
+  return mask;
 }
 
-// scalar path: any width (dim = 15 rows are 60 B; bias tables have width 1)
-template <typename IdxT>
-__global__ void __launch_bounds__(512) adam_stream_scalar_kernel(float* __restrict__ var, float* __restrict__ m,
-                                                                 float* __restrict__ v, IdxT n, uint32_t width,
-                                                                 const uint8_t* __restrict__ touched,
-                                                                 const tfr_opt_scalars* __restrict__ opt) {
+template <int UNROLL>
+__global__ void __launch_bounds__(512) adam_stream_multi_kernel(const __grid_constant__ StreamArgs a,
+                                                                const tfr_opt_scalars* __restrict__ opt, int tl_slot) {
+  TlScope tl_scope(opt, tl_slot);
   const AdamK k = load_k(opt);
-  const IdxT stride = (IdxT)gridDim.x * blockDim.x;
-  for (IdxT j = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-    if (touched[j / width]) continue;
-    float a = ld_stream_f1(var + j), b = ld_stream_f1(m + j), c = ld_stream_f1(v + j);
-    adam_decay(a, b, c, k);
-    st_stream_f1(var + j, a);
-    st_stream_f1(m + j, b);
-    st_stream_f1(v + j, c);
-  }
-}
-
-// ---- slice rows: one lane group per sorted entry; only run heads (first entry of a run) act --------
-template <int VEC, int L>
-__global__ void __launch_bounds__(256) adam_touched_kernel(float* __restrict__ var, float* __restrict__ m,
-                                                           float* __restrict__ v, int width,
-                                                           const int32_t* __restrict__ sid, int64_t n,
-                                                           const float* __restrict__ gsum,
-                                                           const tfr_opt_scalars* __restrict__ opt, int sgd) {
-  const int lane = threadIdx.x & (L - 1);
-  const int64_t kk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
-  if (kk >= n) return;
-  const int32_t id = sid[kk];
-  if (kk > 0 && sid[kk - 1] == id) return;
-  const size_t base = (size_t)id * width;
-  const float* g = gsum + (size_t)kk * width;
-  if (sgd) {  // ops.py:145: scatter_sub; gsum already holds the in-order sum of lr*g
-    for (int c = lane * VEC; c < width; c += L * VEC) {
-      if constexpr (VEC == 4) {
-        float4 a = *reinterpret_cast<float4*>(var + base + c);
-        const float4 gg = *reinterpret_cast<const float4*>(g + c);
-        a.x = sub_rn(a.x, gg.x); a.y = sub_rn(a.y, gg.y); a.z = sub_rn(a.z, gg.z); a.w = sub_rn(a.w, gg.w);
-        *reinterpret_cast<float4*>(var + base + c) = a;
-      } else {
-        var[base + c] = sub_rn(var[base + c], g[c]);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t mask[UNROLL], lu[UNROLL];
+  int tab[UNROLL];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) mask[u] = unit_mask(a, q0 + u * stride, tab[u], lu[u]);
+  for (; q0 < a.total_units; q0 += stride * UNROLL) {
+    float4 x[UNROLL], y[UNROLL], z[UNROLL];
+    uint32_t cm[UNROLL], clu[UNROLL];
+    int ct[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      cm[u] = mask[u]; clu[u] = lu[u]; ct[u] = tab[u];
+      if (cm[u] == 0xFu) {
+        const StreamTab& t = a.t[ct[u]];
+        x[u] = ld_stream_f4(reinterpret_cast<const float4*>(t.var) + clu[u]);
+        y[u] = ld_stream_f4(reinterpret_cast<const float4*>(t.m) + clu[u]);
+        z[u] = ld_stream_f4(reinterpret_cast<const float4*>(t.v) + clu[u]);
       }
     }
-    return;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) mask[u] = unit_mask(a, q0 + (UNROLL + u) * stride, tab[u], lu[u]);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const StreamTab& t = a.t[ct[u]];
+      if (cm[u] == 0xFu) {
+        adam_decay(x[u].x, y[u].x, z[u].x, k);
+        adam_decay(x[u].y, y[u].y, z[u].y, k);
+        adam_decay(x[u].z, y[u].z, z[u].z, k);
+        adam_decay(x[u].w, y[u].w, z[u].w, k);
+        st_stream_f4(reinterpret_cast<float4*>(t.var) + clu[u], x[u]);
+        st_stream_f4(reinterpret_cast<float4*>(t.m) + clu[u], y[u]);
+        st_stream_f4(reinterpret_cast<float4*>(t.v) + clu[u], z[u]);
+      } else if (cm[u]) {  // mixed unit: some floats belong to slice rows (or lie past the end)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (cm[u] >> j & 1u) {
+            const uint32_t e = clu[u] * 4u + j;
+            float p = ld_stream_f1(t.var + e), q = ld_stream_f1(t.m + e), r = ld_stream_f1(t.v + e);
+            adam_decay(p, q, r, k);
+            st_stream_f1(t.var + e, p);
+            st_stream_f1(t.m + e, q);
+            st_stream_f1(t.v + e, r);
+          }
+        }
+      }
+    }
   }
-  const AdamK k = load_k(opt);
-  for (int c = lane * VEC; c < width; c += L * VEC) {
-    if constexpr (VEC == 4) {
-      float4 a = *reinterpret_cast<float4*>(var + base + c);
-      float4 b = *reinterpret_cast<float4*>(m + base + c);
-      float4 d = *reinterpret_cast<float4*>(v + base + c);
-      const float4 gg = *reinterpret_cast<const float4*>(g + c);
-      adam_grad(a.x, b.x, d.x, gg.x, k);
-      adam_grad(a.y, b.y, d.y, gg.y, k);
-      adam_grad(a.z, b.z, d.z, gg.z, k);
-      adam_grad(a.w, b.w, d.w, gg.w, k);
-      *reinterpret_cast<float4*>(var + base + c) = a;
-      *reinterpret_cast<float4*>(m + base + c) = b;
-      *reinterpret_cast<float4*>(v + base + c) = d;
-    } else {
-      float a = var[base + c], b = m[base + c], d = v[base + c];
-      adam_grad(a, b, d, g[c], k);
-      var[base + c] = a; m[base + c] = b; v[base + c] = d;
+}
+
+// ---- slice rows: one lane group per ENT consecutive sorted entries; run heads act --------------------------
+// Both tables' slices (users, items) in ONE launch (blockIdx.y).  A group first decides which of its ENT
+// entries are run heads, then issues the loads of all of them together (up to 4*ENT 16-byte requests per
+// lane in flight) before any arithmetic: the kernel is a chain of dependent latencies otherwise.
+struct SliceSide {
+  float *var, *m, *v;        // feature table (null = not trained)
+  float *bvar, *bm, *bv;     // bias table sharing the row ids (null = not trained)
+  const int32_t* sid;        // sorted ids
+  const float* gsum;         // [n, width] summed gradient at run heads
+  const float* bgsum;        // [n]
+};
+constexpr int SLICE_ENT = 4;
+
+template <int VEC, int L>
+__global__ void __launch_bounds__(256) adam_slice_kernel(SliceSide s0, SliceSide s1, int width, int64_t n,
+                                                         const tfr_opt_scalars* __restrict__ opt, int sgd, int tl_slot) {
+  TlScope tl_scope(opt, tl_slot);
+  const SliceSide s = blockIdx.y ? s1 : s0;
+  const int lane = threadIdx.x & (L - 1);
+  const int64_t kk0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L) * SLICE_ENT;
+  if (kk0 >= n) return;
+  int32_t id[SLICE_ENT];
+  bool head[SLICE_ENT];
+  int32_t prev = kk0 > 0 ? s.sid[kk0 - 1] : -1;
+#pragma unroll
+  for (int e = 0; e < SLICE_ENT; ++e) {
+    const int64_t kk = kk0 + e;
+    id[e] = kk < n ? s.sid[kk] : -1;
+    head[e] = kk < n && id[e] != prev;
+    prev = id[e];
+  }
+  AdamK k;
+  if (!sgd) k = load_k(opt);
+  if (s.bvar && lane == 0) {  // the rows' bias entries (a width-1 table sharing the row ids)
+    float a[SLICE_ENT], b[SLICE_ENT], d[SLICE_ENT], g[SLICE_ENT];
+#pragma unroll
+    for (int e = 0; e < SLICE_ENT; ++e)
+      if (head[e]) {
+        a[e] = s.bvar[id[e]];
+        g[e] = s.bgsum[kk0 + e];
+        if (!sgd) { b[e] = s.bm[id[e]]; d[e] = s.bv[id[e]]; }
+      }
+#pragma unroll
+    for (int e = 0; e < SLICE_ENT; ++e)
+      if (head[e]) {
+        if (sgd) {
+          s.bvar[id[e]] = sub_rn(a[e], g[e]);
+        } else {
+          adam_grad(a[e], b[e], d[e], g[e], k);
+          s.bvar[id[e]] = a[e]; s.bm[id[e]] = b[e]; s.bv[id[e]] = d[e];
+        }
+      }
+  }
+  if (!s.var) return;
+  const int n_units = width / VEC;
+  for (int unit = lane; unit < n_units; unit += L) {
+    float a[SLICE_ENT][VEC], b[SLICE_ENT][VEC], d[SLICE_ENT][VEC], g[SLICE_ENT][VEC];
+#pragma unroll
+    for (int e = 0; e < SLICE_ENT; ++e) {
+      if (!head[e]) continue;
+      const size_t off = (size_t)id[e] * width + (size_t)unit * VEC;
+      const size_t goff = (size_t)(kk0 + e) * width + (size_t)unit * VEC;
+      if constexpr (VEC == 4) {
+        const float4 av = *reinterpret_cast<const float4*>(s.var + off);
+        const float4 gv = *reinterpret_cast<const float4*>(s.gsum + goff);
+        a[e][0] = av.x; a[e][1] = av.y; a[e][2] = av.z; a[e][3] = av.w;
+        g[e][0] = gv.x; g[e][1] = gv.y; g[e][2] = gv.z; g[e][3] = gv.w;
+        if (!sgd) {
+          const float4 bv4 = *reinterpret_cast<const float4*>(s.m + off);
+          const float4 dv4 = *reinterpret_cast<const float4*>(s.v + off);
+          b[e][0] = bv4.x; b[e][1] = bv4.y; b[e][2] = bv4.z; b[e][3] = bv4.w;
+          d[e][0] = dv4.x; d[e][1] = dv4.y; d[e][2] = dv4.z; d[e][3] = dv4.w;
+        }
+      } else {
+        a[e][0] = s.var[off]; g[e][0] = s.gsum[goff];
+        if (!sgd) { b[e][0] = s.m[off]; d[e][0] = s.v[off]; }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < SLICE_ENT; ++e) {
+      if (!head[e]) continue;
+      const size_t off = (size_t)id[e] * width + (size_t)unit * VEC;
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        if (sgd) a[e][c] = sub_rn(a[e][c], g[e][c]);  // ops.py:145 scatter_sub; gsum holds the sum of lr*g
+        else adam_grad(a[e][c], b[e][c], d[e][c], g[e][c], k);
+      }
+      if constexpr (VEC == 4) {
+        *reinterpret_cast<float4*>(s.var + off) = make_float4(a[e][0], a[e][1], a[e][2], a[e][3]);
+        if (!sgd) {
+          *reinterpret_cast<float4*>(s.m + off) = make_float4(b[e][0], b[e][1], b[e][2], b[e][3]);
+          *reinterpret_cast<float4*>(s.v + off) = make_float4(d[e][0], d[e][1], d[e][2], d[e][3]);
+        }
+      } else {
+        s.var[off] = a[e][0];
+        if (!sgd) { s.m[off] = b[e][0]; s.v[off] = d[e][0]; }
+      }
     }
   }
 }
@@ -147,6 +243,7 @@ __global__ void __launch_bounds__(256) finish_step_kernel(tfr_svd_tables t, tfr_
                                                           const int32_t* __restrict__ items, int64_t B,
                                                           const float* __restrict__ partials,
                                                           const double* __restrict__ se_partials, int n_partials) {
+  TlScope tl_scope(opt, TFR_TL_FINISH);
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) {
     t.user_touched[users[b]] = 0;
@@ -203,7 +300,7 @@ __global__ void opt_init_kernel(tfr_opt_scalars* opt, float lr, float reg, float
   opt->flags = flags; opt->var_mask = var_mask;
   opt->global_step = 0; opt->batch_cursor = 0;
   opt->se_sum = 0.0; opt->g_mu = 0.0f; opt->pad_ = 0.0f;
-  opt->se_ring = nullptr; opt->se_ring_len = 0;
+  opt->se_ring = nullptr; opt->se_ring_len = 0; opt->timeline = nullptr;
 }
 
 }  // namespace tfr
@@ -218,80 +315,115 @@ extern "C" int tfr_opt_init(tfr_opt_scalars* opt_dev, float lr, float reg, float
   return TFR_OK;
 }
 
-extern "C" int tfr_adam_stream_untouched(float* var, float* m, float* v, int64_t rows, int32_t width,
-                                         const uint8_t* touched, const tfr_opt_scalars* opt, void* stream) {
-  TFR_CHECK_ARG(rows >= 0 && width > 0);
-  if (rows == 0) return TFR_OK;
-  TFR_CHECK_ARG(var && m && v && touched && opt);
+extern "C" int tfr_adam_stream_multi(const tfr_adam_table* tables, int32_t n_tables, const tfr_opt_scalars* opt,
+                                     int32_t tl_slot, void* stream) {
+  TFR_CHECK_ARG(tables && n_tables >= 1 && n_tables <= 4 && opt && tl_slot >= 0 && tl_slot < TFR_TL_SLOTS);
+  StreamArgs a;
+  memset(&a, 0, sizeof(a));
+  uint64_t units = 0;
+  int nt = 0;
+  for (int i = 0; i < n_tables; ++i) {
+    const tfr_adam_table& t = tables[i];
+    TFR_CHECK_ARG(t.rows >= 0 && t.width > 0);
+    if (t.rows == 0) continue;
+    TFR_CHECK_ARG(t.var && t.m && t.v && t.touched);
+    TFR_CHECK_ARG(((uintptr_t)t.var % 16 == 0) && ((uintptr_t)t.m % 16 == 0) && ((uintptr_t)t.v % 16 == 0));
+    const uint64_t n = (uint64_t)t.rows * (uint64_t)t.width;
+    units += (n + 3) / 4;
+    if (n >= ((uint64_t)1 << 32) || units >= ((uint64_t)1 << 32)) {
+      set_error("adam stream pass: %llu floats exceed the 32-bit unit index (shard the table)", (unsigned long long)n);
+      return TFR_ERR_INVALID;
+    }
+    a.t[nt].var = t.var; a.t[nt].m = t.m; a.t[nt].v = t.v; a.t[nt].touched = t.touched;
+    a.t[nt].n = (uint32_t)n; a.t[nt].width = (uint32_t)t.width; a.t[nt].unit_end = (uint32_t)units;
+    ++nt;
+  }
+  if (nt == 0) return TFR_OK;
+  a.n_tabs = nt;
+  a.total_units = (uint32_t)units;
+  // Grid: NOT persistent by default (TFR_STREAM_CTAS_PER_SM=0): one trip per CTA, thousands of short CTAs, so
+  // that the higher-priority kernels of the step's dependent chain get SM slots at CTA granularity while this
+  // pass soaks up whatever bandwidth is left.  A positive value caps the grid at that many CTAs per SM.
+  static int cfg_ctas = -1, cfg_unroll = 0;
+  if (cfg_ctas < 0) {
+    const char* e1 = getenv("TFR_STREAM_CTAS_PER_SM");
+    const char* e2 = getenv("TFR_STREAM_UNROLL");
+    cfg_ctas = e1 ? atoi(e1) : 0;
+    cfg_unroll = e2 ? atoi(e2) : 2;
+  }
+  int64_t grid = ((int64_t)units + 512 * cfg_unroll - 1) / (512 * cfg_unroll);
+  const int64_t cap = (int64_t)sm_count() * cfg_ctas;
+  if (cfg_ctas > 0 && grid > cap) grid = cap;
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t n = rows * (int64_t)width;
-  const int sms = sm_count();
-  if (width % 4 == 0 && ((uintptr_t)var % 16 == 0) && ((uintptr_t)m % 16 == 0) && ((uintptr_t)v % 16 == 0)) {
-    const int64_t n4 = n / 4;
-    constexpr int UNROLL = 2;
-    int64_t grid = (n4 + 512 * UNROLL - 1) / (512 * UNROLL);
-    const int64_t cap = (int64_t)sms * 3;  // 3 CTAs x 512 threads per SM
-    if (grid > cap) grid = cap;
-    if (n4 < ((int64_t)1 << 31))
-      adam_stream_vec4_kernel<uint32_t, UNROLL><<<(unsigned)grid, 512, 0, st>>>(
-          (float4*)var, (float4*)m, (float4*)v, (uint32_t)n4, (uint32_t)(width / 4), touched, opt);
-    else
-      adam_stream_vec4_kernel<uint64_t, UNROLL><<<(unsigned)grid, 512, 0, st>>>(
-          (float4*)var, (float4*)m, (float4*)v, (uint64_t)n4, (uint32_t)(width / 4), touched, opt);
+  if (cfg_unroll >= 4) {
+    TFR_PREP(adam_stream_multi_kernel<4>);
+    adam_stream_multi_kernel<4><<<(unsigned)grid, 512, 0, st>>>(a, opt, tl_slot);
   } else {
-    int64_t grid = (n + 511) / 512;
-    const int64_t cap = (int64_t)sms * 4;
-    if (grid > cap) grid = cap;
-    if (n < ((int64_t)1 << 31))
-      adam_stream_scalar_kernel<uint32_t><<<(unsigned)grid, 512, 0, st>>>(var, m, v, (uint32_t)n, (uint32_t)width,
-                                                                        touched, opt);
-    else
-      adam_stream_scalar_kernel<uint64_t><<<(unsigned)grid, 512, 0, st>>>(var, m, v, (uint64_t)n, (uint32_t)width,
-                                                                        touched, opt);
+    TFR_PREP(adam_stream_multi_kernel<2>);
+    adam_stream_multi_kernel<2><<<(unsigned)grid, 512, 0, st>>>(a, opt, tl_slot);
   }
   TFR_LAUNCH_CHECK();
   return TFR_OK;
 }
 
-static int launch_touched(float* var, float* m, float* v, int32_t width, const int32_t* sorted_ids, int64_t n,
-                          const float* gsum, const tfr_opt_scalars* opt, int sgd, cudaStream_t st) {
-  const RowGeom g = row_geom(width);
-  const int groups_per_cta = 256 / g.lanes;
-  const unsigned grid = (unsigned)((n + groups_per_cta - 1) / groups_per_cta);
-#define TFR_TOUCH_CASE(V, LL)                                                                                 \
-  if (g.vec == V && g.lanes == LL) {                                                                          \
-    adam_touched_kernel<V, LL><<<grid, 256, 0, st>>>(var, m, v, width, sorted_ids, n, gsum, opt, sgd);        \
-    TFR_LAUNCH_CHECK();                                                                                        \
-    return TFR_OK;                                                                                             \
+extern "C" int tfr_adam_stream_untouched(float* var, float* m, float* v, int64_t rows, int32_t width,
+                                         const uint8_t* touched, const tfr_opt_scalars* opt, void* stream) {
+  tfr_adam_table t{var, m, v, rows, width, touched};
+  return tfr_adam_stream_multi(&t, 1, opt, TFR_TL_SLOTS - 1, stream);
+}
+
+extern "C" int tfr_adam_slice_multi(const tfr_slice_update* sides, int32_t n_sides, int32_t width, int64_t n,
+                                    const tfr_opt_scalars* opt, int32_t sgd, int32_t tl_slot, void* stream) {
+  TFR_CHECK_ARG(sides && n_sides >= 1 && n_sides <= 2 && width > 0 && n >= 0 && tl_slot >= 0 && tl_slot < TFR_TL_SLOTS);
+  if (n == 0) return TFR_OK;
+  TFR_CHECK_ARG(sgd || opt);
+  SliceSide ss[2];
+  memset(ss, 0, sizeof(ss));
+  for (int i = 0; i < n_sides; ++i) {
+    const tfr_slice_update& u = sides[i];
+    TFR_CHECK_ARG(u.sorted_ids);
+    TFR_CHECK_ARG(!u.var || (u.gsum && (sgd || (u.m && u.v))));
+    TFR_CHECK_ARG(!u.bvar || (u.bgsum && (sgd || (u.bm && u.bv))));
+    ss[i].var = u.var; ss[i].m = u.m; ss[i].v = u.v; ss[i].bvar = u.bvar; ss[i].bm = u.bm; ss[i].bv = u.bv;
+    ss[i].sid = u.sorted_ids; ss[i].gsum = u.gsum; ss[i].bgsum = u.bgsum;
   }
-  TFR_TOUCH_CASE(4, 1) TFR_TOUCH_CASE(4, 2) TFR_TOUCH_CASE(4, 4) TFR_TOUCH_CASE(4, 8) TFR_TOUCH_CASE(4, 16)
-  TFR_TOUCH_CASE(4, 32) TFR_TOUCH_CASE(1, 1) TFR_TOUCH_CASE(1, 2) TFR_TOUCH_CASE(1, 4) TFR_TOUCH_CASE(1, 8)
-  TFR_TOUCH_CASE(1, 16) TFR_TOUCH_CASE(1, 32)
-#undef TFR_TOUCH_CASE
+  const RowGeom g = row_geom(width);
+  const int64_t groups = (n + SLICE_ENT - 1) / SLICE_ENT;
+  const int groups_per_cta = 256 / g.lanes;
+  dim3 grid((unsigned)((groups + groups_per_cta - 1) / groups_per_cta), (unsigned)n_sides);
+  cudaStream_t st = (cudaStream_t)stream;
+#define TFR_SLICE_CASE(V, LL)                                                                        \
+  if (g.vec == V && g.lanes == LL) {                                                                 \
+    TFR_PREP((adam_slice_kernel<V, LL>));                                                            \
+    adam_slice_kernel<V, LL><<<grid, 256, 0, st>>>(ss[0], ss[1], width, n, opt, sgd, tl_slot);       \
+    TFR_LAUNCH_CHECK();                                                                               \
+    return TFR_OK;                                                                                    \
+  }
+  TFR_SLICE_CASE(4, 1) TFR_SLICE_CASE(4, 2) TFR_SLICE_CASE(4, 4) TFR_SLICE_CASE(4, 8) TFR_SLICE_CASE(4, 16)
+  TFR_SLICE_CASE(4, 32) TFR_SLICE_CASE(1, 1) TFR_SLICE_CASE(1, 2) TFR_SLICE_CASE(1, 4) TFR_SLICE_CASE(1, 8)
+  TFR_SLICE_CASE(1, 16) TFR_SLICE_CASE(1, 32)
+#undef TFR_SLICE_CASE
   set_error("unsupported width %d", width);
   return TFR_ERR_INVALID;
 }
 
 extern "C" int tfr_adam_touched(float* var, float* m, float* v, int32_t width, const int32_t* sorted_ids, int64_t n,
                                 const float* gsum, const tfr_opt_scalars* opt, void* stream) {
-  TFR_CHECK_ARG(n >= 0 && width > 0);
-  if (n == 0) return TFR_OK;
-  TFR_CHECK_ARG(var && m && v && sorted_ids && gsum && opt);
-  return launch_touched(var, m, v, width, sorted_ids, n, gsum, opt, 0, (cudaStream_t)stream);
+  tfr_slice_update u{var, m, v, nullptr, nullptr, nullptr, sorted_ids, gsum, nullptr};
+  return tfr_adam_slice_multi(&u, 1, width, n, opt, 0, TFR_TL_SLOTS - 1, stream);
 }
 
 extern "C" int tfr_sgd_apply(float* var, int32_t width, const int32_t* sorted_ids, int64_t n, const float* gsum,
                              void* stream) {
-  TFR_CHECK_ARG(n >= 0 && width > 0);
-  if (n == 0) return TFR_OK;
-  TFR_CHECK_ARG(var && sorted_ids && gsum);
-  return launch_touched(var, nullptr, nullptr, width, sorted_ids, n, gsum, nullptr, 1, (cudaStream_t)stream);
+  tfr_slice_update u{var, nullptr, nullptr, nullptr, nullptr, nullptr, sorted_ids, gsum, nullptr};
+  return tfr_adam_slice_multi(&u, 1, width, n, nullptr, 1, TFR_TL_SLOTS - 1, stream);
 }
 
 extern "C" int tfr_svd_finish_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
                                    const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, int32_t n_partials,
                                    void* stream) {
   TFR_CHECK_ARG(t && opt && users && items && ws && B > 0 && n_partials > 0 && n_partials <= TFR_MAX_PARTIALS);
+  TFR_PREP(finish_step_kernel);
   finish_step_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*t, opt, users, items, B,
                                                                                   ws->partials, ws->se_partials,
                                                                                   n_partials);

@@ -1,7 +1,11 @@
 // C-ABI glue: error reporting, workspace carving, the full train step (the sequence that replaces one
 // sess.run([train_op, logits, infer]) of svd_train_val.py:70-72) and CUDA-graph helpers.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <mutex>
+#include <set>
 
 #include "common.cuh"
 
@@ -28,6 +32,21 @@ int sm_count() {
 
 int fwd_err_n_partials(int dim, int64_t B);
 
+void prep_kernel(const void* fn) {
+  static std::mutex mu;
+  static std::set<const void*> done;
+  std::lock_guard<std::mutex> g(mu);
+  if (done.count(fn)) return;
+  static int carve = -1;
+  if (carve < 0) {
+    const char* e = getenv("TFR_SMEM_CARVEOUT");
+    carve = e ? atoi(e) : 50;
+  }
+  if (carve > 0) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  cudaGetLastError();
+  done.insert(fn);
+}
+
 }  // namespace tfr
 
 using namespace tfr;
@@ -45,6 +64,15 @@ extern "C" int tfr_device_sm_count(void) {
 __global__ void set_se_ring_kernel(tfr_opt_scalars* opt, double* ring, int64_t len) {
   opt->se_ring = ring;
   opt->se_ring_len = len;
+}
+
+__global__ void set_timeline_kernel(tfr_opt_scalars* opt, uint64_t* tl) { opt->timeline = tl; }
+
+extern "C" int tfr_opt_set_timeline(tfr_opt_scalars* opt_dev, uint64_t* timeline, void* stream) {
+  TFR_CHECK_ARG(opt_dev);
+  set_timeline_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(opt_dev, timeline);
+  TFR_LAUNCH_CHECK();
+  return TFR_OK;
 }
 
 extern "C" int tfr_opt_set_se_ring(tfr_opt_scalars* opt_dev, double* se_ring, int64_t se_ring_len, void* stream) {
@@ -86,6 +114,8 @@ static int64_t carve(char* base, int64_t B, int32_t dim, tfr_svd_step_ws* o) {
   w.cont_ib = (float*)take(n_tiles * 4);
   w.tail_ub = (float*)take(n_tiles * 4);
   w.tail_ib = (float*)take(n_tiles * 4);
+  w.kind_u = (uint8_t*)take(n_tiles);
+  w.kind_i = (uint8_t*)take(n_tiles);
   w.sort_ws_bytes = tfr_dedup_workspace_bytes(B);
   w.sort_ws = take(w.sort_ws_bytes);
   w.tile = kTile;
@@ -113,15 +143,22 @@ extern "C" int tfr_svd_step_carve(void* workspace, int64_t workspace_bytes, int6
 }
 
 // ---- the step ------------------------------------------------------------------------------------------
-// Fork/join events for the two-stream schedule (streaming pass over the untouched rows overlaps the
-// forward -> sort -> segment-sum chain, which only touches this step's slice rows).
-static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+// Dependency graph of one step.  S0 = caller's stream; optional side streams: BULK (low priority), CHAIN and
+// SORT (high priority).  Without side streams everything runs on S0 in the order below.
+//   BULK : ONE launch: whole-table Adam pass over the rows OUTSIDE the slice (reads only touched maps + tables)
+//   SORT : id sort (needs only the ids)               ||  CHAIN: forward + d cost/d logits
+//   CHAIN: segment sums (need err + sorted pairs) -> fix-up -> slice update (both tables, ONE launch)
+//   S0   : finish (after BULK and CHAIN)
+// The bulk pass is bandwidth-bound and long, the chain is a sequence of short latency-bound kernels: giving the
+// chain priority lets its CTAs in as bulk CTAs retire, and the bulk pass fills the gaps.
+static cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
 extern "C" int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
                                   const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
                                   int32_t flags, int32_t var_mask, void* workspace, int64_t workspace_bytes,
-                                  void* stream, void* side_stream) {
+                                  void* stream, void* const* side_streams, int32_t n_side) {
   TFR_CHECK_ARG(t && opt && users && items && rates && B > 0 && t->dim > 0);
+  TFR_CHECK_ARG(n_side >= 0 && n_side <= 3 && (n_side == 0 || side_streams));
   // flags / var_mask repeat what the caller gave tfr_opt_init: the device copy drives the kernels, the
   // host copy selects which launches are issued (var_list: untrained tables get no launch at all).
   const bool sgd = flags & TFR_OPT_SGD;
@@ -130,47 +167,54 @@ extern "C" int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt,
   tfr_svd_step_ws ws;
   int rc = tfr_svd_step_carve(workspace, workspace_bytes, B, t->dim, &ws);
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaStream_t side = (cudaStream_t)side_stream;
+  cudaStream_t s0 = (cudaStream_t)stream;
+  cudaStream_t bulk = n_side > 0 ? (cudaStream_t)side_streams[0] : s0;
+  cudaStream_t chain = n_side > 1 ? (cudaStream_t)side_streams[1] : s0;
+  cudaStream_t sorts = n_side > 2 ? (cudaStream_t)side_streams[2] : chain;
   const int dim = t->dim;
+  if (n_side > 0 && !g_ev[0])
+    for (int i = 0; i < 5; ++i) TFR_CUDA(cudaEventCreateWithFlags(&g_ev[i], cudaEventDisableTiming));
+  auto fork = [&](cudaStream_t from, cudaStream_t to, cudaEvent_t ev) -> int {
+    if (from == to) return TFR_OK;
+    TFR_CUDA(cudaEventRecord(ev, from));
+    TFR_CUDA(cudaStreamWaitEvent(to, ev, 0));
+    return TFR_OK;
+  };
 
-  if (!sgd && side) {
-    if (!g_ev_fork) {
-      TFR_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
-      TFR_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
-    }
-    TFR_CUDA(cudaEventRecord(g_ev_fork, st));
-    TFR_CUDA(cudaStreamWaitEvent(side, g_ev_fork, 0));
+  TFR_CUDA(n_side > 0 ? cudaEventRecord(g_ev[0], s0) : cudaSuccess);
+  if (bulk != s0) TFR_CUDA(cudaStreamWaitEvent(bulk, g_ev[0], 0));
+  if (chain != s0) TFR_CUDA(cudaStreamWaitEvent(chain, g_ev[0], 0));
+  if (sorts != s0 && sorts != chain) TFR_CUDA(cudaStreamWaitEvent(sorts, g_ev[0], 0));
+
+  if (!sgd) {  // BULK: whole-table decay + step over the rows outside this step's slice
+    tfr_adam_table tabs[4];
+    int nt = 0;
+    if (var_mask & TFR_VAR_UF) tabs[nt++] = tfr_adam_table{t->user_feat, t->m_uf, t->v_uf, t->user_num, dim, t->user_touched};
+    if (var_mask & TFR_VAR_IF) tabs[nt++] = tfr_adam_table{t->item_feat, t->m_if, t->v_if, t->item_num, dim, t->item_touched};
+    if (var_mask & TFR_VAR_UB) tabs[nt++] = tfr_adam_table{t->user_bias, t->m_ub, t->v_ub, t->user_num, 1, t->user_touched};
+    if (var_mask & TFR_VAR_IB) tabs[nt++] = tfr_adam_table{t->item_bias, t->m_ib, t->v_ib, t->item_num, 1, t->item_touched};
+    if (nt && (rc = tfr_adam_stream_multi(tabs, nt, opt, TFR_TL_STREAM_UF, bulk))) return rc;
   }
-  cudaStream_t pass_st = (!sgd && side) ? side : st;
-
-  if ((rc = tfr_svd_fwd_err(t, opt, users, items, rates, B, logits, infer, &ws, st))) return rc;
-  if ((rc = tfr_dedup_sort_pairs(users, t->user_num, ws.su_ids, ws.su_pos, items, t->item_num, ws.si_ids, ws.si_pos,
-                                 B, ws.sort_ws, ws.sort_ws_bytes, st)))
+  if ((rc = tfr_dedup_sort_pairs_tl(users, t->user_num, ws.su_ids, ws.su_pos, items, t->item_num, ws.si_ids,
+                                    ws.si_pos, B, ws.sort_ws, ws.sort_ws_bytes, opt, sorts)))
     return rc;
-  if ((rc = tfr_svd_segment_grads(t, opt, users, items, B, &ws, st))) return rc;
-
-  if (!sgd) {
-    // whole-table decay + step over the rows outside this step's slice (reads only touched maps + tables)
-    if ((var_mask & TFR_VAR_UF) && (rc = tfr_adam_stream_untouched(t->user_feat, t->m_uf, t->v_uf, t->user_num, dim, t->user_touched, opt, pass_st))) return rc;
-    if ((var_mask & TFR_VAR_IF) && (rc = tfr_adam_stream_untouched(t->item_feat, t->m_if, t->v_if, t->item_num, dim, t->item_touched, opt, pass_st))) return rc;
-    if ((var_mask & TFR_VAR_UB) && (rc = tfr_adam_stream_untouched(t->user_bias, t->m_ub, t->v_ub, t->user_num, 1, t->user_touched, opt, pass_st))) return rc;
-    if ((var_mask & TFR_VAR_IB) && (rc = tfr_adam_stream_untouched(t->item_bias, t->m_ib, t->v_ib, t->item_num, 1, t->item_touched, opt, pass_st))) return rc;
-    if ((var_mask & TFR_VAR_UF) && (rc = tfr_adam_touched(t->user_feat, t->m_uf, t->v_uf, dim, ws.su_ids, B, ws.gsum_uf, opt, st))) return rc;
-    if ((var_mask & TFR_VAR_IF) && (rc = tfr_adam_touched(t->item_feat, t->m_if, t->v_if, dim, ws.si_ids, B, ws.gsum_if, opt, st))) return rc;
-    if ((var_mask & TFR_VAR_UB) && (rc = tfr_adam_touched(t->user_bias, t->m_ub, t->v_ub, 1, ws.su_ids, B, ws.gsum_ub, opt, st))) return rc;
-    if ((var_mask & TFR_VAR_IB) && (rc = tfr_adam_touched(t->item_bias, t->m_ib, t->v_ib, 1, ws.si_ids, B, ws.gsum_ib, opt, st))) return rc;
-    if (side) {
-      TFR_CUDA(cudaEventRecord(g_ev_join, side));
-      TFR_CUDA(cudaStreamWaitEvent(st, g_ev_join, 0));
-    }
-  } else {
-    if ((var_mask & TFR_VAR_UF) && (rc = tfr_sgd_apply(t->user_feat, dim, ws.su_ids, B, ws.gsum_uf, st))) return rc;
-    if ((var_mask & TFR_VAR_IF) && (rc = tfr_sgd_apply(t->item_feat, dim, ws.si_ids, B, ws.gsum_if, st))) return rc;
-    if ((var_mask & TFR_VAR_UB) && (rc = tfr_sgd_apply(t->user_bias, 1, ws.su_ids, B, ws.gsum_ub, st))) return rc;
-    if ((var_mask & TFR_VAR_IB) && (rc = tfr_sgd_apply(t->item_bias, 1, ws.si_ids, B, ws.gsum_ib, st))) return rc;
-  }
-  return tfr_svd_finish_step(t, opt, users, items, B, &ws, fwd_err_n_partials(dim, B), st);
+  if ((rc = tfr_svd_fwd_err(t, opt, users, items, rates, B, logits, infer, &ws, chain))) return rc;
+  if ((rc = fork(sorts, chain, g_ev[1]))) return rc;
+  if ((rc = tfr_svd_segment_grads(t, opt, users, items, B, &ws, chain))) return rc;
+  tfr_slice_update sides[2];
+  int ns = 0;
+  if (var_mask & (TFR_VAR_UF | TFR_VAR_UB))
+    sides[ns++] = tfr_slice_update{(var_mask & TFR_VAR_UF) ? t->user_feat : nullptr, t->m_uf, t->v_uf,
+                                   (var_mask & TFR_VAR_UB) ? t->user_bias : nullptr, t->m_ub, t->v_ub,
+                                   ws.su_ids, ws.gsum_uf, ws.gsum_ub};
+  if (var_mask & (TFR_VAR_IF | TFR_VAR_IB))
+    sides[ns++] = tfr_slice_update{(var_mask & TFR_VAR_IF) ? t->item_feat : nullptr, t->m_if, t->v_if,
+                                   (var_mask & TFR_VAR_IB) ? t->item_bias : nullptr, t->m_ib, t->v_ib,
+                                   ws.si_ids, ws.gsum_if, ws.gsum_ib};
+  if (ns && (rc = tfr_adam_slice_multi(sides, ns, dim, B, opt, sgd ? 1 : 0, TFR_TL_TOUCHED_U, chain))) return rc;
+  if ((rc = fork(chain, s0, g_ev[2]))) return rc;
+  if ((rc = fork(bulk, s0, g_ev[3]))) return rc;
+  return tfr_svd_finish_step(t, opt, users, items, B, &ws, fwd_err_n_partials(dim, B), s0);
 }
 
 // ---- CUDA graphs ------------------------------------------------------------------------------------------

@@ -10,6 +10,11 @@ namespace tfr {
 
 void set_error(const char* fmt, ...);
 int sm_count();
+// Gives every kernel of the step the SAME shared-memory carve-out.  An SM cannot host CTAs of two kernels
+// whose carve-outs differ, so without this the persistent streaming pass (no shared memory -> "max L1")
+// keeps the forward / sort / segment-sum kernels (which use shared memory) off every SM until it drains.
+void prep_kernel(const void* fn);
+#define TFR_PREP(kernel) tfr::prep_kernel(reinterpret_cast<const void*>(kernel))
 
 #define TFR_CHECK_ARG(cond)                                                        \
   do {                                                                             \
@@ -75,6 +80,31 @@ __device__ __forceinline__ float ld_gather_f1(const float* p) {
   asm("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
 }
+
+// ---- debug timeline (no nsys on the box): earliest block entry / latest warp exit per kernel --------------
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct TlScope {
+  unsigned long long* tl;
+  int slot;
+  __device__ __forceinline__ TlScope(const tfr_opt_scalars* opt, int slot_) : tl(nullptr), slot(slot_) {
+    if (opt) tl = reinterpret_cast<unsigned long long*>(opt->timeline);
+    // sampled so that the stamps do not serialise on one address: entry = first CTAs, exit = every 64th CTA
+    // and the grid's last 8 (which are scheduled last), one warp each
+    if (tl) {
+      const unsigned bid = blockIdx.x + blockIdx.y * gridDim.x, nb = gridDim.x * gridDim.y;
+      sampled = bid + 8 >= nb || (bid & 63u) == 0;
+      if (bid < 4 && threadIdx.x == 0) atomicMin(tl + slot, gtimer());
+    }
+  }
+  __device__ __forceinline__ ~TlScope() {
+    if (tl && sampled && (threadIdx.x & 31) == 0) atomicMax(tl + TFR_TL_SLOTS + slot, gtimer());
+  }
+  bool sampled = false;
+};
 
 // lane-group (L = 1..32, power of two) butterfly sum; every lane of the group gets the total.
 template <int L>

@@ -4,7 +4,7 @@
 //
 // One cooperative launch sorts TWO independent key arrays (the batch's user ids and item ids): the
 // first half of the grid owns problem A, the second half problem B, and both advance through the
-// 8-bit digit passes in lock step with grid-wide barriers.  Per pass: (a) per-CTA digit histogram of
+// digit passes (<= 9 bits each: 2 passes for the 18-bit ids of ML-25M) in lock step with grid-wide barriers.  Per pass: (a) per-CTA digit histogram of
 // the CTA's contiguous chunk, (b) grid barrier, (c) every CTA derives its own scatter bases from all
 // histograms (digit-exclusive scan + counts of lower CTAs), (d) stable scatter tile by tile: inside a
 // warp equal digits are ranked with __match_any_sync, across warps by a per-digit walk over the 16
@@ -21,7 +21,8 @@ namespace tfr {
 
 constexpr int SORT_THREADS = 512;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int RADIX = 256;
+constexpr int RADIX_BITS_MAX = 9;           // digit width is chosen per call: ceil(key bits / passes) <= 9
+constexpr int RADIX = 1 << RADIX_BITS_MAX;  // 512 bins -> 18-bit ids (ML-25M) in 2 passes, 27-bit (1e8) in 3
 constexpr int SORT_MAX_BPP = 64;  // CTAs per problem; 2*64 <= 148 SMs keeps the grid co-resident
 
 struct SortProblem {
@@ -34,17 +35,22 @@ struct SortProblem {
 };
 
 __global__ void __launch_bounds__(SORT_THREADS) dedup_sort_kernel(SortProblem pa, SortProblem pb, int bpp, int n_passes,
-                                                                  uint32_t* __restrict__ hist_g) {
+                                                                  int digit_bits, uint32_t* __restrict__ hist_g,
+                                                                  const tfr_opt_scalars* __restrict__ opt) {
+  TlScope tl_scope(opt, TFR_TL_SORT);
   cg::grid_group grid = cg::this_grid();
   __shared__ uint32_t s_wc[SORT_WARPS][RADIX];
   __shared__ uint32_t s_base[RADIX];
   __shared__ uint32_t s_scan[RADIX / 32];
+  static_assert(RADIX <= SORT_THREADS, "one thread per digit");
 
   const int prob = blockIdx.x / bpp;
   const int blk = blockIdx.x % bpp;
   const SortProblem p = prob ? pb : pa;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t dmask = (1u << digit_bits) - 1u;
+  const uint32_t invalid_digit = RADIX;  // never matches a real digit in __match_any_sync
 
   int64_t chunk = (p.n + bpp - 1) / bpp;
   chunk = (chunk + SORT_THREADS - 1) / SORT_THREADS * SORT_THREADS;
@@ -55,7 +61,7 @@ __global__ void __launch_bounds__(SORT_THREADS) dedup_sort_kernel(SortProblem pa
   for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_wc[0][0])[i] = 0;
 
   for (int pass = 0; pass < n_passes; ++pass) {
-    const int shift = pass * 8;
+    const int shift = pass * digit_bits;
     // ping-pong so that the LAST pass lands in out_*
     const bool to_out = ((n_passes - 1 - pass) & 1) == 0;
     const int32_t* src_ids = pass == 0 ? p.in_ids : (to_out ? p.tmp_ids : p.out_ids);
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(SORT_THREADS) dedup_sort_kernel(SortProblem pa
     for (int64_t i0 = begin; i0 < end; i0 += SORT_THREADS) {
       const int64_t i = i0 + tid;
       const bool valid = i < end;
-      const uint32_t digit = valid ? (((uint32_t)src_ids[i] >> shift) & 255u) : 256u;
+      const uint32_t digit = valid ? (((uint32_t)src_ids[i] >> shift) & dmask) : invalid_digit;
       const uint32_t peers = __match_any_sync(0xffffffffu, digit);
       if (valid && (peers & lt_mask) == 0) atomicAdd(&s_base[digit], __popc(peers));
     }
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(SORT_THREADS) dedup_sort_kernel(SortProblem pa
       const bool valid = i < end;
       const int32_t key = valid ? src_ids[i] : 0;
       const int32_t pos = valid ? (src_pos ? src_pos[i] : (int32_t)i) : 0;
-      const uint32_t digit = valid ? (((uint32_t)key >> shift) & 255u) : 256u;
+      const uint32_t digit = valid ? (((uint32_t)key >> shift) & dmask) : invalid_digit;
       const uint32_t peers = __match_any_sync(0xffffffffu, digit);
       const uint32_t lrank = __popc(peers & lt_mask);
       const bool leader = valid && lrank == 0;
@@ -211,6 +217,14 @@ extern "C" int tfr_dedup_sort_pairs(const int32_t* ids_a, int64_t max_id_a, int3
                                     int32_t* sorted_pos_a, const int32_t* ids_b, int64_t max_id_b,
                                     int32_t* sorted_ids_b, int32_t* sorted_pos_b, int64_t n, void* workspace,
                                     int64_t workspace_bytes, void* stream) {
+  return tfr_dedup_sort_pairs_tl(ids_a, max_id_a, sorted_ids_a, sorted_pos_a, ids_b, max_id_b, sorted_ids_b,
+                                 sorted_pos_b, n, workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int tfr_dedup_sort_pairs_tl(const int32_t* ids_a, int64_t max_id_a, int32_t* sorted_ids_a,
+                                       int32_t* sorted_pos_a, const int32_t* ids_b, int64_t max_id_b,
+                                       int32_t* sorted_ids_b, int32_t* sorted_pos_b, int64_t n, void* workspace,
+                                       int64_t workspace_bytes, const tfr_opt_scalars* opt, void* stream) {
   TFR_CHECK_ARG(n >= 0 && n < ((int64_t)1 << 31));
   if (n == 0) return TFR_OK;
   TFR_CHECK_ARG(ids_a && sorted_ids_a && sorted_pos_a && workspace && max_id_a > 0);
@@ -228,9 +242,11 @@ extern "C" int tfr_dedup_sort_pairs(const int32_t* ids_a, int64_t max_id_a, int3
   SortProblem pb{ids_b, sorted_ids_b, sorted_pos_b, (int32_t*)(w + 2 * seg), (int32_t*)(w + 3 * seg), ids_b ? n : 0};
   int bits = bits_for(max_id_a);
   if (ids_b && bits_for(max_id_b) > bits) bits = bits_for(max_id_b);
-  int n_passes = (bits + 7) / 8;
+  int n_passes = (bits + RADIX_BITS_MAX - 1) / RADIX_BITS_MAX;
+  int digit_bits = (bits + n_passes - 1) / n_passes;
   int bpp = sort_bpp(n);
-  void* args[] = {&pa, &pb, &bpp, &n_passes, &hist};
+  void* args[] = {&pa, &pb, &bpp, &n_passes, &digit_bits, &hist, &opt};
+  TFR_PREP(dedup_sort_kernel);
   TFR_CUDA(cudaLaunchCooperativeKernel((const void*)dedup_sort_kernel, dim3(2 * bpp), dim3(SORT_THREADS), args, 0,
                                        (cudaStream_t)stream));
   return TFR_OK;

@@ -31,8 +31,14 @@ struct SegSide {
   const float* partner_feat;
   const float* own_bias;
   float *gsum, *gsum_b, *cont, *cont_b, *tail, *tail_b;
+  uint8_t* kind;  // per tile: TILE_MID | TILE_START (see segsum_fixup_kernel)
   int is_item;
 };
+
+// tile classification written by the tiles kernel, read by the fix-up:
+//   TILE_MID   the whole tile is ONE run that began in an earlier tile and goes on into the next
+//   TILE_START the tile's last run begins here and goes on into the next tile (tail[t] is valid)
+constexpr uint8_t TILE_MID = 1, TILE_START = 2;
 
 template <int VEC>
 struct Acc {
@@ -65,6 +71,7 @@ template <int VEC, int L, int UNITS>
 __global__ void __launch_bounds__(256) segsum_tiles_kernel(SegSide su, SegSide si, const tfr_opt_scalars* __restrict__ opt,
                                                            const float* __restrict__ err, int64_t B, int dim,
                                                            int n_tiles) {
+  TlScope tl_scope(opt, TFR_TL_TILES);
   const SegSide s = blockIdx.y ? si : su;
   const int lane = threadIdx.x & (L - 1);
   const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
@@ -89,6 +96,7 @@ __global__ void __launch_bounds__(256) segsum_tiles_kernel(SegSide su, SegSide s
   float acc_b = 0.0f, own_b = 0.0f;
   int32_t cur = -1;
   int64_t run_start = k0;
+  uint8_t kind = 0;
 
   auto flush = [&](int64_t k_end) {  // the run [run_start, k_end) of id `cur` is over (within this tile)
     const bool starts = run_start > k0 || cur != prev_id;
@@ -96,8 +104,8 @@ __global__ void __launch_bounds__(256) segsum_tiles_kernel(SegSide su, SegSide s
     float* dst;
     float* dst_b;
     if (starts && ends) { dst = s.gsum + (size_t)run_start * dim; dst_b = s.gsum_b + run_start; }
-    else if (!starts)   { dst = s.cont + (size_t)t * dim;         dst_b = s.cont_b + t; }
-    else                { dst = s.tail + (size_t)t * dim;         dst_b = s.tail_b + t; }
+    else if (!starts)   { dst = s.cont + (size_t)t * dim;         dst_b = s.cont_b + t; if (!ends) kind |= TILE_MID; }
+    else                { dst = s.tail + (size_t)t * dim;         dst_b = s.tail_b + t; kind |= TILE_START; }
 #pragma unroll
     for (int q = 0; q < UNITS; ++q) {
       const int unit = lane + q * L;
@@ -167,53 +175,72 @@ __global__ void __launch_bounds__(256) segsum_tiles_kernel(SegSide su, SegSide s
     }
   }
   if (cur >= 0) flush(k1);
+  if (lane == 0) s.kind[t] = kind;
 }
 
-// One lane group per tile; only the tile in which a boundary-crossing run BEGINS does work: it adds
-// tail[t] + cont[t+1] + cont[t+2] + ... in tile order and writes gsum at the run's head index.
-template <int VEC, int L, int UNITS>
-__global__ void __launch_bounds__(256) segsum_fixup_kernel(SegSide su, SegSide si, int64_t B, int dim, int n_tiles) {
+// Fix-up: one CTA per tile, only CTAs of TILE_START tiles work.  A run that begins in tile t0 and ends in
+// tile t1 has the partial sums tail[t0], cont[t0+1], ..., cont[t1]; tiles t0+1..t1-1 are TILE_MID.  The CTA's G
+// thread groups add the cont rows j = g, g+G, g+2G, ... (each in increasing j), then group 0 adds
+// tail + p_0 + p_1 + ... + p_{G-1}: a fixed tree, so the result is deterministic, and a hot row with
+// thousands of occurrences costs ~n/(32*G) dependent steps instead of n/32.
+template <int VEC>
+__global__ void __launch_bounds__(256) segsum_fixup_kernel(SegSide su, SegSide si, const tfr_opt_scalars* __restrict__ opt,
+                                                           int64_t B, int dim, int n_tiles, int cw) {
+  TlScope tl_scope(opt, TFR_TL_FIXUP);
+  extern __shared__ float s_part[];  // [G][dim] (+ [G] bias partials)
   const SegSide s = blockIdx.y ? si : su;
-  const int lane = threadIdx.x & (L - 1);
-  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
-  if (t >= n_tiles) return;
+  const int t0 = blockIdx.x;
+  if (!(s.kind[t0] & TILE_START)) return;
+  const int G = 256 / cw;
+  const int g = threadIdx.x / cw, c = threadIdx.x % cw;
   const int n_units = dim / VEC;
-  const int64_t k0 = t * SEG_TILE;
-  const int64_t k1 = min(k0 + SEG_TILE, B);
-  if (k1 >= B) return;  // last tile: nothing continues past it
-  const int32_t last_id = s.sid[k1 - 1];
-  if (s.sid[k1] != last_id) return;  // last run ends here
-  // head of the last run inside this tile (ids are sorted: the run is a suffix of the tile)
-  int64_t a = k1 - 1;
-  while (a > k0 && s.sid[a - 1] == last_id) --a;
-  if (a == k0 && k0 > 0 && s.sid[k0 - 1] == last_id) return;  // begun in an earlier tile
-  Acc<VEC> tot[UNITS];
-#pragma unroll
-  for (int q = 0; q < UNITS; ++q) {
-    const int unit = lane + q * L;
-    if (unit < n_units) tot[q] = load_units<VEC>(s.tail + (size_t)t * dim, unit);
-  }
-  float tot_b = s.tail_b[t];
-  for (int64_t tt = t + 1; tt < n_tiles; ++tt) {
-#pragma unroll
-    for (int q = 0; q < UNITS; ++q) {
-      const int unit = lane + q * L;
-      if (unit < n_units) {
-        const Acc<VEC> c = load_units<VEC>(s.cont + (size_t)tt * dim, unit);
-#pragma unroll
-        for (int cc = 0; cc < VEC; ++cc) tot[q].v[cc] = add_rn(tot[q].v[cc], c.v[cc]);
-      }
+  __shared__ int s_t1;
+  if (threadIdx.x < 32) {  // t1 = first tile after t0 that is not TILE_MID
+    int t1 = -1;
+    for (int base = t0 + 1; t1 < 0; base += 32) {
+      const int tt = base + threadIdx.x;
+      const bool stop = tt >= n_tiles || !(s.kind[tt] & TILE_MID);
+      const unsigned m = __ballot_sync(0xffffffffu, stop);
+      if (m) t1 = base + __ffs(m) - 1;
     }
-    tot_b = add_rn(tot_b, s.cont_b[tt]);
-    const int64_t e1 = min((tt + 1) * (int64_t)SEG_TILE, B);
-    if (e1 >= B || s.sid[e1] != last_id) break;
+    if (threadIdx.x == 0) s_t1 = min(t1, n_tiles - 1);
   }
+  __syncthreads();
+  const int t1 = s_t1;
+  float* bias_part = s_part + (size_t)G * dim;
+  for (int unit = c; unit < n_units; unit += cw) {
+    Acc<VEC> acc;
 #pragma unroll
-  for (int q = 0; q < UNITS; ++q) {
-    const int unit = lane + q * L;
-    if (unit < n_units) store_units<VEC>(s.gsum + (size_t)a * dim, unit, tot[q]);
+    for (int q = 0; q < VEC; ++q) acc.v[q] = 0.0f;
+    for (int tt = t0 + 1 + g; tt <= t1; tt += G) {
+      const Acc<VEC> x = load_units<VEC>(s.cont + (size_t)tt * dim, unit);
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) acc.v[q] = add_rn(acc.v[q], x.v[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) s_part[(size_t)g * dim + unit * VEC + q] = acc.v[q];
   }
-  if (lane == 0) s.gsum_b[a] = tot_b;
+  if (c == 0) {
+    float ab = 0.0f;
+    for (int tt = t0 + 1 + g; tt <= t1; tt += G) ab = add_rn(ab, s.cont_b[tt]);
+    bias_part[g] = ab;
+  }
+  __syncthreads();
+  // head index of the run inside t0 (ids are sorted: the run is the tile's suffix)
+  const int64_t k0 = (int64_t)t0 * SEG_TILE, k1 = min(k0 + SEG_TILE, B);
+  const int32_t id = s.sid[k1 - 1];
+  int64_t a = k1 - 1;
+  while (a > k0 && s.sid[a - 1] == id) --a;
+  for (int col = threadIdx.x; col < dim; col += 256) {
+    float tot = s.tail[(size_t)t0 * dim + col];
+    for (int gg = 0; gg < G; ++gg) tot = add_rn(tot, s_part[(size_t)gg * dim + col]);
+    s.gsum[(size_t)a * dim + col] = tot;
+  }
+  if (threadIdx.x == 0) {
+    float tot = s.tail_b[t0];
+    for (int gg = 0; gg < G; ++gg) tot = add_rn(tot, bias_part[gg]);
+    s.gsum_b[a] = tot;
+  }
 }
 
 }  // namespace tfr
@@ -228,17 +255,24 @@ extern "C" int tfr_svd_segment_grads(const tfr_svd_tables* t, const tfr_opt_scal
   const int units = (dim / g.vec + g.lanes - 1) / g.lanes;
   const int n_tiles = (int)((B + SEG_TILE - 1) / SEG_TILE);
   SegSide su{ws->su_ids, ws->su_pos, items, t->user_feat, t->item_feat, t->user_bias,
-             ws->gsum_uf, ws->gsum_ub, ws->cont_uf, ws->cont_ub, ws->tail_uf, ws->tail_ub, 0};
+             ws->gsum_uf, ws->gsum_ub, ws->cont_uf, ws->cont_ub, ws->tail_uf, ws->tail_ub, ws->kind_u, 0};
   SegSide si{ws->si_ids, ws->si_pos, users, t->item_feat, t->user_feat, t->item_bias,
-             ws->gsum_if, ws->gsum_ib, ws->cont_if, ws->cont_ib, ws->tail_if, ws->tail_ib, 1};
+             ws->gsum_if, ws->gsum_ib, ws->cont_if, ws->cont_ib, ws->tail_if, ws->tail_ib, ws->kind_i, 1};
+  int cw = 1;
+  while (cw < dim / g.vec && cw < 256) cw <<= 1;
+  const int G = 256 / cw;
+  const size_t fix_smem = ((size_t)G * dim + G) * sizeof(float);
+  dim3 fix_grid((unsigned)n_tiles, 2);
   const int groups_per_cta = 256 / g.lanes;
   dim3 grid((unsigned)((n_tiles + groups_per_cta - 1) / groups_per_cta), 2);
   cudaStream_t st = (cudaStream_t)stream;
 #define TFR_SEG_CASE(V, LL, UU)                                                                                   \
   if (g.vec == V && g.lanes == LL && units == UU) {                                                               \
+    TFR_PREP((segsum_tiles_kernel<V, LL, UU>));                                                                    \
+    TFR_PREP((segsum_fixup_kernel<V>));                                                                            \
     segsum_tiles_kernel<V, LL, UU><<<grid, 256, 0, st>>>(su, si, opt, ws->err, B, dim, n_tiles);                  \
     TFR_LAUNCH_CHECK();                                                                                            \
-    segsum_fixup_kernel<V, LL, UU><<<grid, 256, 0, st>>>(su, si, B, dim, n_tiles);                                \
+    segsum_fixup_kernel<V><<<fix_grid, 256, fix_smem, st>>>(su, si, opt, B, dim, n_tiles, cw);                    \
     TFR_LAUNCH_CHECK();                                                                                            \
     return TFR_OK;                                                                                                 \
   }

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(256) svd_forward_kernel(tfr_svd_tables t, cons
                                                           float* __restrict__ logits, float* __restrict__ infer,
                                                           float* __restrict__ err, float* __restrict__ partials,
                                                           double* __restrict__ se_partials) {
+  TlScope tl_scope(TRAIN ? opt : nullptr, TFR_TL_FWD);
   constexpr int GPW = 32 / L;  // groups per warp
   const int lane = threadIdx.x & (L - 1);
   const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(256) batch_assemble_kernel(tfr_svd_tables t, t
                                                              const int64_t* __restrict__ row_index, int64_t batch_index,
                                                              int64_t B, int32_t* __restrict__ users,
                                                              int32_t* __restrict__ items, float* __restrict__ rates) {
+  TlScope tl_scope(opt, TFR_TL_ASSEMBLE);
   const int64_t batch = batch_index >= 0 ? batch_index : opt->batch_cursor;
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) {
@@ -170,6 +172,7 @@ static int launch_forward(const tfr_svd_tables* t, const tfr_opt_scalars* opt, c
   if (n_partials_out) *n_partials_out = (int)grid;
 #define TFR_FWD_CASE(V, LL)                                                                                     \
   if (g.vec == V && g.lanes == LL) {                                                                            \
+    TFR_PREP((svd_forward_kernel<V, LL, TRAIN>));                                                               \
     svd_forward_kernel<V, LL, TRAIN><<<(unsigned)grid, 256, 0, st>>>(*t, opt, users, items, rates, B, flags, logits, \
                                                                      infer, err, partials, se_partials);        \
     TFR_LAUNCH_CHECK();                                                                                          \
@@ -218,6 +221,7 @@ extern "C" int tfr_svd_batch_assemble(const tfr_svd_tables* t, tfr_opt_scalars* 
                                       void* stream) {
   TFR_CHECK_ARG(t && opt && B > 0 && users && items && rates && col_user && col_item && col_rate && row_index);
   TFR_CHECK_ARG(t->user_touched && t->item_touched);
+  TFR_PREP(batch_assemble_kernel);
   batch_assemble_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       *t, opt, col_user, col_item, col_rate, row_index, batch_index, B, users, items, rates);
   TFR_LAUNCH_CHECK();
@@ -227,6 +231,7 @@ extern "C" int tfr_svd_batch_assemble(const tfr_svd_tables* t, tfr_opt_scalars* 
 extern "C" int tfr_svd_mark_touched(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
                                     const int32_t* items, int64_t B, void* stream) {
   TFR_CHECK_ARG(t && opt && B > 0 && users && items && t->user_touched && t->item_touched);
+  TFR_PREP(batch_assemble_kernel);
   batch_assemble_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       *t, opt, nullptr, nullptr, nullptr, nullptr, 0, B, const_cast<int32_t*>(users), const_cast<int32_t*>(items),
       nullptr);

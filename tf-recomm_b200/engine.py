@@ -63,7 +63,10 @@ class SvdEngine:
             self.user_touched = torch.zeros(self.U, dtype=torch.uint8, device=dev)
             self.item_touched = torch.zeros(self.I, dtype=torch.uint8, device=dev)
             self.opt = torch.zeros(C.sizeof(OptScalars), dtype=torch.uint8, device=dev)
-            self.side_stream = torch.cuda.Stream(device=dev)
+            # BULK (low priority) / CHAIN, SORT (high priority): see tfr_svd_train_step
+            self.side_streams = [torch.cuda.Stream(device=dev, priority=0), torch.cuda.Stream(device=dev, priority=-1),
+                                 torch.cuda.Stream(device=dev, priority=-1)]
+            self._side_arr = (C.c_void_p * 3)(*[s_.cuda_stream for s_ in self.side_streams])
             self._fill_struct()
             check(self.L.tfr_opt_init(self.opt.data_ptr(), lr, reg, beta1, beta2, eps, self.flags, self.var_mask,
                                       self._stream()))
@@ -75,6 +78,10 @@ class SvdEngine:
         self.overlap = True
 
     # ---- plumbing ---------------------------------------------------------------------------------------
+    def _n_side(self):
+        """How many side streams the step may fork onto (self.overlap: True = 3, False = 0, or an int)."""
+        return 3 if self.overlap is True else min(3, int(self.overlap))
+
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -140,11 +147,10 @@ class SvdEngine:
             if not marked:
                 check(self.L.tfr_svd_mark_touched(C.byref(self.tables_struct), self.opt.data_ptr(), users.data_ptr(),
                                                   items.data_ptr(), B, st))
-            side = self.side_stream.cuda_stream if (self.overlap and not self.sgd) else None
             check(self.L.tfr_svd_train_step(C.byref(self.tables_struct), self.opt.data_ptr(), users.data_ptr(),
                                             items.data_ptr(), rates.data_ptr(), B, logits.data_ptr(),
                                             infer.data_ptr(), self.flags, self.var_mask, ws.data_ptr(), ws.numel(),
-                                            st, side))
+                                            st, self._side_arr, self._n_side()))
         return logits, infer
 
     # ---- host-fed step (the feed_dict path): pinned staging, H2D, step, D2H of the fetched predictions -------
@@ -189,7 +195,13 @@ class SvdEngine:
         else:
             ri = torch.from_numpy(np.ascontiguousarray(row_index, dtype=np.int64)).to(self.device)
         assert ri.numel() % B == 0
-        self.row_index = ri
+        # captured graphs bake the buffer's address: keep ONE persistent buffer and copy new streams into it
+        cap = getattr(self, "_row_index_buf", None)
+        if cap is None or cap.numel() < ri.numel():
+            self._row_index_buf = torch.empty(max(ri.numel(), 1), dtype=torch.int64, device=self.device)
+            self._graphs.clear()
+        self._row_index_buf[:ri.numel()].copy_(ri)
+        self.row_index = self._row_index_buf
         self.stream_B = B
         self.set_batch_cursor(0)
 
@@ -201,6 +213,26 @@ class SvdEngine:
         self.se_ring = torch.zeros(n, dtype=torch.float64, device=self.device)
         check(self.L.tfr_opt_set_se_ring(self.opt.data_ptr(), self.se_ring.data_ptr(), n, self._stream()))
 
+    # ---- debug timeline (in-kernel %globaltimer stamps; there is no nsys on the box) ----------------------
+    TL_NAMES = ("assemble", "fwd_err", "sort", "seg_tiles", "seg_fixup", "adam_stream", "-", "-", "-", "adam_slice",
+                "-", "finish")
+
+    def enable_timeline(self):
+        self.timeline = torch.zeros(32, dtype=torch.int64, device=self.device)
+        check(self.L.tfr_opt_set_timeline(self.opt.data_ptr(), self.timeline.data_ptr(), self._stream()))
+
+    def reset_timeline(self):
+        self.timeline[:16] = torch.iinfo(torch.int64).max
+        self.timeline[16:] = 0
+
+    def read_timeline(self):
+        """{kernel: (start_us, end_us)} relative to the earliest kernel start of the step."""
+        t = self.timeline.cpu().numpy()
+        begin, end = t[:16], t[16:]
+        live = [k for k in range(len(self.TL_NAMES)) if end[k] > 0]
+        t0 = min(begin[k] for k in live)
+        return {self.TL_NAMES[k]: ((begin[k] - t0) / 1e3, (end[k] - t0) / 1e3) for k in live}
+
     def _enqueue_stream_step(self, B, bufs, batch_index=-1):
         st = self._stream()
         check(self.L.tfr_svd_batch_assemble(C.byref(self.tables_struct), self.opt.data_ptr(),
@@ -209,11 +241,10 @@ class SvdEngine:
                                             bufs["users"].data_ptr(), bufs["items"].data_ptr(),
                                             bufs["rates"].data_ptr(), st))
         ws = self.workspace(B)
-        side = self.side_stream.cuda_stream if (self.overlap and not self.sgd) else None
         check(self.L.tfr_svd_train_step(C.byref(self.tables_struct), self.opt.data_ptr(), bufs["users"].data_ptr(),
                                         bufs["items"].data_ptr(), bufs["rates"].data_ptr(), B,
                                         bufs["logits"].data_ptr(), bufs["infer"].data_ptr(), self.flags,
-                                        self.var_mask, ws.data_ptr(), ws.numel(), st, side))
+                                        self.var_mask, ws.data_ptr(), ws.numel(), st, self._side_arr, self._n_side()))
 
     def stream_buffers(self, B):
         key = ("bufs", B)
