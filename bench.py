@@ -161,33 +161,22 @@ def time_stream_steps(eng, steps, torch):
     return ev0.elapsed_time(ev1) / 1e3
 
 
-def _adam_tables(eng, _lib):
+def _adam_tables(eng, ws, _lib):
     T, S = eng.t, eng.slots
     arr = (_lib.AdamTable * 4)()
-    for k, (tab, rows, width, touched) in enumerate((("user_feat", eng.U, eng.d, eng.user_touched),
-                                                     ("item_feat", eng.I, eng.d, eng.item_touched),
-                                                     ("user_bias", eng.U, 1, eng.user_touched),
-                                                     ("item_bias", eng.I, 1, eng.item_touched))):
+    for k, (tab, rows, width, slot, gsum) in enumerate((("user_feat", eng.U, eng.d, eng.user_slot, ws.gsum_uf),
+                                                        ("item_feat", eng.I, eng.d, eng.item_slot, ws.gsum_if),
+                                                        ("user_bias", eng.U, 1, eng.user_slot, ws.gsum_ub),
+                                                        ("item_bias", eng.I, 1, eng.item_slot, ws.gsum_ib))):
         arr[k].var, arr[k].m, arr[k].v = T[tab].data_ptr(), S["m_" + tab].data_ptr(), S["v_" + tab].data_ptr()
-        arr[k].rows, arr[k].width, arr[k].touched = rows, width, touched.data_ptr()
-    return arr
-
-
-def _slice_sides(eng, ws, _lib):
-    T, S = eng.t, eng.slots
-    arr = (_lib.SliceUpdate * 2)()
-    for k, (feat, bias, sid, gs, gsb) in enumerate((("user_feat", "user_bias", ws.su_ids, ws.gsum_uf, ws.gsum_ub),
-                                                    ("item_feat", "item_bias", ws.si_ids, ws.gsum_if, ws.gsum_ib))):
-        arr[k].var, arr[k].m, arr[k].v = T[feat].data_ptr(), S["m_" + feat].data_ptr(), S["v_" + feat].data_ptr()
-        arr[k].bvar, arr[k].bm, arr[k].bv = T[bias].data_ptr(), S["m_" + bias].data_ptr(), S["v_" + bias].data_ptr()
-        arr[k].sorted_ids, arr[k].gsum, arr[k].bgsum = sid, gs, gsb
+        arr[k].rows, arr[k].width, arr[k].slot, arr[k].gsum = rows, width, slot.data_ptr(), gsum
     return arr
 
 
 def kernel_roofline(eng, w, cols, steps, torch, peak, peak_src):
-    """Times the dominant kernel (adam_stream_multi_kernel: the whole-table TF-Adam pass over every row outside the
-    step's slice, all four tables in one launch) live with CUDA events around its launches, inside otherwise complete
-    steps issued piecewise through the C ABI on one stream."""
+    """Times the dominant kernel (adam_stream_multi_kernel: the whole-table TF-Adam pass, every row of all four
+    tables in one launch) live with CUDA events around its launches, inside otherwise complete steps issued
+    piecewise through the C ABI on one stream."""
     from tf_recomm_b200 import _lib
     from tf_recomm_b200._lib import check
     L = eng.L
@@ -198,33 +187,30 @@ def kernel_roofline(eng, w, cols, steps, torch, peak, peak_src):
     st = torch.cuda.current_stream().cuda_stream
     opt = eng.opt.data_ptr()
     logits = torch.empty(B, device=eng.device); infer = torch.empty(B, device=eng.device)
-    tabs, sides = _adam_tables(eng, _lib), _slice_sides(eng, ws, _lib)
-    tot_ms, tot_bytes = 0.0, 0.0
+    tabs = _adam_tables(eng, ws, _lib)
+    tot_ms = 0.0
     for s in range(steps):
         rows = rng.integers(0, len(cols[0]), B)
         du = eng._dev_i32(cols[0][rows]); di = eng._dev_i32(cols[1][rows]); dr = eng._dev_f32(cols[2][rows])
-        check(L.tfr_svd_mark_touched(tp, opt, du.data_ptr(), di.data_ptr(), B, st))
+        check(L.tfr_svd_begin_step(opt, st))
         check(L.tfr_svd_fwd_err(tp, opt, du.data_ptr(), di.data_ptr(), dr.data_ptr(), B, logits.data_ptr(),
                                 infer.data_ptr(), C.byref(ws), st))
         check(L.tfr_dedup_sort_pairs(du.data_ptr(), U, ws.su_ids, ws.su_pos, di.data_ptr(), I, ws.si_ids,
                                      ws.si_pos, B, ws.sort_ws, ws.sort_ws_bytes, st))
         check(L.tfr_svd_segment_grads(tp, opt, du.data_ptr(), di.data_ptr(), B, C.byref(ws), st))
-        nu = U - int(eng.user_touched.sum().item()); ni = I - int(eng.item_touched.sum().item())
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         check(L.tfr_adam_stream_multi(tabs, 4, opt, 15, st))
         ev1.record()
-        check(L.tfr_adam_slice_multi(sides, 2, d, B, opt, 0, 15, st))
         check(L.tfr_svd_finish_step(tp, opt, du.data_ptr(), di.data_ptr(), B, C.byref(ws), _n_partials(d, B), st))
         torch.cuda.synchronize()
         tot_ms += ev0.elapsed_time(ev1)
-        tot_bytes += 24.0 * (nu + ni) * (d + 1)
-    achieved = tot_bytes / (tot_ms / 1e3) / 1e9
-    return {"bound": "hbm", "kernel": "adam_stream_multi_kernel (whole-table TF-Adam pass over the rows outside the slice)",
+    bytes_launch = 24.0 * (U + I) * (d + 1)
+    achieved = bytes_launch / (tot_ms / steps / 1e3) / 1e9
+    return {"bound": "hbm", "kernel": "adam_stream_multi_kernel (TF-Adam pass over every row of all tables, one launch)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-            "bytes_per_launch": tot_bytes / steps, "launch_ms": tot_ms / steps,
-            "algorithmic_bytes": "24 B/param x (rows outside the step's slice) x (dim+1), both tables",
-            "traffic": None}
+            "bytes_per_launch": bytes_launch, "launch_ms": tot_ms / steps,
+            "algorithmic_bytes": "24 B/param x (users+items) x (dim+1)", "traffic": None}
 
 
 def _n_partials(d, B):
@@ -350,7 +336,7 @@ def main():
                 "peak_gbs": r["peak"], "peak_source": r["peak_src"]},
         "epoch_s": steps_epoch * r["ms_per_step"] / 1e3,
         "roofline": r.get("roofline"), "cpu_baseline": cpu, "e2e": r.get("e2e"), "clocks": r["clocks"],
-        "gpu_launches": 8 * args.steps,
+        "gpu_launches": 7 * args.steps,
     }
     if not args.no_also and name == "ml25m_d128_b65536":
         a2 = argparse.Namespace(**vars(args))

@@ -99,8 +99,8 @@ typedef struct {
   float* user_feat; /* user_features [U,dim] ops.py:29 */
   float* item_feat; /* item_features [I,dim] ops.py:31 */
   float *m_mu, *v_mu, *m_ub, *v_ub, *m_ib, *v_ib, *m_uf, *v_uf, *m_if, *v_if; /* null in SGD mode */
-  uint8_t* user_touched; /* [U] all zero between steps: rows of this step's IndexedSlices      */
-  uint8_t* item_touched; /* [I]                                                                */
+  int32_t* user_slot; /* [U] -1 between steps; during a step: for the rows of this step's IndexedSlices, the */
+  int32_t* item_slot; /* [I] sorted index k of the run head whose gsum[k] is the row's summed gradient         */
 } tfr_svd_tables;
 
 /* ---- forward only: replaces sess.run([logits, infer]) at svd_train_val.py:121-122 -----------
@@ -114,8 +114,7 @@ int tfr_svd_forward(const tfr_svd_tables* t, const int32_t* users, const int32_t
  * cols_* are the training columns resident in HBM; row_index holds the pre-drawn MT19937
  * `np.random.randint(0, N, B)` stream for many steps (generated on the host so that it is the
  * reference's stream).  Batch k = rows row_index[k*B .. k*B+B).  If batch_index < 0 the batch
- * number is read from opt->batch_cursor (graph replay).  Also marks users/items in the touched
- * maps and computes lr_t for this step. */
+ * number is read from opt->batch_cursor (graph replay).  Also computes lr_t for this step. */
 int tfr_svd_batch_assemble(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* col_user,
                            const int32_t* col_item, const float* col_rate, const int64_t* row_index,
                            int64_t batch_index, int64_t B, int32_t* users, int32_t* items, float* rates,
@@ -147,14 +146,11 @@ int tfr_unique_first_occurrence(const int32_t* sorted_ids, const int32_t* sorted
  * the gathered rows, ops.py:81-89,140) -> TF sparse Adam over the WHOLE tables (A.4) / dense Adam on
  * bias_global (A.5), or scatter_sub SGD (ops.py:145).  logits/infer come from the PRE-update tables
  * (A.7).  users/items/rates are the assembled batch (device).  Advances opt->global_step,
- * beta powers and batch_cursor; leaves the touched maps zeroed. */
+ * beta powers and batch_cursor; leaves the slot maps at -1. */
 int64_t tfr_svd_step_workspace_bytes(int64_t B, int32_t dim);
 /* flags / var_mask must equal what tfr_opt_init was given (the host copy selects the launches, the
- * device copy drives the kernels).  side_streams (optional; n_side = 0..3 distinct streams) let independent
- * parts of the step run concurrently: [0] BULK, low priority: the streaming pass over the rows outside the
- * slice; [1] CHAIN, high priority: forward -> segment sums -> slice update; [2] SORT, high priority: the id
- * sort next to the forward.  Fork/join is by events, so the whole step is still capturable as one graph from
- * `stream`. */
+ * device copy drives the kernels).  side_streams (optional; n_side = 0..1): [0] runs the id sort next to the
+ * forward.  Fork/join is by events, so the whole step is still capturable as one graph from `stream`. */
 int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
                        const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
                        int32_t flags, int32_t var_mask, void* workspace, int64_t workspace_bytes, void* stream,
@@ -180,27 +176,28 @@ int tfr_svd_step_carve(void* workspace, int64_t workspace_bytes, int64_t B, int3
 int tfr_svd_fwd_err(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
                     const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
                     const tfr_svd_step_ws* ws, void* stream);
-/* marks touched rows + computes lr_t (what tfr_svd_batch_assemble does for a device-assembled batch) */
-int tfr_svd_mark_touched(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
-                         const int32_t* items, int64_t B, void* stream);
+/* start of a step on a caller-assembled batch: computes lr_t (tfr_svd_batch_assemble does it too) */
+int tfr_svd_begin_step(tfr_opt_scalars* opt, void* stream);
 /* ordered segment sums of the per-occurrence gradients (never materialised): for every run of equal
  * ids in the sorted pairs, gsum[head k] = sum in batch order of (e_b*partner_row + reg*own_row). */
 int tfr_svd_segment_grads(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
                           const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, void* stream);
-/* TF sparse Adam (A.4), split in two kernels that together read and write every parameter once per step:
- * (1) the streaming pass over the rows NOT marked touched (pure decay + step), all tables in ONE launch;
- * (2) the slice rows: var/m/v[sorted_ids[k]] for every run head k with the summed gradient gsum[k], the
- *     feature rows and the bias entries of both tables in ONE launch.  SGD (ops.py:145): var -= gsum. */
+/* TF sparse Adam (A.4) as ONE streaming pass over every table, all tables in ONE launch: each parameter is
+ * read and written exactly once per step (24 B/param), in address order.  A row that is in this step's slice
+ * (slot[row] = k >= 0) takes its summed gradient from gsum[k]; every other row gets the pure decay + step.
+ * slot may be null (no row has a gradient). */
 typedef struct {
-  float *var, *m, *v;     /* [rows*width], 16-byte aligned */
+  float *var, *m, *v;  /* [rows*width], 16-byte aligned */
   int64_t rows;
   int32_t width;
-  const uint8_t* touched; /* [rows] */
+  const int32_t* slot; /* [rows] row -> run-head index into gsum, -1 = not in the slice */
+  const float* gsum;   /* [n, width] */
 } tfr_adam_table;
 int tfr_adam_stream_multi(const tfr_adam_table* tables, int32_t n_tables /* 1..4 */, const tfr_opt_scalars* opt,
                           int32_t tl_slot, void* stream);
-int tfr_adam_stream_untouched(float* var, float* m, float* v, int64_t rows, int32_t width,
-                              const uint8_t* touched, const tfr_opt_scalars* opt, void* stream);
+/* The slice rows alone: var/m/v[sorted_ids[k]] for every run head k with the summed gradient gsum[k]; feature
+ * rows and bias entries of both tables in ONE launch.  Used for SGD (ops.py:145: var -= gsum, no table pass)
+ * and by callers that schedule the slice separately. */
 typedef struct {
   float *var, *m, *v;        /* feature table [rows, width]; null = not in var_list          */
   float *bvar, *bm, *bv;     /* bias table [rows] sharing the row ids; null = not in var_list  */
@@ -215,7 +212,7 @@ int tfr_adam_touched(float* var, float* m, float* v, int32_t width, const int32_
 int tfr_sgd_apply(float* var, int32_t width, const int32_t* sorted_ids, int64_t n, const float* gsum,
                   void* stream);
 /* end of step: dense Adam/SGD on bias_global from the err partials (A.5), advance beta powers and
- * counters (TF: adam.py::_finish), clear the touched maps. */
+ * counters (TF: adam.py::_finish), reset the slot maps to -1. */
 int tfr_svd_finish_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
                         const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, int32_t n_partials,
                         void* stream);

@@ -181,7 +181,7 @@ def test_segment_grads_vs_oracle(d, B, flags):
     logits = torch.empty(B, device="cuda")
     infer = torch.empty(B, device="cuda")
     tp = C.byref(eng.tables_struct)
-    _lib.check(L.tfr_svd_mark_touched(tp, eng.opt.data_ptr(), du.data_ptr(), di.data_ptr(), B, st))
+    _lib.check(L.tfr_svd_begin_step(eng.opt.data_ptr(), st))
     _lib.check(L.tfr_svd_fwd_err(tp, eng.opt.data_ptr(), du.data_ptr(), di.data_ptr(), dr.data_ptr(), B,
                                  logits.data_ptr(), infer.data_ptr(), C.byref(ws), st))
     _lib.check(L.tfr_dedup_sort_pairs(du.data_ptr(), U, ws.su_ids, ws.su_pos, di.data_ptr(), I, ws.si_ids, ws.si_pos,
@@ -237,7 +237,7 @@ def test_train_step_parity_readme_adam(U, I, d, B, steps):
     assert sc.global_step == steps == orc.global_step
     assert sc.beta1_power == pytest.approx(orc.s.beta1_power, rel=0, abs=0)   # same fp32 multiply chain
     assert sc.beta2_power == pytest.approx(orc.s.beta2_power, rel=0, abs=0)
-    assert int(eng.user_touched.sum()) == 0 and int(eng.item_touched.sum()) == 0
+    assert int((eng.user_slot != -1).sum()) == 0 and int((eng.item_slot != -1).sum()) == 0
 
 
 @pytest.mark.parametrize("overlap", [False, True])
@@ -383,7 +383,7 @@ def test_fm_forward_golden_and_oracle(golden_dir):
 # ---- BASELINE.json full sizes: size-independent properties -----------------------------------------------
 def test_full_size_config4_properties():
     """ML-25M shape (162541 x 62423, d=128, B=65536): sortedness + permutation of the dedup, idempotence,
-    touched maps cleared, lr=0 leaves var unchanged while m,v decay exactly, and the device-drawn step equals a
+    slot maps reset, lr=0 leaves var unchanged while m,v decay exactly, and the device-drawn step equals a
     second engine fed the same batch (determinism)."""
     U, I, d, B = 162541, 62423, 128, 65536
     rng = np.random.default_rng(23)
@@ -407,7 +407,7 @@ def test_full_size_config4_properties():
     a, b = engs[0].get_tables(), engs[1].get_tables()
     for n in a:
         assert np.array_equal(a[n], b[n]), n                              # deterministic, run to run
-    assert int(engs[0].user_touched.sum()) == 0 and int(engs[0].item_touched.sum()) == 0
+    assert int((engs[0].user_slot != -1).sum()) == 0 and int((engs[0].item_slot != -1).sum()) == 0
     # linearity-type property of the whole-table pass: with lr = 0, var is unchanged and m, v of rows outside
     # the slice are exactly m*beta1, v*beta2
     e0 = SvdEngine(U, I, d, 0.0, 0.05, device_init_seed=7)

@@ -41,7 +41,7 @@ class SvdTables(C.Structure):
                 ("mu", vp), ("user_bias", vp), ("item_bias", vp), ("user_feat", vp), ("item_feat", vp),
                 ("m_mu", vp), ("v_mu", vp), ("m_ub", vp), ("v_ub", vp), ("m_ib", vp), ("v_ib", vp),
                 ("m_uf", vp), ("v_uf", vp), ("m_if", vp), ("v_if", vp),
-                ("user_touched", vp), ("item_touched", vp)]
+                ("user_slot", vp), ("item_slot", vp)]
 
 
 class StepWs(C.Structure):
@@ -57,7 +57,7 @@ class StepWs(C.Structure):
 
 class AdamTable(C.Structure):
     """Mirror of tfr_adam_table."""
-    _fields_ = [("var", vp), ("m", vp), ("v", vp), ("rows", i64), ("width", i32), ("touched", vp)]
+    _fields_ = [("var", vp), ("m", vp), ("v", vp), ("rows", i64), ("width", i32), ("slot", vp), ("gsum", vp)]
 
 
 class SliceUpdate(C.Structure):
@@ -86,9 +86,8 @@ _PROTOS = {
                                      C.POINTER(vp), i32]),
     "tfr_svd_step_carve": (C.c_int, [vp, i64, i64, i32, C.POINTER(StepWs)]),
     "tfr_svd_fwd_err": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, i64, vp, vp, C.POINTER(StepWs), vp]),
-    "tfr_svd_mark_touched": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, vp]),
+    "tfr_svd_begin_step": (C.c_int, [vp, vp]),
     "tfr_svd_segment_grads": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, C.POINTER(StepWs), vp]),
-    "tfr_adam_stream_untouched": (C.c_int, [vp, vp, vp, i64, i32, vp, vp, vp]),
     "tfr_adam_stream_multi": (C.c_int, [C.POINTER(AdamTable), i32, vp, i32, vp]),
     "tfr_adam_touched": (C.c_int, [vp, vp, vp, i32, vp, i64, vp, vp, vp]),
     "tfr_adam_slice_multi": (C.c_int, [C.POINTER(SliceUpdate), i32, i32, i64, vp, i32, i32, vp]),

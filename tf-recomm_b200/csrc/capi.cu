@@ -143,22 +143,18 @@ extern "C" int tfr_svd_step_carve(void* workspace, int64_t workspace_bytes, int6
 }
 
 // ---- the step ------------------------------------------------------------------------------------------
-// Dependency graph of one step.  S0 = caller's stream; optional side streams: BULK (low priority), CHAIN and
-// SORT (high priority).  Without side streams everything runs on S0 in the order below.
-//   BULK : ONE launch: whole-table Adam pass over the rows OUTSIDE the slice (reads only touched maps + tables)
-//   SORT : id sort (needs only the ids)               ||  CHAIN: forward + d cost/d logits
-//   CHAIN: segment sums (need err + sorted pairs) -> fix-up -> slice update (both tables, ONE launch)
-//   S0   : finish (after BULK and CHAIN)
-// The bulk pass is bandwidth-bound and long, the chain is a sequence of short latency-bound kernels: giving the
-// chain priority lets its CTAs in as bulk CTAs retire, and the bulk pass fills the gaps.
-static cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+//   SORT (side stream, optional): id sort (needs only the ids)   ||   S0: forward + d cost/d logits
+//   S0: segment sums (need err + sorted pairs) -> fix-up  (write gsum and the row -> slot maps)
+//   S0: Adam: ONE in-order pass over every row of every table  |  SGD: slice rows only (ops.py:145)
+//   S0: finish
+static cudaEvent_t g_ev[2] = {nullptr, nullptr};
 
 extern "C" int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
                                   const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
                                   int32_t flags, int32_t var_mask, void* workspace, int64_t workspace_bytes,
                                   void* stream, void* const* side_streams, int32_t n_side) {
   TFR_CHECK_ARG(t && opt && users && items && rates && B > 0 && t->dim > 0);
-  TFR_CHECK_ARG(n_side >= 0 && n_side <= 3 && (n_side == 0 || side_streams));
+  TFR_CHECK_ARG(n_side >= 0 && n_side <= 1 && (n_side == 0 || side_streams));
   // flags / var_mask repeat what the caller gave tfr_opt_init: the device copy drives the kernels, the
   // host copy selects which launches are issued (var_list: untrained tables get no launch at all).
   const bool sgd = flags & TFR_OPT_SGD;
@@ -168,52 +164,44 @@ extern "C" int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt,
   int rc = tfr_svd_step_carve(workspace, workspace_bytes, B, t->dim, &ws);
   if (rc) return rc;
   cudaStream_t s0 = (cudaStream_t)stream;
-  cudaStream_t bulk = n_side > 0 ? (cudaStream_t)side_streams[0] : s0;
-  cudaStream_t chain = n_side > 1 ? (cudaStream_t)side_streams[1] : s0;
-  cudaStream_t sorts = n_side > 2 ? (cudaStream_t)side_streams[2] : chain;
+  cudaStream_t sorts = n_side > 0 ? (cudaStream_t)side_streams[0] : s0;
   const int dim = t->dim;
-  if (n_side > 0 && !g_ev[0])
-    for (int i = 0; i < 5; ++i) TFR_CUDA(cudaEventCreateWithFlags(&g_ev[i], cudaEventDisableTiming));
-  auto fork = [&](cudaStream_t from, cudaStream_t to, cudaEvent_t ev) -> int {
-    if (from == to) return TFR_OK;
-    TFR_CUDA(cudaEventRecord(ev, from));
-    TFR_CUDA(cudaStreamWaitEvent(to, ev, 0));
-    return TFR_OK;
-  };
-
-  TFR_CUDA(n_side > 0 ? cudaEventRecord(g_ev[0], s0) : cudaSuccess);
-  if (bulk != s0) TFR_CUDA(cudaStreamWaitEvent(bulk, g_ev[0], 0));
-  if (chain != s0) TFR_CUDA(cudaStreamWaitEvent(chain, g_ev[0], 0));
-  if (sorts != s0 && sorts != chain) TFR_CUDA(cudaStreamWaitEvent(sorts, g_ev[0], 0));
-
-  if (!sgd) {  // BULK: whole-table decay + step over the rows outside this step's slice
-    tfr_adam_table tabs[4];
-    int nt = 0;
-    if (var_mask & TFR_VAR_UF) tabs[nt++] = tfr_adam_table{t->user_feat, t->m_uf, t->v_uf, t->user_num, dim, t->user_touched};
-    if (var_mask & TFR_VAR_IF) tabs[nt++] = tfr_adam_table{t->item_feat, t->m_if, t->v_if, t->item_num, dim, t->item_touched};
-    if (var_mask & TFR_VAR_UB) tabs[nt++] = tfr_adam_table{t->user_bias, t->m_ub, t->v_ub, t->user_num, 1, t->user_touched};
-    if (var_mask & TFR_VAR_IB) tabs[nt++] = tfr_adam_table{t->item_bias, t->m_ib, t->v_ib, t->item_num, 1, t->item_touched};
-    if (nt && (rc = tfr_adam_stream_multi(tabs, nt, opt, TFR_TL_STREAM_UF, bulk))) return rc;
+  if (sorts != s0) {
+    if (!g_ev[0])
+      for (int i = 0; i < 2; ++i) TFR_CUDA(cudaEventCreateWithFlags(&g_ev[i], cudaEventDisableTiming));
+    TFR_CUDA(cudaEventRecord(g_ev[0], s0));
+    TFR_CUDA(cudaStreamWaitEvent(sorts, g_ev[0], 0));
   }
   if ((rc = tfr_dedup_sort_pairs_tl(users, t->user_num, ws.su_ids, ws.su_pos, items, t->item_num, ws.si_ids,
                                     ws.si_pos, B, ws.sort_ws, ws.sort_ws_bytes, opt, sorts)))
     return rc;
-  if ((rc = tfr_svd_fwd_err(t, opt, users, items, rates, B, logits, infer, &ws, chain))) return rc;
-  if ((rc = fork(sorts, chain, g_ev[1]))) return rc;
-  if ((rc = tfr_svd_segment_grads(t, opt, users, items, B, &ws, chain))) return rc;
-  tfr_slice_update sides[2];
-  int ns = 0;
-  if (var_mask & (TFR_VAR_UF | TFR_VAR_UB))
-    sides[ns++] = tfr_slice_update{(var_mask & TFR_VAR_UF) ? t->user_feat : nullptr, t->m_uf, t->v_uf,
-                                   (var_mask & TFR_VAR_UB) ? t->user_bias : nullptr, t->m_ub, t->v_ub,
-                                   ws.su_ids, ws.gsum_uf, ws.gsum_ub};
-  if (var_mask & (TFR_VAR_IF | TFR_VAR_IB))
-    sides[ns++] = tfr_slice_update{(var_mask & TFR_VAR_IF) ? t->item_feat : nullptr, t->m_if, t->v_if,
-                                   (var_mask & TFR_VAR_IB) ? t->item_bias : nullptr, t->m_ib, t->v_ib,
-                                   ws.si_ids, ws.gsum_if, ws.gsum_ib};
-  if (ns && (rc = tfr_adam_slice_multi(sides, ns, dim, B, opt, sgd ? 1 : 0, TFR_TL_TOUCHED_U, chain))) return rc;
-  if ((rc = fork(chain, s0, g_ev[2]))) return rc;
-  if ((rc = fork(bulk, s0, g_ev[3]))) return rc;
+  if ((rc = tfr_svd_fwd_err(t, opt, users, items, rates, B, logits, infer, &ws, s0))) return rc;
+  if (sorts != s0) {
+    TFR_CUDA(cudaEventRecord(g_ev[1], sorts));
+    TFR_CUDA(cudaStreamWaitEvent(s0, g_ev[1], 0));
+  }
+  if ((rc = tfr_svd_segment_grads(t, opt, users, items, B, &ws, s0))) return rc;
+  if (!sgd) {
+    tfr_adam_table tabs[4];
+    int nt = 0;
+    if (var_mask & TFR_VAR_UF) tabs[nt++] = tfr_adam_table{t->user_feat, t->m_uf, t->v_uf, t->user_num, dim, t->user_slot, ws.gsum_uf};
+    if (var_mask & TFR_VAR_IF) tabs[nt++] = tfr_adam_table{t->item_feat, t->m_if, t->v_if, t->item_num, dim, t->item_slot, ws.gsum_if};
+    if (var_mask & TFR_VAR_UB) tabs[nt++] = tfr_adam_table{t->user_bias, t->m_ub, t->v_ub, t->user_num, 1, t->user_slot, ws.gsum_ub};
+    if (var_mask & TFR_VAR_IB) tabs[nt++] = tfr_adam_table{t->item_bias, t->m_ib, t->v_ib, t->item_num, 1, t->item_slot, ws.gsum_ib};
+    if (nt && (rc = tfr_adam_stream_multi(tabs, nt, opt, TFR_TL_STREAM_UF, s0))) return rc;
+  } else {
+    tfr_slice_update sides[2];
+    int ns = 0;
+    if (var_mask & (TFR_VAR_UF | TFR_VAR_UB))
+      sides[ns++] = tfr_slice_update{(var_mask & TFR_VAR_UF) ? t->user_feat : nullptr, nullptr, nullptr,
+                                     (var_mask & TFR_VAR_UB) ? t->user_bias : nullptr, nullptr, nullptr,
+                                     ws.su_ids, ws.gsum_uf, ws.gsum_ub};
+    if (var_mask & (TFR_VAR_IF | TFR_VAR_IB))
+      sides[ns++] = tfr_slice_update{(var_mask & TFR_VAR_IF) ? t->item_feat : nullptr, nullptr, nullptr,
+                                     (var_mask & TFR_VAR_IB) ? t->item_bias : nullptr, nullptr, nullptr,
+                                     ws.si_ids, ws.gsum_if, ws.gsum_ib};
+    if (ns && (rc = tfr_adam_slice_multi(sides, ns, dim, B, opt, 1, TFR_TL_TOUCHED_U, s0))) return rc;
+  }
   return tfr_svd_finish_step(t, opt, users, items, B, &ws, fwd_err_n_partials(dim, B), s0);
 }
 

@@ -32,6 +32,7 @@ struct SegSide {
   const float* own_bias;
   float *gsum, *gsum_b, *cont, *cont_b, *tail, *tail_b;
   uint8_t* kind;  // per tile: TILE_MID | TILE_START (see segsum_fixup_kernel)
+  int32_t* slot;  // [rows] row -> head index of its run (where its gsum lives); -1 between steps
   int is_item;
 };
 
@@ -111,7 +112,10 @@ __global__ void __launch_bounds__(256) segsum_tiles_kernel(SegSide su, SegSide s
       const int unit = lane + q * L;
       if (unit < n_units) store_units<VEC>(dst, unit, acc[q]);
     }
-    if (lane == 0) *dst_b = acc_b;
+    if (lane == 0) {
+      *dst_b = acc_b;
+      if (starts && ends) s.slot[cur] = (int32_t)run_start;
+    }
   };
 
   for (int64_t kb = k0; kb < k1; kb += L) {
@@ -240,6 +244,7 @@ __global__ void __launch_bounds__(256) segsum_fixup_kernel(SegSide su, SegSide s
     float tot = s.tail_b[t0];
     for (int gg = 0; gg < G; ++gg) tot = add_rn(tot, bias_part[gg]);
     s.gsum_b[a] = tot;
+    s.slot[id] = (int32_t)a;
   }
 }
 
@@ -249,15 +254,15 @@ using namespace tfr;
 
 extern "C" int tfr_svd_segment_grads(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
                                      const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, void* stream) {
-  TFR_CHECK_ARG(t && opt && users && items && ws && B > 0 && t->dim > 0);
+  TFR_CHECK_ARG(t && opt && users && items && ws && B > 0 && t->dim > 0 && t->user_slot && t->item_slot);
   const int dim = t->dim;
   const RowGeom g = row_geom(dim);
   const int units = (dim / g.vec + g.lanes - 1) / g.lanes;
   const int n_tiles = (int)((B + SEG_TILE - 1) / SEG_TILE);
   SegSide su{ws->su_ids, ws->su_pos, items, t->user_feat, t->item_feat, t->user_bias,
-             ws->gsum_uf, ws->gsum_ub, ws->cont_uf, ws->cont_ub, ws->tail_uf, ws->tail_ub, ws->kind_u, 0};
+             ws->gsum_uf, ws->gsum_ub, ws->cont_uf, ws->cont_ub, ws->tail_uf, ws->tail_ub, ws->kind_u, t->user_slot, 0};
   SegSide si{ws->si_ids, ws->si_pos, users, t->item_feat, t->user_feat, t->item_bias,
-             ws->gsum_if, ws->gsum_ib, ws->cont_if, ws->cont_ib, ws->tail_if, ws->tail_ib, ws->kind_i, 1};
+             ws->gsum_if, ws->gsum_ib, ws->cont_if, ws->cont_ib, ws->tail_if, ws->tail_ib, ws->kind_i, t->item_slot, 1};
   int cw = 1;
   while (cw < dim / g.vec && cw < 256) cw <<= 1;
   const int G = 256 / cw;

@@ -11,6 +11,8 @@
 // consecutive floats of the row per pass (128-bit loads when dim % 4 == 0).  Two rows per group are
 // in flight to double the outstanding gathers.  Products and adds are separate fp32 roundings
 // (tf.multiply then tf.reduce_sum), the lane-group butterfly fixes the reduction order.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace tfr {
@@ -140,21 +142,11 @@ __global__ void __launch_bounds__(256) batch_assemble_kernel(tfr_svd_tables t, t
   TlScope tl_scope(opt, TFR_TL_ASSEMBLE);
   const int64_t batch = batch_index >= 0 ? batch_index : opt->batch_cursor;
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) {
-    int32_t u, i;
-    if (row_index) {
-      const int64_t row = row_index[batch * B + b];
-      u = col_user[row];
-      i = col_item[row];
-      rates[b] = col_rate[row];
-      users[b] = u;
-      items[b] = i;
-    } else {
-      u = users[b];
-      i = items[b];
-    }
-    t.user_touched[u] = 1;
-    t.item_touched[i] = 1;
+  if (b < B && row_index) {
+    const int64_t row = row_index[batch * B + b];
+    users[b] = col_user[row];
+    items[b] = col_item[row];
+    rates[b] = col_rate[row];
   }
   if (b == 0) begin_step_scalars(opt);
 }
@@ -220,7 +212,6 @@ extern "C" int tfr_svd_batch_assemble(const tfr_svd_tables* t, tfr_opt_scalars* 
                                       int64_t batch_index, int64_t B, int32_t* users, int32_t* items, float* rates,
                                       void* stream) {
   TFR_CHECK_ARG(t && opt && B > 0 && users && items && rates && col_user && col_item && col_rate && row_index);
-  TFR_CHECK_ARG(t->user_touched && t->item_touched);
   TFR_PREP(batch_assemble_kernel);
   batch_assemble_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       *t, opt, col_user, col_item, col_rate, row_index, batch_index, B, users, items, rates);
@@ -228,13 +219,13 @@ extern "C" int tfr_svd_batch_assemble(const tfr_svd_tables* t, tfr_opt_scalars* 
   return TFR_OK;
 }
 
-extern "C" int tfr_svd_mark_touched(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
-                                    const int32_t* items, int64_t B, void* stream) {
-  TFR_CHECK_ARG(t && opt && B > 0 && users && items && t->user_touched && t->item_touched);
+extern "C" int tfr_svd_begin_step(tfr_opt_scalars* opt, void* stream) {
+  TFR_CHECK_ARG(opt);
+  tfr_svd_tables none;
+  memset(&none, 0, sizeof(none));
   TFR_PREP(batch_assemble_kernel);
-  batch_assemble_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      *t, opt, nullptr, nullptr, nullptr, nullptr, 0, B, const_cast<int32_t*>(users), const_cast<int32_t*>(items),
-      nullptr);
+  batch_assemble_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(none, opt, nullptr, nullptr, nullptr, nullptr, 0, 1, nullptr,
+                                                            nullptr, nullptr);
   TFR_LAUNCH_CHECK();
   return TFR_OK;
 }

@@ -60,13 +60,13 @@ class SvdEngine:
                 for n in TABLE_NAMES:
                     self.slots["m_" + n] = torch.zeros_like(self.t[n])
                     self.slots["v_" + n] = torch.zeros_like(self.t[n])
-            self.user_touched = torch.zeros(self.U, dtype=torch.uint8, device=dev)
-            self.item_touched = torch.zeros(self.I, dtype=torch.uint8, device=dev)
+            # row -> slot maps (-1 between steps): where a slice row finds its summed gradient during a step
+            self.user_slot = torch.full((self.U,), -1, dtype=torch.int32, device=dev)
+            self.item_slot = torch.full((self.I,), -1, dtype=torch.int32, device=dev)
             self.opt = torch.zeros(C.sizeof(OptScalars), dtype=torch.uint8, device=dev)
-            # BULK (low priority) / CHAIN, SORT (high priority): see tfr_svd_train_step
-            self.side_streams = [torch.cuda.Stream(device=dev, priority=0), torch.cuda.Stream(device=dev, priority=-1),
-                                 torch.cuda.Stream(device=dev, priority=-1)]
-            self._side_arr = (C.c_void_p * 3)(*[s_.cuda_stream for s_ in self.side_streams])
+            # side stream for the id sort (runs next to the forward): see tfr_svd_train_step
+            self.side_streams = [torch.cuda.Stream(device=dev)]
+            self._side_arr = (C.c_void_p * 1)(*[s_.cuda_stream for s_ in self.side_streams])
             self._fill_struct()
             check(self.L.tfr_opt_init(self.opt.data_ptr(), lr, reg, beta1, beta2, eps, self.flags, self.var_mask,
                                       self._stream()))
@@ -79,8 +79,8 @@ class SvdEngine:
 
     # ---- plumbing ---------------------------------------------------------------------------------------
     def _n_side(self):
-        """How many side streams the step may fork onto (self.overlap: True = 3, False = 0, or an int)."""
-        return 3 if self.overlap is True else min(3, int(self.overlap))
+        """How many side streams the step may fork onto (self.overlap: True = 1, False = 0)."""
+        return 1 if self.overlap else 0
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -94,7 +94,7 @@ class SvdEngine:
             for n, (mf, vf) in _SLOT_FIELDS.items():
                 setattr(s, mf, self.slots["m_" + n].data_ptr())
                 setattr(s, vf, self.slots["v_" + n].data_ptr())
-        s.user_touched, s.item_touched = self.user_touched.data_ptr(), self.item_touched.data_ptr()
+        s.user_slot, s.item_slot = self.user_slot.data_ptr(), self.item_slot.data_ptr()
         self.tables_struct = s
 
     def workspace(self, B):
@@ -134,7 +134,7 @@ class SvdEngine:
         return logits, infer
 
     # ---- one train step on a device-resident batch: sess.run([train_op, logits, infer]), :70-72 -------------
-    def train_step(self, users, items, rates, logits=None, infer=None, marked=False):
+    def train_step(self, users, items, rates, logits=None, infer=None):
         users, items, rates = self._dev_i32(users), self._dev_i32(items), self._dev_f32(rates)
         B = users.numel()
         if logits is None:
@@ -144,9 +144,7 @@ class SvdEngine:
         ws = self.workspace(B)
         with torch.cuda.device(self.device):
             st = self._stream()
-            if not marked:
-                check(self.L.tfr_svd_mark_touched(C.byref(self.tables_struct), self.opt.data_ptr(), users.data_ptr(),
-                                                  items.data_ptr(), B, st))
+            check(self.L.tfr_svd_begin_step(self.opt.data_ptr(), st))
             check(self.L.tfr_svd_train_step(C.byref(self.tables_struct), self.opt.data_ptr(), users.data_ptr(),
                                             items.data_ptr(), rates.data_ptr(), B, logits.data_ptr(),
                                             infer.data_ptr(), self.flags, self.var_mask, ws.data_ptr(), ws.numel(),
@@ -214,7 +212,7 @@ class SvdEngine:
         check(self.L.tfr_opt_set_se_ring(self.opt.data_ptr(), self.se_ring.data_ptr(), n, self._stream()))
 
     # ---- debug timeline (in-kernel %globaltimer stamps; there is no nsys on the box) ----------------------
-    TL_NAMES = ("assemble", "fwd_err", "sort", "seg_tiles", "seg_fixup", "adam_stream", "-", "-", "-", "adam_slice",
+    TL_NAMES = ("assemble", "fwd_err", "sort", "seg_tiles", "seg_fixup", "adam_pass", "-", "-", "-", "sgd_slice",
                 "-", "finish")
 
     def enable_timeline(self):

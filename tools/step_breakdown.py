@@ -31,7 +31,7 @@ def main():
     logits = torch.empty(B, device=eng.device); infer = torch.empty(B, device=eng.device)
     T, S = eng.t, eng.slots
     from tf_recomm_b200 import _lib
-    tabs, sides = bench._adam_tables(eng, _lib), bench._slice_sides(eng, ws, _lib)
+    tabs = bench._adam_tables(eng, ws, _lib)
     acc = {}
 
     def timed(label, fn):
@@ -44,16 +44,15 @@ def main():
         du = eng._dev_i32(cols[0][rows]); di = eng._dev_i32(cols[1][rows]); dr = eng._dev_f32(cols[2][rows])
         if s == 3:
             acc.clear()
-        timed("mark_touched", lambda: check(L.tfr_svd_mark_touched(tp, opt, du.data_ptr(), di.data_ptr(), B, st)))
+        timed("begin_step", lambda: check(L.tfr_svd_begin_step(opt, st)))
         timed("fwd_err", lambda: check(L.tfr_svd_fwd_err(tp, opt, du.data_ptr(), di.data_ptr(), dr.data_ptr(), B,
                                                          logits.data_ptr(), infer.data_ptr(), C.byref(ws), st)))
         timed("dedup_sort", lambda: check(L.tfr_dedup_sort_pairs(du.data_ptr(), U, ws.su_ids, ws.su_pos, di.data_ptr(), I,
                                                                  ws.si_ids, ws.si_pos, B, ws.sort_ws, ws.sort_ws_bytes, st)))
         timed("segment_grads(tiles+fixup)", lambda: check(L.tfr_svd_segment_grads(tp, opt, du.data_ptr(), di.data_ptr(), B,
                                                                                   C.byref(ws), st)))
-        timed("adam_stream (4 tables, 1 launch)", lambda: check(L.tfr_adam_stream_multi(tabs, 4, opt, 15, st)))
-        timed("adam_slice (2 tables, 1 launch)", lambda: check(L.tfr_adam_slice_multi(sides, 2, d, B, opt, 0, 15, st)))
-        nu = int(eng.user_touched.sum()); ni = int(eng.item_touched.sum())
+        timed("adam_pass (4 tables, 1 launch)", lambda: check(L.tfr_adam_stream_multi(tabs, 4, opt, 15, st)))
+        nu = int((eng.user_slot >= 0).sum()); ni = int((eng.item_slot >= 0).sum())
         timed("finish", lambda: check(L.tfr_svd_finish_step(tp, opt, du.data_ptr(), di.data_ptr(), B, C.byref(ws),
                                                             bench._n_partials(d, B), st)))
     torch.cuda.synchronize()

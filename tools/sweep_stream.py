@@ -21,10 +21,11 @@ U, d, B = w["U"], w["d"], w["B"]
 
 
 def alone(reps=30):
+    from tf_recomm_b200 import _lib
+    tabs = bench._adam_tables(eng, eng.step_ws(B), _lib)
+
     def go():
-        check(L.tfr_adam_stream_untouched(eng.t["user_feat"].data_ptr(), eng.slots["m_user_feat"].data_ptr(),
-                                          eng.slots["v_user_feat"].data_ptr(), U, d, eng.user_touched.data_ptr(),
-                                          eng.opt.data_ptr(), st))
+        check(L.tfr_adam_stream_multi(tabs, 4, eng.opt.data_ptr(), 15, st))
     for _ in range(5):
         go()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -33,7 +34,7 @@ def alone(reps=30):
         go()
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3
-    return us, 24.0 * U * d / us / 1e3
+    return us, 24.0 * (U + w['I']) * (d + 1) / us / 1e3
 
 
 us, gbs = alone()
