@@ -101,6 +101,11 @@ typedef struct {
   float *m_mu, *v_mu, *m_ub, *v_ub, *m_ib, *v_ib, *m_uf, *v_uf, *m_if, *v_if; /* null in SGD mode */
   int32_t* user_slot; /* [U] -1 between steps; during a step: for the rows of this step's IndexedSlices, the */
   int32_t* item_slot; /* [I] sorted index k of the run head whose gsum[k] is the row's summed gradient         */
+  /* Row-sharded mode (tables hold only this rank's rows, id mod G == rank).  When non-null, the
+   * batch's gathered rows by BATCH POSITION ([B,dim] / [B], exchanged between ranks) replace the by-id gathers
+   * of the forward and of the partner rows in the backward; the users/items arrays given to the step are then
+   * LOCAL row indices, with the value user_num / item_num marking occurrences owned by another rank. */
+  const float *g_user_feat, *g_item_feat, *g_user_bias, *g_item_bias;
 } tfr_svd_tables;
 
 /* ---- forward only: replaces sess.run([logits, infer]) at svd_train_val.py:121-122 -----------
@@ -216,6 +221,15 @@ int tfr_sgd_apply(float* var, int32_t width, const int32_t* sorted_ids, int64_t 
 int tfr_svd_finish_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
                         const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, int32_t n_partials,
                         void* stream);
+
+/* ---- row-sharded tables: the owner's half of the id -> row exchange ------------------------------
+ * For every batch position b: if ids[b] mod n_ranks == rank, copy the local row ids[b] / n_ranks (and its bias)
+ * to out_feat[b] / out_bias[b] and set local_keys[b] = ids[b] / n_ranks; otherwise write zeros and
+ * local_keys[b] = rows_local (the "not mine" mark).  Summing out_* over ranks (NCCL all-reduce, exact: one
+ * non-zero term per element) gives every rank the batch's gathered rows. */
+int tfr_shard_gather_rows(const float* feat_local, const float* bias_local, int64_t rows_local, int32_t dim,
+                          const int32_t* ids, int64_t B, int32_t n_ranks, int32_t rank, float* out_feat,
+                          float* out_bias, int32_t* local_keys, void* stream);
 
 /* ---- FM forward: replaces forward.py:21-22 `fma` ---------------------------------------------
  * yhat[r] = w0 + sum_i W_i x_i + 0.5 * sum_f ((sum_i V_if x_i)^2 - sum_i V_if^2 x_i^2) on CSR rows

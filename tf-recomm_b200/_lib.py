@@ -41,7 +41,8 @@ class SvdTables(C.Structure):
                 ("mu", vp), ("user_bias", vp), ("item_bias", vp), ("user_feat", vp), ("item_feat", vp),
                 ("m_mu", vp), ("v_mu", vp), ("m_ub", vp), ("v_ub", vp), ("m_ib", vp), ("v_ib", vp),
                 ("m_uf", vp), ("v_uf", vp), ("m_if", vp), ("v_if", vp),
-                ("user_slot", vp), ("item_slot", vp)]
+                ("user_slot", vp), ("item_slot", vp),
+                ("g_user_feat", vp), ("g_item_feat", vp), ("g_user_bias", vp), ("g_item_bias", vp)]
 
 
 class StepWs(C.Structure):
@@ -93,6 +94,7 @@ _PROTOS = {
     "tfr_adam_slice_multi": (C.c_int, [C.POINTER(SliceUpdate), i32, i32, i64, vp, i32, i32, vp]),
     "tfr_sgd_apply": (C.c_int, [vp, i32, vp, i64, vp, vp]),
     "tfr_svd_finish_step": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, C.POINTER(StepWs), i32, vp]),
+    "tfr_shard_gather_rows": (C.c_int, [vp, vp, i64, i32, vp, i64, i32, i32, vp, vp, vp, vp]),
     "tfr_fm_forward": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
     "tfr_graph_begin_capture": (C.c_int, [vp]),
     "tfr_graph_end_capture": (C.c_int, [vp, C.POINTER(vp)]),

@@ -253,9 +253,10 @@ __global__ void __launch_bounds__(256) finish_step_kernel(tfr_svd_tables t, tfr_
                                                           const double* __restrict__ se_partials, int n_partials) {
   TlScope tl_scope(opt, TFR_TL_FINISH);
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) {
-    t.user_slot[users[b]] = -1;
-    t.item_slot[items[b]] = -1;
+  if (b < B) {  // ids >= the table size mark occurrences owned by another rank (row-sharded mode)
+    const int32_t u = users[b], i = items[b];
+    if (u < t.user_num) t.user_slot[u] = -1;
+    if (i < t.item_num) t.item_slot[i] = -1;
   }
   if (blockIdx.x == 0 && threadIdx.x < 32) {
     float a = 0.0f;

@@ -172,8 +172,10 @@ extern "C" int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt,
     TFR_CUDA(cudaEventRecord(g_ev[0], s0));
     TFR_CUDA(cudaStreamWaitEvent(sorts, g_ev[0], 0));
   }
-  if ((rc = tfr_dedup_sort_pairs_tl(users, t->user_num, ws.su_ids, ws.su_pos, items, t->item_num, ws.si_ids,
-                                    ws.si_pos, B, ws.sort_ws, ws.sort_ws_bytes, opt, sorts)))
+  // + 1: in row-sharded mode the value user_num / item_num itself occurs (the "not mine" mark)
+  if ((rc = tfr_dedup_sort_pairs_tl(users, (int64_t)t->user_num + 1, ws.su_ids, ws.su_pos, items,
+                                    (int64_t)t->item_num + 1, ws.si_ids, ws.si_pos, B, ws.sort_ws,
+                                    ws.sort_ws_bytes, opt, sorts)))
     return rc;
   if ((rc = tfr_svd_fwd_err(t, opt, users, items, rates, B, logits, infer, &ws, s0))) return rc;
   if (sorts != s0) {

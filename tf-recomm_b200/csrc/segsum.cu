@@ -33,6 +33,7 @@ struct SegSide {
   float *gsum, *gsum_b, *cont, *cont_b, *tail, *tail_b;
   uint8_t* kind;  // per tile: TILE_MID | TILE_START (see segsum_fixup_kernel)
   int32_t* slot;  // [rows] row -> head index of its run (where its gsum lives); -1 between steps
+  int32_t n_rows; // ids >= n_rows mark occurrences owned by another rank (row-sharded mode): skipped
   int is_item;
 };
 
@@ -92,6 +93,10 @@ __global__ void __launch_bounds__(256) segsum_tiles_kernel(SegSide su, SegSide s
   const int64_t k1 = min(k0 + SEG_TILE, B);
   const int32_t prev_id = k0 > 0 ? s.sid[k0 - 1] : -1;
   const int32_t next_id = k1 < B ? s.sid[k1] : -1;
+  if (s.sid[k0] >= s.n_rows) {  // the whole tile belongs to other ranks
+    if (lane == 0) s.kind[t] = 0;
+    return;
+  }
 
   Acc<VEC> acc[UNITS], own[UNITS];
   float acc_b = 0.0f, own_b = 0.0f;
@@ -127,13 +132,19 @@ __global__ void __launch_bounds__(256) segsum_tiles_kernel(SegSide su, SegSide s
       my_id = s.sid[k];
       const int32_t b = s.spos[k];
       my_e = err[b];
-      my_partner = s.partner[b];
+      my_partner = s.partner ? s.partner[b] : b;  // row-sharded mode: partner rows are gathered by position
     }
     const int cnt = (int)min((int64_t)L, k1 - kb);
     for (int j = 0; j < cnt; ++j) {
       const int32_t id = __shfl_sync(gmask, my_id, j, L);
       const float e = __shfl_sync(gmask, my_e, j, L);
       const int32_t pid = __shfl_sync(gmask, my_partner, j, L);
+      if (id >= s.n_rows) {  // sorted to the end: nothing of mine follows
+        if (cur >= 0) flush(kb + j);
+        cur = -1;
+        kb = k1;  // leave both loops
+        break;
+      }
       if (id != cur) {
         if (cur >= 0) flush(kb + j);
         cur = id;
@@ -259,10 +270,14 @@ extern "C" int tfr_svd_segment_grads(const tfr_svd_tables* t, const tfr_opt_scal
   const RowGeom g = row_geom(dim);
   const int units = (dim / g.vec + g.lanes - 1) / g.lanes;
   const int n_tiles = (int)((B + SEG_TILE - 1) / SEG_TILE);
-  SegSide su{ws->su_ids, ws->su_pos, items, t->user_feat, t->item_feat, t->user_bias,
-             ws->gsum_uf, ws->gsum_ub, ws->cont_uf, ws->cont_ub, ws->tail_uf, ws->tail_ub, ws->kind_u, t->user_slot, 0};
-  SegSide si{ws->si_ids, ws->si_pos, users, t->item_feat, t->user_feat, t->item_bias,
-             ws->gsum_if, ws->gsum_ib, ws->cont_if, ws->cont_ib, ws->tail_if, ws->tail_ib, ws->kind_i, t->item_slot, 1};
+  const bool gathered = t->g_user_feat != nullptr;
+  TFR_CHECK_ARG(!gathered || t->g_item_feat);
+  SegSide su{ws->su_ids, ws->su_pos, gathered ? nullptr : items, t->user_feat,
+             gathered ? t->g_item_feat : t->item_feat, t->user_bias,
+             ws->gsum_uf, ws->gsum_ub, ws->cont_uf, ws->cont_ub, ws->tail_uf, ws->tail_ub, ws->kind_u, t->user_slot, t->user_num, 0};
+  SegSide si{ws->si_ids, ws->si_pos, gathered ? nullptr : users, t->item_feat,
+             gathered ? t->g_user_feat : t->user_feat, t->item_bias,
+             ws->gsum_if, ws->gsum_ib, ws->cont_if, ws->cont_ib, ws->tail_if, ws->tail_ib, ws->kind_i, t->item_slot, t->item_num, 1};
   int cw = 1;
   while (cw < dim / g.vec && cw < 256) cw <<= 1;
   const int G = 256 / cw;

@@ -68,6 +68,11 @@ __global__ void __launch_bounds__(256) svd_forward_kernel(tfr_svd_tables t, cons
   const bool abs_item = flags & TFR_ABS_ITEM;
   const int dim = t.dim;
   const float mu = *t.mu;
+  const bool gathered = t.g_user_feat != nullptr;
+  const float* __restrict__ uf = gathered ? t.g_user_feat : t.user_feat;
+  const float* __restrict__ itf = gathered ? t.g_item_feat : t.item_feat;
+  const float* __restrict__ ubias = gathered ? t.g_user_bias : t.user_bias;
+  const float* __restrict__ ibias = gathered ? t.g_item_bias : t.item_bias;
   float err_acc = 0.0f;
   double se_acc = 0.0;
 
@@ -76,10 +81,11 @@ __global__ void __launch_bounds__(256) svd_forward_kernel(tfr_svd_tables t, cons
   for (int64_t b0 = warp_first; b0 < B; b0 += 2 * n_groups) {
     const int64_t ba = b0 + (group % GPW), bb = ba + n_groups;
     const bool va = ba < B, vb = bb < B;
-    const int32_t ua = va ? users[ba] : 0, ia = va ? items[ba] : 0;
-    const int32_t ub = vb ? users[bb] : 0, ib = vb ? items[bb] : 0;
-    const float xa0 = row_dot<VEC, L>(t.user_feat + (size_t)ua * dim, t.item_feat + (size_t)ia * dim, dim, lane, abs_item);
-    const float xb0 = row_dot<VEC, L>(t.user_feat + (size_t)ub * dim, t.item_feat + (size_t)ib * dim, dim, lane, abs_item);
+    // row-sharded mode: the batch's rows were gathered by position (t.g_*), otherwise gather by id
+    const int32_t ua = va ? (gathered ? (int32_t)ba : users[ba]) : 0, ia = va ? (gathered ? (int32_t)ba : items[ba]) : 0;
+    const int32_t ub = vb ? (gathered ? (int32_t)bb : users[bb]) : 0, ib = vb ? (gathered ? (int32_t)bb : items[bb]) : 0;
+    const float xa0 = row_dot<VEC, L>(uf + (size_t)ua * dim, itf + (size_t)ia * dim, dim, lane, abs_item);
+    const float xb0 = row_dot<VEC, L>(uf + (size_t)ub * dim, itf + (size_t)ib * dim, dim, lane, abs_item);
     if (lane == 0) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -88,8 +94,8 @@ __global__ void __launch_bounds__(256) svd_forward_kernel(tfr_svd_tables t, cons
         const int64_t b = h ? bb : ba;
         const int32_t u = h ? ub : ua, i = h ? ib : ia;
         float x = add_rn(h ? xb0 : xa0, mu);               // ops.py:45
-        x = add_rn(x, ld_gather_f1(t.user_bias + u));      // ops.py:46
-        x = add_rn(x, ld_gather_f1(t.item_bias + i));      // ops.py:47
+        x = add_rn(x, ld_gather_f1(ubias + u));            // ops.py:46
+        x = add_rn(x, ld_gather_f1(ibias + i));            // ops.py:47
         const float inf = head(flags, x);
         if (logits) logits[b] = x;
         if (infer) infer[b] = inf;
