@@ -419,3 +419,74 @@ def test_full_size_config4_properties():
     keep = np.ones(U, bool); keep[users[0]] = False
     assert np.array_equal(t2["m_user_feat"][keep], t1["m_user_feat"][keep] * np.float32(0.9))
     assert np.array_equal(t2["v_user_feat"][keep], t1["v_user_feat"][keep] * np.float32(0.999))
+
+
+# ---- row-sharded tables (BASELINE configs[4]) emulated on ONE GPU: G virtual ranks, the all-reduce is a plain sum ----
+@pytest.mark.parametrize("G,U,I,d,B", [(2, 301, 157, 20, 500), (4, 1000, 333, 128, 2048), (8, 97, 61, 15, 200)])
+def test_sharded_step_matches_oracle(G, U, I, d, B):
+    from tf_recomm_b200 import sharding
+    from tf_recomm_b200.sharded import ShardedSvdEngine
+    rng = np.random.default_rng(G * 100 + d)
+    tabs = init.init_tables(U, I, d, seed=2, bias_init="truncated_normal")
+    orc = oracle.SvdOracle(tabs["mu"], tabs["user_bias"], tabs["item_bias"], tabs["user_feat"], tabs["item_feat"], 1e-3, 0.05)
+    engs = [ShardedSvdEngine(U, I, d, 1e-3, 0.05, rank=r, world=G, tables=tabs) for r in range(G)]
+    for step in range(6):
+        users, items, rates = make_batch(rng, U, I, B)
+        du, di, dr = (engs[0].local._dev_i32(users), engs[0].local._dev_i32(items), engs[0].local._dev_f32(rates))
+        bufs = [e._buffers(B) for e in engs]
+        for e, b in zip(engs, bufs):
+            e.gather_owned(du, di, b)
+        total = torch.stack([b["flat"] for b in bufs]).sum(0)       # what the NCCL all-reduce computes
+        # exactly one rank contributes each element: the sum reproduces the owner's row bit for bit
+        assert np.array_equal(total[:B * d].view(B, d).cpu().numpy(), np.asarray(eng_table(engs, "user_feat", G))[users])
+        outs = []
+        for e, b in zip(engs, bufs):
+            b["flat"].copy_(total)
+            outs.append(e.local_step(b, dr)[0].cpu().numpy())
+        ref_logits, _ = orc.train_step(users, items, rates)
+        for o in outs:
+            assert np.array_equal(o, outs[0])                        # every rank computes the same predictions
+        np.testing.assert_allclose(outs[0], ref_logits, rtol=RTOL, atol=1e-6)
+        for name in ("user_feat", "item_feat", "user_bias", "item_bias"):
+            assert_fp32_close(eng_table(engs, name, G), getattr(orc, name), "sharded step %d %s" % (step, name),
+                              max_abs=4e-3 + 1e-6)
+        for e in engs:
+            assert_fp32_close(e.local.t["mu"].cpu().numpy(), orc.mu, "sharded mu")
+            assert int((e.local.user_slot != -1).sum()) == 0 and int((e.local.item_slot != -1).sum()) == 0
+
+
+def eng_table(engs, name, G):
+    from tf_recomm_b200 import sharding
+    return sharding.unshard_table([e.local.t[name].cpu().numpy() for e in engs])
+
+
+def test_adam_pass_splits_tables_beyond_32bit_floats():
+    """A table with more floats than the kernel's 32-bit index (the 50M x 128 user shard of configs[4] at G=2) is cut
+    into row ranges: emulate with a width that makes rows*width cross 2^32 cheaply is impossible on small memory, so
+    check the splitting arithmetic through a narrow table against the unsplit result instead (row ranges must not
+    change any value)."""
+    L = _lib.load()
+    dev = torch.device("cuda")
+    rows, w = 4099, 12
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    var = torch.randn(rows, w, device=dev, generator=g) * 0.02
+    m = torch.randn(rows, w, device=dev, generator=g) * 1e-3
+    v = torch.rand(rows, w, device=dev, generator=g) * 1e-5
+    eng, _ = both(8, 8, 4, 1e-3, 0.05)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.tfr_svd_begin_step(eng.opt.data_ptr(), st))
+    ref = [t.clone() for t in (var, m, v)]
+    one = (_lib.AdamTable * 1)()
+    one[0].var, one[0].m, one[0].v, one[0].rows, one[0].width = ref[0].data_ptr(), ref[1].data_ptr(), ref[2].data_ptr(), rows, w
+    _lib.check(L.tfr_adam_stream_multi(one, 1, eng.opt.data_ptr(), 15, st))
+    parts = [t.clone() for t in (var, m, v)]
+    cut = 2048  # multiple of 4 rows
+    two = (_lib.AdamTable * 2)()
+    for k, (r0, r1) in enumerate(((0, cut), (cut, rows))):
+        two[k].var, two[k].m, two[k].v = (parts[j][r0:].data_ptr() for j in range(3))
+        two[k].rows, two[k].width = r1 - r0, w
+    _lib.check(L.tfr_adam_stream_multi(two, 2, eng.opt.data_ptr(), 15, st))
+    torch.cuda.synchronize()
+    for a, b in zip(ref, parts):
+        assert torch.equal(a, b)
+    assert not torch.equal(ref[0], var)

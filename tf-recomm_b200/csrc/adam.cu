@@ -324,34 +324,19 @@ extern "C" int tfr_opt_init(tfr_opt_scalars* opt_dev, float lr, float reg, float
   return TFR_OK;
 }
 
-extern "C" int tfr_adam_stream_multi(const tfr_adam_table* tables, int32_t n_tables, const tfr_opt_scalars* opt,
-                                     int32_t tl_slot, void* stream) {
-  TFR_CHECK_ARG(tables && n_tables >= 1 && n_tables <= 4 && opt && tl_slot >= 0 && tl_slot < TFR_TL_SLOTS);
+static int launch_stream_chunks(const StreamTab* chunks, int n_chunks, const tfr_opt_scalars* opt, int tl_slot,
+                                cudaStream_t st) {
   StreamArgs a;
   memset(&a, 0, sizeof(a));
   uint64_t units = 0;
-  int nt = 0;
-  for (int i = 0; i < n_tables; ++i) {
-    const tfr_adam_table& t = tables[i];
-    TFR_CHECK_ARG(t.rows >= 0 && t.width > 0);
-    if (t.rows == 0) continue;
-    TFR_CHECK_ARG(t.var && t.m && t.v && (!t.slot || t.gsum));
-    TFR_CHECK_ARG(((uintptr_t)t.var % 16 == 0) && ((uintptr_t)t.m % 16 == 0) && ((uintptr_t)t.v % 16 == 0));
-    TFR_CHECK_ARG(!t.gsum || t.width % 4 != 0 || (uintptr_t)t.gsum % 16 == 0);
-    const uint64_t n = (uint64_t)t.rows * (uint64_t)t.width;
-    units += (n + 3) / 4;
-    if (n >= ((uint64_t)1 << 32) || units >= ((uint64_t)1 << 32)) {
-      set_error("adam pass: %llu floats exceed the 32-bit unit index (shard the table)", (unsigned long long)n);
-      return TFR_ERR_INVALID;
-    }
-    a.t[nt].var = t.var; a.t[nt].m = t.m; a.t[nt].v = t.v; a.t[nt].slot = t.slot; a.t[nt].gsum = t.gsum;
-    a.t[nt].n = (uint32_t)n; a.t[nt].width = (uint32_t)t.width; a.t[nt].unit_end = (uint32_t)units;
-    ++nt;
+  for (int i = 0; i < n_chunks; ++i) {
+    a.t[i] = chunks[i];
+    units += ((uint64_t)chunks[i].n + 3) / 4;
+    a.t[i].unit_end = (uint32_t)units;
   }
-  if (nt == 0) return TFR_OK;
-  a.n_tabs = nt;
+  a.n_tabs = n_chunks;
   a.total_units = (uint32_t)units;
-  // persistent grid: 2 CTAs x 512 threads per SM, 2 units per thread and trip (measured best: 6.0 TB/s)
+  // persistent grid: 2 CTAs x 512 threads per SM, 2 units per thread and trip (measured best: ~6 TB/s)
   static int cfg_ctas = -1, cfg_unroll = 0;
   if (cfg_ctas < 0) {
     const char* e1 = getenv("TFR_STREAM_CTAS_PER_SM");
@@ -362,7 +347,6 @@ extern "C" int tfr_adam_stream_multi(const tfr_adam_table* tables, int32_t n_tab
   int64_t grid = ((int64_t)units + 512 * cfg_unroll - 1) / (512 * cfg_unroll);
   const int64_t cap = (int64_t)sm_count() * cfg_ctas;
   if (cfg_ctas > 0 && grid > cap) grid = cap;
-  cudaStream_t st = (cudaStream_t)stream;
   if (cfg_unroll >= 4) {
     TFR_PREP(adam_stream_multi_kernel<4>);
     adam_stream_multi_kernel<4><<<(unsigned)grid, 512, 0, st>>>(a, opt, tl_slot);
@@ -371,6 +355,50 @@ extern "C" int tfr_adam_stream_multi(const tfr_adam_table* tables, int32_t n_tab
     adam_stream_multi_kernel<2><<<(unsigned)grid, 512, 0, st>>>(a, opt, tl_slot);
   }
   TFR_LAUNCH_CHECK();
+  return TFR_OK;
+}
+
+extern "C" int tfr_adam_stream_multi(const tfr_adam_table* tables, int32_t n_tables, const tfr_opt_scalars* opt,
+                                     int32_t tl_slot, void* stream) {
+  TFR_CHECK_ARG(tables && n_tables >= 1 && n_tables <= 4 && opt && tl_slot >= 0 && tl_slot < TFR_TL_SLOTS);
+  // The kernel indexes floats with 32 bits: a table of >= 2^32 floats (the 50M x 128 user shard of configs[4] at
+  // G = 2) is cut into row ranges, and launches are split so that one launch covers < 2^32 units.
+  const uint64_t kMaxFloats = ((uint64_t)1 << 32) - 8;
+  StreamTab pending[4];
+  int np = 0;
+  uint64_t pending_units = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < n_tables; ++i) {
+    const tfr_adam_table& t = tables[i];
+    TFR_CHECK_ARG(t.rows >= 0 && t.width > 0);
+    if (t.rows == 0) continue;
+    TFR_CHECK_ARG(t.var && t.m && t.v && (!t.slot || t.gsum));
+    TFR_CHECK_ARG(((uintptr_t)t.var % 16 == 0) && ((uintptr_t)t.m % 16 == 0) && ((uintptr_t)t.v % 16 == 0));
+    TFR_CHECK_ARG(!t.gsum || t.width % 4 != 0 || (uintptr_t)t.gsum % 16 == 0);
+    uint64_t rows_per_chunk = kMaxFloats / (uint64_t)t.width;
+    rows_per_chunk -= rows_per_chunk % 4;  // keeps every chunk's first float 16-byte aligned for any width
+    for (uint64_t r0 = 0; r0 < (uint64_t)t.rows; r0 += rows_per_chunk) {
+      const uint64_t nr = ((uint64_t)t.rows - r0 < rows_per_chunk) ? (uint64_t)t.rows - r0 : rows_per_chunk;
+      StreamTab c;
+      const uint64_t off = r0 * (uint64_t)t.width;
+      c.var = t.var + off; c.m = t.m + off; c.v = t.v + off;
+      c.slot = t.slot ? t.slot + r0 : nullptr;
+      c.gsum = t.gsum;
+      c.n = (uint32_t)(nr * (uint64_t)t.width);
+      c.width = (uint32_t)t.width;
+      c.unit_end = 0;
+      const uint64_t cu = ((uint64_t)c.n + 3) / 4;
+      if (np == 4 || pending_units + cu >= ((uint64_t)1 << 32)) {
+        int rc = launch_stream_chunks(pending, np, opt, tl_slot, st);
+        if (rc) return rc;
+        np = 0;
+        pending_units = 0;
+      }
+      pending[np++] = c;
+      pending_units += cu;
+    }
+  }
+  if (np) return launch_stream_chunks(pending, np, opt, tl_slot, st);
   return TFR_OK;
 }
 

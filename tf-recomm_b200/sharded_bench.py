@@ -1,0 +1,213 @@
+"""bench.py --gpus N (N >= 2): BASELINE configs[4] -- SVD dim 128 on 100M users x 10M items, global batch 65536,
+tables + Adam state row-sharded (id mod N) over the N GPUs of one box, one process per GPU (torchrun).
+
+Strong scaling: the workload is the same at every N (340.6 GB of table traffic per step in total, 170 GB of state),
+so the baseline is the 2-GPU run -- the state does not fit one 180 GB GPU.  Per step and rank:
+all-gather of the batch slices (NCCL), owner-side row gather (kernel), all-reduce of the gathered rows (NCCL over
+NVLink), then the single-GPU kernels on the local shard.  Timed with CUDA events between barriers, max over ranks.
+"""
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+SHARDED = dict(U=100_000_000, I=10_000_000, N=2_000_000_000, d=128, B=65536, config="configs[4]")
+LR, REG = 1e-3, 0.05
+
+
+def _draw_slice(torch, gen, n, U, I, device):
+    """This rank's slice of the global batch, drawn on the device (no 2B-row host array): users
+    uniform, items skewed (cube of a uniform: a few hot items collect most ratings)."""
+    users = torch.randint(0, U, (n,), generator=gen, device=device, dtype=torch.int64).to(torch.int32)
+    u = torch.rand(n, generator=gen, device=device, dtype=torch.float64)
+    items = torch.clamp((u * u * u * I).to(torch.int64), max=I - 1).to(torch.int32)
+    rates = torch.randint(1, 6, (n,), generator=gen, device=device).to(torch.float32)
+    return users, items, rates
+
+
+def reference_line(args, world, bench):
+    """CPU restatement on a bounded sample: tables scaled down by `scale` (the step time of the TF path is
+    dominated by the table-wide Adam passes, i.e. proportional to the parameter count), same batch."""
+    scale = 64
+    w = dict(U=SHARDED["U"] // scale, I=SHARDED["I"] // scale, d=SHARDED["d"], B=SHARDED["B"], config=SHARDED["config"])
+    steps = min(args.steps or 3, 3)
+    tot, n = bench.cpu_reference_run(w, steps, 1)
+    t_full = tot / n * scale
+    val = SHARDED["B"] / t_full
+    cores = os.cpu_count()
+    return {
+        "impl": "reference", "metric": "train ratings/sec", "value": val, "unit": "ratings/s", "n_gpus": world,
+        "steps": n, "warmup": 1, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "sharded_100Mx10M_d128_b65536", "baseline_config": SHARDED["config"],
+                   "users": SHARDED["U"], "items": SHARDED["I"], "dim": SHARDED["d"], "batch": SHARDED["B"]},
+        "cpu_baseline": {"value": val, "unit": "ratings/s", "cores": cores, "kind": "port",
+                         "sample": "%d train steps (batch 65536) of oracle/tfr_oracle.c (OpenMP, %d threads) on tables "
+                                   "scaled down %dx (%d x %d: the full 170 GB state does not fit host memory); step time "
+                                   "multiplied by %d because the TF path's cost is the table-wide Adam passes"
+                                   % (n, cores, scale, w["U"], w["I"], scale)},
+        "e2e": {"value": val, "unit": "ratings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main(args):
+    import bench
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(reference_line(args, max(world, args.gpus), bench)))
+        return
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from ._lib import check
+    from .sharded import ShardedSvdEngine
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
+    assert torch.cuda.is_available(), "bench.py needs CUDA devices; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+    w = dict(SHARDED)
+    if os.environ.get("TFR_SHARDED_SCALE"):       # smaller tables for smoke runs: TFR_SHARDED_SCALE=100
+        s = int(os.environ["TFR_SHARDED_SCALE"])
+        w["U"], w["I"] = w["U"] // s, w["I"] // s
+    B, d = w["B"], w["d"]
+    steps = args.steps or 30
+    warmup = max(args.warmup, 3)
+    eng = ShardedSvdEngine(w["U"], w["I"], d, LR, REG, rank, world, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(13575 + rank)
+    lo, hi = eng_slice(B, world, rank)
+    slices = [_draw_slice(torch, gen, hi - lo, w["U"], w["I"], dev) for _ in range(warmup + steps)]
+    for k in range(warmup):
+        eng.train_step_from_slices(*slices[k])
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = bench.ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(warmup, warmup + steps):
+        eng.train_step_from_slices(*slices[k])
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    secs = float(ms.item()) / 1e3
+    clocks = sampler.stop() if sampler else None
+
+    # roofline of the dominant kernel (the local Adam pass), timed live with events inside complete steps
+    pass_ms, n_pass = 0.0, min(steps, 5)
+    bufs = eng._buffers(B)
+    for k in range(n_pass):
+        us, it, rt = slices[warmup + k]
+        parts = torch.stack([us.view(torch.float32), it.view(torch.float32), rt])
+        out = torch.empty((world,) + tuple(parts.shape), dtype=parts.dtype, device=dev)
+        dist.all_gather_into_tensor(out, parts)
+        gu = out[:, 0].reshape(-1).view(torch.int32).contiguous()
+        gi = out[:, 1].reshape(-1).view(torch.int32).contiguous()
+        gr = out[:, 2].reshape(-1).contiguous()
+        eng.gather_owned(gu, gi, bufs)
+        dist.all_reduce(bufs["flat"])
+        pass_ms += timed_local_step(eng, bufs, gr, torch, _lib, check)
+    pass_ms /= n_pass
+    params_local = (eng.U_loc + eng.I_loc) * (d + 1)
+    peak, peak_src = bench.measured_peaks()
+    pass_gbs = 24.0 * params_local / (pass_ms / 1e3) / 1e9
+    t = torch.tensor([pass_gbs], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    pass_gbs = float(t.item())
+
+    # e2e: each rank's slice comes from pinned host memory, its slice of the predictions goes back
+    n_e2e = min(steps, 10)
+    host = [tuple(x.cpu().pin_memory() for x in s) for s in slices[:n_e2e]]
+    pred_host = torch.empty(hi - lo, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    for hs in host:
+        ds = [x.to(dev, non_blocking=True) for x in hs]
+        _, infer = eng.train_step_from_slices(*ds)
+        pred_host.copy_(infer[lo:hi], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_val = B * n_e2e / float(dt.item())
+
+    if rank == 0:
+        bytes_step = 24 * (w["U"] + w["I"]) * (d + 1) + 8 * B * (d + 1) + 12 * B
+        line = {
+            "metric": "train ratings/sec", "value": B * steps / secs, "unit": "ratings/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": secs / steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "sharded_100Mx10M_d128_b65536", "baseline_config": w["config"], "users": w["U"],
+                       "items": w["I"], "dim": d, "batch": B, "ratings": w["N"], "sharding": "rows id mod %d" % world,
+                       "model": "README: squared error + L2 + Adam (TF IndexedSlices semantics)",
+                       "scaling_baseline": "n_gpus=2: the 170 GB of tables + Adam state do not fit one 180 GB GPU",
+                       "l2_policy": "local shard %.1f GB per step >> 126 MB L2: no flush needed" % (24 * params_local / 1e9),
+                       "timing": "CUDA events between barriers, max over ranks"},
+            "hbm": {"algorithmic_bytes_per_step": bytes_step, "achieved_gbs_per_gpu": bytes_step / world / (secs / steps) / 1e9,
+                    "frac_of_measured_peak": bytes_step / world / (secs / steps) / 1e9 / peak, "peak_gbs": peak,
+                    "peak_source": peak_src},
+            "roofline": {"bound": "hbm", "kernel": "adam_stream_multi_kernel (local shard, min over ranks)",
+                         "achieved": pass_gbs, "peak": peak, "unit": "GB/s", "frac": pass_gbs / peak,
+                         "peak_source": peak_src, "bytes_per_launch": 24.0 * params_local, "launch_ms": pass_ms,
+                         "traffic": None},
+            "comm": {"per_rank_bytes_per_step": eng.exchange_bytes(B), "collectives": "all_gather(ids) + all_reduce(rows) [NCCL]"},
+            "cpu_baseline": None,
+            "e2e": {"value": e2e_val, "unit": "ratings/s", "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 4 * B,
+                    "steps": n_e2e, "path": "ShardedSvdEngine.train_step_from_slices with pinned host slices"},
+            "clocks": clocks, "gpu_launches": (2 + 6) * steps,
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def eng_slice(B, world, rank):
+    from . import sharding
+    return sharding.batch_slice(B, world, rank)
+
+
+def timed_local_step(eng, bufs, rates, torch, _lib, check):
+    """One local step issued piecewise so that CUDA events bracket the Adam pass alone; returns its ms."""
+    e, L = eng.local, eng.L
+    B, d = rates.numel(), eng.d
+    t = bufs["tables"]
+    tp = C.byref(t)
+    ws_t = e.workspace(B)
+    ws = e.step_ws(B)
+    st = e._stream()
+    opt = e.opt.data_ptr()
+    ku, ki = bufs["key_u"].data_ptr(), bufs["key_i"].data_ptr()
+    check(L.tfr_svd_begin_step(opt, st))
+    check(L.tfr_svd_fwd_err(tp, opt, ku, ki, rates.data_ptr(), B, bufs["logits"].data_ptr(), bufs["infer"].data_ptr(),
+                            C.byref(ws), st))
+    check(L.tfr_dedup_sort_pairs(ku, eng.U_loc + 1, ws.su_ids, ws.su_pos, ki, eng.I_loc + 1, ws.si_ids, ws.si_pos, B,
+                                 ws.sort_ws, ws.sort_ws_bytes, st))
+    check(L.tfr_svd_segment_grads(tp, opt, ku, ki, B, C.byref(ws), st))
+    T, S = e.t, e.slots
+    arr = (_lib.AdamTable * 4)()
+    for k, (tab, rows, width, slot, gsum) in enumerate((("user_feat", eng.U_loc, d, e.user_slot, ws.gsum_uf),
+                                                        ("item_feat", eng.I_loc, d, e.item_slot, ws.gsum_if),
+                                                        ("user_bias", eng.U_loc, 1, e.user_slot, ws.gsum_ub),
+                                                        ("item_bias", eng.I_loc, 1, e.item_slot, ws.gsum_ib))):
+        arr[k].var, arr[k].m, arr[k].v = T[tab].data_ptr(), S["m_" + tab].data_ptr(), S["v_" + tab].data_ptr()
+        arr[k].rows, arr[k].width, arr[k].slot, arr[k].gsum = rows, width, slot.data_ptr(), gsum
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(L.tfr_adam_stream_multi(arr, 4, opt, 15, st))
+    e1.record()
+    import bench
+    check(L.tfr_svd_finish_step(tp, opt, ku, ki, B, C.byref(ws), bench._n_partials(d, B), st))
+    torch.cuda.synchronize()
+    del ws_t
+    return e0.elapsed_time(e1)
