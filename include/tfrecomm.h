@@ -118,8 +118,9 @@ int tfr_svd_forward(const tfr_svd_tables* t, const int32_t* users, const int32_t
 /* ---- batch assembly: replaces dataio.ShuffleIterator.next (dataio.py:114-117) on the device ---
  * cols_* are the training columns resident in HBM; row_index holds the pre-drawn MT19937
  * `np.random.randint(0, N, B)` stream for many steps (generated on the host so that it is the
- * reference's stream).  Batch k = rows row_index[k*B .. k*B+B).  If batch_index < 0 the batch
- * number is read from opt->batch_cursor (graph replay).  Also computes lr_t for this step. */
+ * reference's stream).  Batch k = rows row_index[k*B .. k*B+B).  batch_index >= 0 selects that batch;
+ * batch_index = -1-k selects batch (opt->batch_cursor + k): -1 = this step's batch (graph replay), -2 = the
+ * NEXT step's batch, assembled ahead under the current step's table pass. */
 int tfr_svd_batch_assemble(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* col_user,
                            const int32_t* col_item, const float* col_rate, const int64_t* row_index,
                            int64_t batch_index, int64_t B, int32_t* users, int32_t* items, float* rates,
@@ -153,6 +154,21 @@ int tfr_unique_first_occurrence(const int32_t* sorted_ids, const int32_t* sorted
  * (A.7).  users/items/rates are the assembled batch (device).  Advances opt->global_step,
  * beta powers and batch_cursor; leaves the slot maps at -1. */
 int64_t tfr_svd_step_workspace_bytes(int64_t B, int32_t dim);
+/* The id-only half of a step, for the NEXT batch, to be run on a side stream under the current step's table pass:
+ * tfr_svd_batch_assemble(batch_index) into users/items/rates + tfr_dedup_sort_pairs into `workspace`'s sorted-pair
+ * buffers.  tfr_svd_train_step_presorted then runs the rest (forward -> segment sums -> Adam pass -> finish) on
+ * a workspace prepared that way. */
+int tfr_svd_prefetch_batch(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* col_user,
+                           const int32_t* col_item, const float* col_rate, const int64_t* row_index,
+                           int64_t batch_index, int64_t B, int32_t* users, int32_t* items, float* rates,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+/* phases: 1 = forward + segment sums (read the tables), 2 = Adam pass / SGD slice + finish (write them), 3 = both.
+ * A caller that prefetches the next batch forks its side stream between the two phases, so that the id-only work
+ * runs under the bandwidth-bound pass instead of beside the latency-bound gathers. */
+int tfr_svd_train_step_presorted(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
+                                 const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
+                                 int32_t flags, int32_t var_mask, int32_t phases, void* workspace,
+                                 int64_t workspace_bytes, void* stream);
 /* flags / var_mask must equal what tfr_opt_init was given (the host copy selects the launches, the
  * device copy drives the kernels).  side_streams (optional; n_side = 0..1): [0] runs the id sort next to the
  * forward.  Fork/join is by events, so the whole step is still capturable as one graph from `stream`. */

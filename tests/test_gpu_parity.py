@@ -334,12 +334,17 @@ def test_stream_graph_matches_host_fed():
     eng_a, orc = both(U, I, d, 1e-3, 0.05)
     eng_b, _ = both(U, I, d, 1e-3, 0.05)
     eng_c, _ = both(U, I, d, 1e-3, 0.05)
-    for e in (eng_b, eng_c):
+    eng_d, _ = both(U, I, d, 1e-3, 0.05)
+    eng_e, _ = both(U, I, d, 1e-3, 0.05)
+    for e in (eng_b, eng_c, eng_d, eng_e):
         e.set_train_data(cu, ci, cr)
         e.set_index_stream(row_index, B)
         e.set_se_ring(steps)
-    eng_b.run_stream_steps(steps, use_graph=True)
-    eng_c.run_stream_steps(steps, use_graph=False)
+    eng_b.run_stream_steps(steps, use_graph=True)                    # pipelined (next batch sorted ahead), graphs
+    eng_c.run_stream_steps(steps, use_graph=False)                   # pipelined, eager
+    eng_d.run_stream_steps(steps, use_graph=True, pipeline=False)    # one plain graph per step
+    eng_e.run_stream_steps(3, use_graph=True)                        # pipelined, in two calls (re-uses the primed set)
+    eng_e.run_stream_steps(steps - 3, use_graph=True)
     se_ref = []
     for s in range(steps):
         rows = row_index[s * B:(s + 1) * B]
@@ -348,10 +353,12 @@ def test_stream_graph_matches_host_fed():
         np.testing.assert_allclose(out[1], ref_infer, rtol=RTOL, atol=1e-6)
         se_ref.append(np.sum((cr[rows].astype(np.float64) - ref_infer.astype(np.float64)) ** 2))
     torch.cuda.synchronize()
-    ta, tb, tc = eng_a.get_tables(), eng_b.get_tables(), eng_c.get_tables()
-    for n in ta:
-        assert np.array_equal(ta[n], tb[n]), n    # same kernels, same order: bit-identical
-        assert np.array_equal(ta[n], tc[n]), n
+    ta = eng_a.get_tables()
+    for other in (eng_b, eng_c, eng_d, eng_e):
+        to = other.get_tables()
+        for n in ta:
+            assert np.array_equal(ta[n], to[n]), n    # same kernels, same order: bit-identical
+        assert other.global_step == steps
     assert eng_b.global_step == steps
     np.testing.assert_allclose(eng_b.se_ring.cpu().numpy(), np.array(se_ref), rtol=1e-5)
 

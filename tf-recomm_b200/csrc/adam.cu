@@ -291,6 +291,10 @@ __global__ void __launch_bounds__(256) finish_step_kernel(tfr_svd_tables t, tfr_
       if (!sgd) {  // TF: adam.py::_finish
         opt->beta1_power = mul_rn(opt->beta1_power, opt->beta1);
         opt->beta2_power = mul_rn(opt->beta2_power, opt->beta2);
+        // lr_t of the NEXT step (TF: _apply_sparse_shared recomputes it from the advanced powers), so that a step
+        // needs no kernel in front of the forward
+        float tt = sqrt_rn(sub_rn(1.0f, opt->beta2_power));
+        opt->lr_t = div_rn(mul_rn(opt->lr, tt), sub_rn(1.0f, opt->beta1_power));
       }
       opt->global_step += 1;
       opt->batch_cursor += 1;
@@ -336,23 +340,26 @@ static int launch_stream_chunks(const StreamTab* chunks, int n_chunks, const tfr
   }
   a.n_tabs = n_chunks;
   a.total_units = (uint32_t)units;
-  // persistent grid: 2 CTAs x 512 threads per SM, 2 units per thread and trip (measured best: ~6 TB/s)
-  static int cfg_ctas = -1, cfg_unroll = 0;
+  // persistent grid: 2 CTAs x 512 threads x 64 registers per SM, 2 units per thread and trip: 5.9 TB/s in situ.
+  // (3 x 256 leaves room for another kernel's CTAs beside it but measures 7 % slower: TFR_STREAM_* to experiment.)
+  static int cfg_ctas = -1, cfg_unroll = 0, cfg_threads = 512;
   if (cfg_ctas < 0) {
     const char* e1 = getenv("TFR_STREAM_CTAS_PER_SM");
     const char* e2 = getenv("TFR_STREAM_UNROLL");
+    const char* e3 = getenv("TFR_STREAM_THREADS");
     cfg_ctas = e1 ? atoi(e1) : 2;
     cfg_unroll = e2 ? atoi(e2) : 2;
+    cfg_threads = e3 ? atoi(e3) : 512;
   }
-  int64_t grid = ((int64_t)units + 512 * cfg_unroll - 1) / (512 * cfg_unroll);
+  int64_t grid = ((int64_t)units + cfg_threads * cfg_unroll - 1) / (cfg_threads * cfg_unroll);
   const int64_t cap = (int64_t)sm_count() * cfg_ctas;
   if (cfg_ctas > 0 && grid > cap) grid = cap;
   if (cfg_unroll >= 4) {
     TFR_PREP(adam_stream_multi_kernel<4>);
-    adam_stream_multi_kernel<4><<<(unsigned)grid, 512, 0, st>>>(a, opt, tl_slot);
+    adam_stream_multi_kernel<4><<<(unsigned)grid, cfg_threads, 0, st>>>(a, opt, tl_slot);
   } else {
     TFR_PREP(adam_stream_multi_kernel<2>);
-    adam_stream_multi_kernel<2><<<(unsigned)grid, 512, 0, st>>>(a, opt, tl_slot);
+    adam_stream_multi_kernel<2><<<(unsigned)grid, cfg_threads, 0, st>>>(a, opt, tl_slot);
   }
   TFR_LAUNCH_CHECK();
   return TFR_OK;

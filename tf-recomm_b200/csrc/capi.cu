@@ -149,10 +149,10 @@ extern "C" int tfr_svd_step_carve(void* workspace, int64_t workspace_bytes, int6
 //   S0: finish
 static cudaEvent_t g_ev[2] = {nullptr, nullptr};
 
-extern "C" int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
-                                  const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
-                                  int32_t flags, int32_t var_mask, void* workspace, int64_t workspace_bytes,
-                                  void* stream, void* const* side_streams, int32_t n_side) {
+static int run_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users, const int32_t* items,
+                    const float* rates, int64_t B, float* logits, float* infer, int32_t flags, int32_t var_mask,
+                    void* workspace, int64_t workspace_bytes, void* stream, void* const* side_streams, int32_t n_side,
+                    bool presorted, int phases = 3) {
   TFR_CHECK_ARG(t && opt && users && items && rates && B > 0 && t->dim > 0);
   TFR_CHECK_ARG(n_side >= 0 && n_side <= 1 && (n_side == 0 || side_streams));
   // flags / var_mask repeat what the caller gave tfr_opt_init: the device copy drives the kernels, the
@@ -164,8 +164,9 @@ extern "C" int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt,
   int rc = tfr_svd_step_carve(workspace, workspace_bytes, B, t->dim, &ws);
   if (rc) return rc;
   cudaStream_t s0 = (cudaStream_t)stream;
-  cudaStream_t sorts = n_side > 0 ? (cudaStream_t)side_streams[0] : s0;
+  cudaStream_t sorts = (n_side > 0 && !presorted) ? (cudaStream_t)side_streams[0] : s0;
   const int dim = t->dim;
+  if (!(phases & 1)) goto phase2;
   if (sorts != s0) {
     if (!g_ev[0])
       for (int i = 0; i < 2; ++i) TFR_CUDA(cudaEventCreateWithFlags(&g_ev[i], cudaEventDisableTiming));
@@ -173,9 +174,9 @@ extern "C" int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt,
     TFR_CUDA(cudaStreamWaitEvent(sorts, g_ev[0], 0));
   }
   // + 1: in row-sharded mode the value user_num / item_num itself occurs (the "not mine" mark)
-  if ((rc = tfr_dedup_sort_pairs_tl(users, (int64_t)t->user_num + 1, ws.su_ids, ws.su_pos, items,
-                                    (int64_t)t->item_num + 1, ws.si_ids, ws.si_pos, B, ws.sort_ws,
-                                    ws.sort_ws_bytes, opt, sorts)))
+  if (!presorted && (rc = tfr_dedup_sort_pairs_tl(users, (int64_t)t->user_num + 1, ws.su_ids, ws.su_pos, items,
+                                                  (int64_t)t->item_num + 1, ws.si_ids, ws.si_pos, B, ws.sort_ws,
+                                                  ws.sort_ws_bytes, opt, sorts)))
     return rc;
   if ((rc = tfr_svd_fwd_err(t, opt, users, items, rates, B, logits, infer, &ws, s0))) return rc;
   if (sorts != s0) {
@@ -183,6 +184,8 @@ extern "C" int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt,
     TFR_CUDA(cudaStreamWaitEvent(s0, g_ev[1], 0));
   }
   if ((rc = tfr_svd_segment_grads(t, opt, users, items, B, &ws, s0))) return rc;
+phase2:
+  if (!(phases & 2)) return TFR_OK;
   if (!sgd) {
     tfr_adam_table tabs[4];
     int nt = 0;
@@ -205,6 +208,39 @@ extern "C" int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt,
     if (ns && (rc = tfr_adam_slice_multi(sides, ns, dim, B, opt, 1, TFR_TL_TOUCHED_U, s0))) return rc;
   }
   return tfr_svd_finish_step(t, opt, users, items, B, &ws, fwd_err_n_partials(dim, B), s0);
+}
+
+extern "C" int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
+                                  const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
+                                  int32_t flags, int32_t var_mask, void* workspace, int64_t workspace_bytes,
+                                  void* stream, void* const* side_streams, int32_t n_side) {
+  return run_step(t, opt, users, items, rates, B, logits, infer, flags, var_mask, workspace, workspace_bytes, stream,
+                  side_streams, n_side, false);
+}
+
+extern "C" int tfr_svd_train_step_presorted(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
+                                            const int32_t* items, const float* rates, int64_t B, float* logits,
+                                            float* infer, int32_t flags, int32_t var_mask, int32_t phases,
+                                            void* workspace, int64_t workspace_bytes, void* stream) {
+  TFR_CHECK_ARG(phases >= 1 && phases <= 3);
+  return run_step(t, opt, users, items, rates, B, logits, infer, flags, var_mask, workspace, workspace_bytes, stream,
+                  nullptr, 0, true, phases);
+}
+
+extern "C" int tfr_svd_prefetch_batch(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* col_user,
+                                      const int32_t* col_item, const float* col_rate, const int64_t* row_index,
+                                      int64_t batch_index, int64_t B, int32_t* users, int32_t* items, float* rates,
+                                      void* workspace, int64_t workspace_bytes, void* stream) {
+  TFR_CHECK_ARG(t && B > 0 && t->dim > 0);
+  tfr_svd_step_ws ws;
+  int rc = tfr_svd_step_carve(workspace, workspace_bytes, B, t->dim, &ws);
+  if (rc) return rc;
+  if ((rc = tfr_svd_batch_assemble(t, opt, col_user, col_item, col_rate, row_index, batch_index, B, users, items,
+                                   rates, stream)))
+    return rc;
+  return tfr_dedup_sort_pairs_tl(users, (int64_t)t->user_num + 1, ws.su_ids, ws.su_pos, items,
+                                 (int64_t)t->item_num + 1, ws.si_ids, ws.si_pos, B, ws.sort_ws, ws.sort_ws_bytes, opt,
+                                 stream);
 }
 
 // ---- CUDA graphs ------------------------------------------------------------------------------------------

@@ -2,7 +2,7 @@
 // replaces TF optimizer.py::_deduplicate_indexed_slices (tf.unique + tf.unsorted_segment_sum; SURVEY
 // A.3, reached from ops.py:144/148 through Optimizer.minimize).
 //
-// One cooperative launch sorts TWO independent key arrays (the batch's user ids and item ids): the
+// One launch sorts TWO independent key arrays (the batch's user ids and item ids): the
 // first half of the grid owns problem A, the second half problem B, and both advance through the
 // digit passes (<= 9 bits each: 2 passes for the 18-bit ids of ML-25M) in lock step with grid-wide barriers.  Per pass: (a) per-CTA digit histogram of
 // the CTA's contiguous chunk, (b) grid barrier, (c) every CTA derives its own scatter bases from all
@@ -11,15 +11,26 @@
 // warps' counters.  Because positions start as 0..n-1 and every pass is stable, equal ids end up in
 // ascending position = batch order, which is what makes the segment sums reproduce
 // unsorted_segment_sum's in-order adds.
-#include <cooperative_groups.h>
-
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace tfr {
 
-constexpr int SORT_THREADS = 512;
+// Grid-wide barrier of a grid whose CTAs all become resident (<= 128 CTAs of 512 threads on 148 SMs, and no
+// kernel that can run beside this one waits on it).  A plain launch + this barrier instead of a cooperative
+// launch: the driver gang-schedules cooperative grids only onto an otherwise idle GPU, which kept the next
+// batch's sort from running under the current step's table pass (measured with tools/timeline.py).
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) __nanosleep(32);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+constexpr int SORT_THREADS = 256;  // 8 warps, ~8K registers per CTA: fits beside the table pass's 3 x 256 x 64
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int RADIX_BITS_MAX = 9;           // digit width is chosen per call: ceil(key bits / passes) <= 9
 constexpr int RADIX = 1 << RADIX_BITS_MAX;  // 512 bins -> 18-bit ids (ML-25M) in 2 passes, 27-bit (1e8) in 3
@@ -36,13 +47,14 @@ struct SortProblem {
 
 __global__ void __launch_bounds__(SORT_THREADS) dedup_sort_kernel(SortProblem pa, SortProblem pb, int bpp, int n_passes,
                                                                   int digit_bits, uint32_t* __restrict__ hist_g,
-                                                                  const tfr_opt_scalars* __restrict__ opt) {
+                                                                  const tfr_opt_scalars* __restrict__ opt,
+                                                                  unsigned int* __restrict__ barrier) {
   TlScope tl_scope(opt, TFR_TL_SORT);
-  cg::grid_group grid = cg::this_grid();
+  unsigned int epoch = 0;
   __shared__ uint32_t s_wc[SORT_WARPS][RADIX];
   __shared__ uint32_t s_base[RADIX];
-  __shared__ uint32_t s_scan[RADIX / 32];
-  static_assert(RADIX <= SORT_THREADS, "one thread per digit");
+  __shared__ uint32_t s_scan[SORT_WARPS];
+  static_assert(RADIX % SORT_THREADS == 0, "whole digits per thread");
 
   const int prob = blockIdx.x / bpp;
   const int blk = blockIdx.x % bpp;
@@ -70,7 +82,7 @@ __global__ void __launch_bounds__(SORT_THREADS) dedup_sort_kernel(SortProblem pa
     int32_t* dst_pos = to_out ? p.out_pos : p.tmp_pos;
 
     // (a) histogram of my chunk
-    if (tid < RADIX) s_base[tid] = 0;
+    for (int dg = tid; dg < RADIX; dg += SORT_THREADS) s_base[dg] = 0;
     __syncthreads();
     for (int64_t i0 = begin; i0 < end; i0 += SORT_THREADS) {
       const int64_t i = i0 + tid;
@@ -80,32 +92,40 @@ __global__ void __launch_bounds__(SORT_THREADS) dedup_sort_kernel(SortProblem pa
       if (valid && (peers & lt_mask) == 0) atomicAdd(&s_base[digit], __popc(peers));
     }
     __syncthreads();
-    if (tid < RADIX) my_hist[tid] = s_base[tid];
-    grid.sync();
+    for (int dg = tid; dg < RADIX; dg += SORT_THREADS) my_hist[dg] = s_base[dg];
+    grid_barrier(barrier, ++epoch * gridDim.x);
 
-    // (c) my scatter bases: exclusive scan over digits of the problem-wide totals + lower CTAs' counts
-    uint32_t tot = 0, mine = 0;
-    if (tid < RADIX) {
-      const uint32_t* h = hist_g + (size_t)prob * bpp * RADIX + tid;
+    // (c) my scatter bases: exclusive scan over digits of the problem-wide totals + lower CTAs' counts.
+    // Thread tid owns the DPT consecutive digits tid*DPT .. tid*DPT+DPT-1.
+    constexpr int DPT = RADIX / SORT_THREADS;
+    uint32_t tot[DPT], mine[DPT];
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) {
+      const int dg = tid * DPT + j;
+      const uint32_t* h = hist_g + (size_t)prob * bpp * RADIX + dg;
+      uint32_t t_ = 0, m_ = 0;
       for (int b = 0; b < bpp; ++b) {
         const uint32_t c = h[(size_t)b * RADIX];
-        if (b < blk) mine += c;
-        tot += c;
+        if (b < blk) m_ += c;
+        t_ += c;
       }
-      uint32_t incl = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-      }
-      if (lane == 31) s_scan[warp] = incl;
-      tot = incl - tot;  // exclusive within the warp
+      tot[j] = t_; mine[j] = m_; tsum += t_;
     }
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_scan[warp] = incl;
     __syncthreads();
-    if (tid < RADIX) {
-      uint32_t off = 0;
-      for (int w = 0; w < warp; ++w) off += s_scan[w];
-      s_base[tid] = tot + off + mine;
+    uint32_t run0 = incl - tsum;
+    for (int w = 0; w < warp; ++w) run0 += s_scan[w];
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) {
+      s_base[tid * DPT + j] = run0 + mine[j];
+      run0 += tot[j];
     }
     __syncthreads();
 
@@ -121,14 +141,14 @@ __global__ void __launch_bounds__(SORT_THREADS) dedup_sort_kernel(SortProblem pa
       const bool leader = valid && lrank == 0;
       if (leader) s_wc[warp][digit] = __popc(peers);
       __syncthreads();
-      if (tid < RADIX) {
-        uint32_t run = s_base[tid];
+      for (int dg = tid; dg < RADIX; dg += SORT_THREADS) {
+        uint32_t run = s_base[dg];
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; ++w) {
-          const uint32_t c = s_wc[w][tid];
-          if (c) { s_wc[w][tid] = run; run += c; }
+          const uint32_t c = s_wc[w][dg];
+          if (c) { s_wc[w][dg] = run; run += c; }
         }
-        s_base[tid] = run;
+        s_base[dg] = run;
       }
       __syncthreads();
       if (valid) {
@@ -139,7 +159,7 @@ __global__ void __launch_bounds__(SORT_THREADS) dedup_sort_kernel(SortProblem pa
       __syncwarp();
       if (leader) s_wc[warp][digit] = 0;
     }
-    grid.sync();
+    grid_barrier(barrier, ++epoch * gridDim.x);
   }
 }
 
@@ -202,7 +222,7 @@ static int bits_for(int64_t max_id) {
 using namespace tfr;
 
 static int sort_bpp(int64_t n) {
-  int64_t bpp = (n + 2047) / 2048;
+  int64_t bpp = (n + 1023) / 1024;
   if (bpp < 1) bpp = 1;
   if (bpp > SORT_MAX_BPP) bpp = SORT_MAX_BPP;
   return (int)bpp;
@@ -210,7 +230,7 @@ static int sort_bpp(int64_t n) {
 
 extern "C" int64_t tfr_dedup_workspace_bytes(int64_t n) {
   if (n < 0) return TFR_ERR_INVALID;
-  return align_up(2 * SORT_MAX_BPP * RADIX * (int64_t)sizeof(uint32_t), 256) + 4 * align_up(n * 4, 256) + 256;
+  return 256 + align_up(2 * SORT_MAX_BPP * RADIX * (int64_t)sizeof(uint32_t), 256) + 4 * align_up(n * 4, 256) + 256;
 }
 
 extern "C" int tfr_dedup_sort_pairs(const int32_t* ids_a, int64_t max_id_a, int32_t* sorted_ids_a,
@@ -235,6 +255,8 @@ extern "C" int tfr_dedup_sort_pairs_tl(const int32_t* ids_a, int64_t max_id_a, i
     return TFR_ERR_WORKSPACE;
   }
   char* w = reinterpret_cast<char*>(align_up((int64_t)(uintptr_t)workspace, 256));
+  unsigned int* barrier = reinterpret_cast<unsigned int*>(w);
+  w += 256;
   uint32_t* hist = reinterpret_cast<uint32_t*>(w);
   w += align_up(2 * SORT_MAX_BPP * RADIX * (int64_t)sizeof(uint32_t), 256);
   const int64_t seg = align_up(n * 4, 256);
@@ -245,10 +267,11 @@ extern "C" int tfr_dedup_sort_pairs_tl(const int32_t* ids_a, int64_t max_id_a, i
   int n_passes = (bits + RADIX_BITS_MAX - 1) / RADIX_BITS_MAX;
   int digit_bits = (bits + n_passes - 1) / n_passes;
   int bpp = sort_bpp(n);
-  void* args[] = {&pa, &pb, &bpp, &n_passes, &digit_bits, &hist, &opt};
+  TFR_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned int), (cudaStream_t)stream));
   TFR_PREP(dedup_sort_kernel);
-  TFR_CUDA(cudaLaunchCooperativeKernel((const void*)dedup_sort_kernel, dim3(2 * bpp), dim3(SORT_THREADS), args, 0,
-                                       (cudaStream_t)stream));
+  dedup_sort_kernel<<<2 * bpp, SORT_THREADS, 0, (cudaStream_t)stream>>>(pa, pb, bpp, n_passes, digit_bits, hist, opt,
+                                                                        barrier);
+  TFR_LAUNCH_CHECK();
   return TFR_OK;
 }
 

@@ -8,8 +8,8 @@
 //   ops.py:124-126      d cost/d logits (squared error / sigmoid-CE)                 -> tfr::dloss
 //
 // Layout: warp lanes are split in groups of L lanes, one group per batch row; a lane owns VEC
-// consecutive floats of the row per pass (128-bit loads when dim % 4 == 0).  Two rows per group are
-// in flight to double the outstanding gathers.  Products and adds are separate fp32 roundings
+// consecutive floats of the row per pass (128-bit loads when dim % 4 == 0).  Four rows per group are
+// in flight (8 gathers outstanding per lane).  Products and adds are separate fp32 roundings
 // (tf.multiply then tf.reduce_sum), the lane-group butterfly fixes the reduction order.
 #include <string.h>
 
@@ -76,35 +76,82 @@ __global__ void __launch_bounds__(256) svd_forward_kernel(tfr_svd_tables t, cons
   float err_acc = 0.0f;
   double se_acc = 0.0;
 
-  // all lanes of a warp iterate the same number of times (shuffles inside row_dot need full warps)
+  // all lanes of a warp iterate the same number of times (the butterflies need full warps).  R rows per group
+  // are in flight: their 2*R row loads (and lane 0's bias / rating loads) are issued before any arithmetic.
+  constexpr int R = 4;
   const int64_t warp_first = group - (group % GPW);
-  for (int64_t b0 = warp_first; b0 < B; b0 += 2 * n_groups) {
-    const int64_t ba = b0 + (group % GPW), bb = ba + n_groups;
-    const bool va = ba < B, vb = bb < B;
-    // row-sharded mode: the batch's rows were gathered by position (t.g_*), otherwise gather by id
-    const int32_t ua = va ? (gathered ? (int32_t)ba : users[ba]) : 0, ia = va ? (gathered ? (int32_t)ba : items[ba]) : 0;
-    const int32_t ub = vb ? (gathered ? (int32_t)bb : users[bb]) : 0, ib = vb ? (gathered ? (int32_t)bb : items[bb]) : 0;
-    const float xa0 = row_dot<VEC, L>(uf + (size_t)ua * dim, itf + (size_t)ia * dim, dim, lane, abs_item);
-    const float xb0 = row_dot<VEC, L>(uf + (size_t)ub * dim, itf + (size_t)ib * dim, dim, lane, abs_item);
+  for (int64_t b0 = warp_first; b0 < B; b0 += R * n_groups) {
+    int64_t bs[R];
+    bool val[R];
+    int32_t uu[R], ii[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      bs[r] = b0 + (group % GPW) + r * n_groups;
+      val[r] = bs[r] < B;
+      // row-sharded mode: the batch's rows were gathered by position (t.g_*), otherwise gather by id
+      uu[r] = val[r] ? (gathered ? (int32_t)bs[r] : users[bs[r]]) : 0;
+      ii[r] = val[r] ? (gathered ? (int32_t)bs[r] : items[bs[r]]) : 0;
+    }
+    float bu[R], bi[R], zz[R];
     if (lane == 0) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const bool valid = h ? vb : va;
-        if (!valid) continue;
-        const int64_t b = h ? bb : ba;
-        const int32_t u = h ? ub : ua, i = h ? ib : ia;
-        float x = add_rn(h ? xb0 : xa0, mu);               // ops.py:45
-        x = add_rn(x, ld_gather_f1(ubias + u));            // ops.py:46
-        x = add_rn(x, ld_gather_f1(ibias + i));            // ops.py:47
+      for (int r = 0; r < R; ++r) {
+        bu[r] = ld_gather_f1(ubias + uu[r]);
+        bi[r] = ld_gather_f1(ibias + ii[r]);
+        zz[r] = (TRAIN && val[r]) ? rates[bs[r]] : 0.0f;
+      }
+    }
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0f;
+    if (VEC == 4) {
+      const int n4 = dim >> 2;
+      for (int k = lane; k < n4; k += L) {
+        float4 a[R], q[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          a[r] = ld_gather_f4(reinterpret_cast<const float4*>(uf + (size_t)uu[r] * dim) + k);
+          q[r] = ld_gather_f4(reinterpret_cast<const float4*>(itf + (size_t)ii[r] * dim) + k);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (abs_item) { q[r].x = fabsf(q[r].x); q[r].y = fabsf(q[r].y); q[r].z = fabsf(q[r].z); q[r].w = fabsf(q[r].w); }
+          acc[r] = add_rn(acc[r], mul_rn(a[r].x, q[r].x));
+          acc[r] = add_rn(acc[r], mul_rn(a[r].y, q[r].y));
+          acc[r] = add_rn(acc[r], mul_rn(a[r].z, q[r].z));
+          acc[r] = add_rn(acc[r], mul_rn(a[r].w, q[r].w));
+        }
+      }
+    } else {
+      for (int k = lane; k < dim; k += L) {
+        float a[R], q[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          a[r] = ld_gather_f1(uf + (size_t)uu[r] * dim + k);
+          q[r] = ld_gather_f1(itf + (size_t)ii[r] * dim + k);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = add_rn(acc[r], mul_rn(a[r], abs_item ? fabsf(q[r]) : q[r]));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = group_sum<L>(acc[r]);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!val[r]) continue;
+        const int64_t b = bs[r];
+        float x = add_rn(acc[r], mu);   // ops.py:45
+        x = add_rn(x, bu[r]);           // ops.py:46
+        x = add_rn(x, bi[r]);           // ops.py:47
         const float inf = head(flags, x);
         if (logits) logits[b] = x;
         if (infer) infer[b] = inf;
         if (TRAIN) {
-          const float z = rates[b];
-          const float e = dloss(flags, x, z);
+          const float e = dloss(flags, x, zz[r]);
           err[b] = e;
           err_acc = add_rn(err_acc, e);
-          const double dse = (double)z - (double)inf;
+          const double dse = (double)zz[r] - (double)inf;
           se_acc += dse * dse;
         }
       }
@@ -138,6 +185,8 @@ __device__ __forceinline__ void begin_step_scalars(tfr_opt_scalars* opt) {
   opt->lr_t = div_rn(tt, sub_rn(1.0f, opt->beta1_power));
 }
 
+__global__ void begin_step_kernel(tfr_opt_scalars* opt) { begin_step_scalars(opt); }
+
 __global__ void __launch_bounds__(256) batch_assemble_kernel(tfr_svd_tables t, tfr_opt_scalars* opt,
                                                              const int32_t* __restrict__ col_user,
                                                              const int32_t* __restrict__ col_item,
@@ -146,15 +195,16 @@ __global__ void __launch_bounds__(256) batch_assemble_kernel(tfr_svd_tables t, t
                                                              int64_t B, int32_t* __restrict__ users,
                                                              int32_t* __restrict__ items, float* __restrict__ rates) {
   TlScope tl_scope(opt, TFR_TL_ASSEMBLE);
-  const int64_t batch = batch_index >= 0 ? batch_index : opt->batch_cursor;
+  // batch_index >= 0: that batch; batch_index = -1-k: batch (opt->batch_cursor + k), k = 0 for "this step's",
+  // k = 1 when the NEXT step's batch is assembled ahead, under the current step's table pass
+  const int64_t batch = batch_index >= 0 ? batch_index : opt->batch_cursor + (-1 - batch_index);
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B && row_index) {
+  if (b < B) {
     const int64_t row = row_index[batch * B + b];
     users[b] = col_user[row];
     items[b] = col_item[row];
     rates[b] = col_rate[row];
   }
-  if (b == 0) begin_step_scalars(opt);
 }
 
 template <bool TRAIN>
@@ -162,7 +212,7 @@ static int launch_forward(const tfr_svd_tables* t, const tfr_opt_scalars* opt, c
                           const int32_t* items, const float* rates, int64_t B, int flags, float* logits, float* infer,
                           float* err, float* partials, double* se_partials, int* n_partials_out, cudaStream_t st) {
   const RowGeom g = row_geom(t->dim);
-  const int64_t rows_per_cta = 256 / g.lanes * 2;
+  const int64_t rows_per_cta = 256 / g.lanes * 4;
   int64_t grid = (B + rows_per_cta - 1) / rows_per_cta;
   const int64_t cap = TRAIN ? TFR_MAX_PARTIALS : (int64_t)sm_count() * 16;
   if (grid > cap) grid = cap;
@@ -185,7 +235,7 @@ static int launch_forward(const tfr_svd_tables* t, const tfr_opt_scalars* opt, c
 
 int fwd_err_n_partials(int dim, int64_t B) {
   const RowGeom g = row_geom(dim);
-  const int64_t rows_per_cta = 256 / g.lanes * 2;
+  const int64_t rows_per_cta = 256 / g.lanes * 4;
   int64_t grid = (B + rows_per_cta - 1) / rows_per_cta;
   if (grid > TFR_MAX_PARTIALS) grid = TFR_MAX_PARTIALS;
   if (grid < 1) grid = 1;
@@ -227,11 +277,7 @@ extern "C" int tfr_svd_batch_assemble(const tfr_svd_tables* t, tfr_opt_scalars* 
 
 extern "C" int tfr_svd_begin_step(tfr_opt_scalars* opt, void* stream) {
   TFR_CHECK_ARG(opt);
-  tfr_svd_tables none;
-  memset(&none, 0, sizeof(none));
-  TFR_PREP(batch_assemble_kernel);
-  batch_assemble_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(none, opt, nullptr, nullptr, nullptr, nullptr, 0, 1, nullptr,
-                                                            nullptr, nullptr);
+  begin_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(opt);
   TFR_LAUNCH_CHECK();
   return TFR_OK;
 }

@@ -76,6 +76,7 @@ class SvdEngine:
         self.data = None
         self.se_ring = None
         self.overlap = True
+        self._primed = None
 
     # ---- plumbing ---------------------------------------------------------------------------------------
     def _n_side(self):
@@ -97,12 +98,14 @@ class SvdEngine:
         s.user_slot, s.item_slot = self.user_slot.data_ptr(), self.item_slot.data_ptr()
         self.tables_struct = s
 
-    def workspace(self, B):
-        ws = self._ws.get(B)
+    def workspace(self, key):
+        """Step workspace for batch size `key` (or (B, slot) for the pipelined double buffer)."""
+        ws = self._ws.get(key)
         if ws is None:
+            B = key[0] if isinstance(key, tuple) else key
             nbytes = check(self.L.tfr_svd_step_workspace_bytes(B, self.d))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self._ws[B] = ws
+            self._ws[key] = ws
         return ws
 
     def step_ws(self, B):
@@ -194,16 +197,20 @@ class SvdEngine:
             ri = torch.from_numpy(np.ascontiguousarray(row_index, dtype=np.int64)).to(self.device)
         assert ri.numel() % B == 0
         # captured graphs bake the buffer's address: keep ONE persistent buffer and copy new streams into it
+        # (+ B zero entries of slack: the pipelined step assembles one batch past the end)
         cap = getattr(self, "_row_index_buf", None)
-        if cap is None or cap.numel() < ri.numel():
-            self._row_index_buf = torch.empty(max(ri.numel(), 1), dtype=torch.int64, device=self.device)
+        if cap is None or cap.numel() < ri.numel() + B:
+            self._row_index_buf = torch.zeros(ri.numel() + B, dtype=torch.int64, device=self.device)
             self._graphs.clear()
         self._row_index_buf[:ri.numel()].copy_(ri)
+        self._row_index_buf[ri.numel():].zero_()
+        self._primed = None
         self.row_index = self._row_index_buf
         self.stream_B = B
         self.set_batch_cursor(0)
 
     def set_batch_cursor(self, k):
+        self._primed = None
         off = OptScalars.batch_cursor.offset
         self.opt[off:off + 8].copy_(torch.tensor([k], dtype=torch.int64).view(torch.uint8))
 
@@ -232,6 +239,7 @@ class SvdEngine:
         return {self.TL_NAMES[k]: ((begin[k] - t0) / 1e3, (end[k] - t0) / 1e3) for k in live}
 
     def _enqueue_stream_step(self, B, bufs, batch_index=-1):
+        """assemble -> full step, one batch, everything on the current stream (+ the sort's side stream)."""
         st = self._stream()
         check(self.L.tfr_svd_batch_assemble(C.byref(self.tables_struct), self.opt.data_ptr(),
                                             self.data["user"].data_ptr(), self.data["item"].data_ptr(),
@@ -244,8 +252,45 @@ class SvdEngine:
                                         bufs["logits"].data_ptr(), bufs["infer"].data_ptr(), self.flags,
                                         self.var_mask, ws.data_ptr(), ws.numel(), st, self._side_arr, self._n_side()))
 
-    def stream_buffers(self, B):
-        key = ("bufs", B)
+    def _prefetch(self, B, slot, k_ahead, stream_handle):
+        """Batch (cursor + k_ahead): assemble + id sort into buffer set `slot` (tfr_svd_prefetch_batch)."""
+        bufs, ws = self.stream_buffers(B, slot), self.workspace((B, slot))
+        check(self.L.tfr_svd_prefetch_batch(C.byref(self.tables_struct), self.opt.data_ptr(),
+                                            self.data["user"].data_ptr(), self.data["item"].data_ptr(),
+                                            self.data["rate"].data_ptr(), self.row_index.data_ptr(), -1 - k_ahead, B,
+                                            bufs["users"].data_ptr(), bufs["items"].data_ptr(),
+                                            bufs["rates"].data_ptr(), ws.data_ptr(), ws.numel(), stream_handle))
+
+    def _enqueue_pipelined_step(self, B, slot):
+        """Step on the batch already assembled + sorted in set `slot`, while the NEXT batch is assembled + sorted
+        into the other set on the side stream: the id-only work leaves the critical path (it runs under the
+        bandwidth-bound table pass, which it barely disturbs)."""
+        main = torch.cuda.current_stream(self.device)
+        side = self.side_streams[0]
+        bufs, ws = self.stream_buffers(B, slot), self.workspace((B, slot))
+
+        def phase(p):
+            check(self.L.tfr_svd_train_step_presorted(C.byref(self.tables_struct), self.opt.data_ptr(),
+                                                      bufs["users"].data_ptr(), bufs["items"].data_ptr(),
+                                                      bufs["rates"].data_ptr(), B, bufs["logits"].data_ptr(),
+                                                      bufs["infer"].data_ptr(), self.flags, self.var_mask, p,
+                                                      ws.data_ptr(), ws.numel(), main.cuda_stream))
+        # Where to fork the next batch's assemble + sort: UNDER the table pass when that pass is long (it is
+        # bandwidth-bound and barely notices them, while the latency-bound gathers of phase 1 would slow down
+        # beside them); at the start of the step when the tables are small and the pass is a few microseconds.
+        small = 24 * (self.U + self.I) * (self.d + 1) < 64e6
+        if small:
+            side.wait_stream(main)
+            self._prefetch(B, 1 - slot, 1, side.cuda_stream)
+        phase(1)                      # forward + segment sums
+        if not small:
+            side.wait_stream(main)
+            self._prefetch(B, 1 - slot, 1, side.cuda_stream)
+        phase(2)                      # Adam pass + finish
+        main.wait_stream(side)
+
+    def stream_buffers(self, B, slot=0):
+        key = ("bufs", B, slot)
         b = self._stage.get(key)
         if b is None:
             dev = self.device
@@ -257,37 +302,68 @@ class SvdEngine:
             self._stage[key] = b
         return b
 
-    def run_stream_steps(self, n_steps, use_graph=True):
-        """Runs n_steps train steps on batches drawn by the device-resident index stream, starting at the
-        current batch_cursor.  With use_graph the whole step (assemble -> ... -> finish) is ONE captured CUDA
-        graph replayed n_steps times: no per-step host work besides the graph launch."""
+    def _capture(self, fn):
+        cap = torch.cuda.Stream(device=self.device)
+        cap.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(cap):
+            check(self.L.tfr_graph_begin_capture(cap.cuda_stream))
+            try:
+                fn()
+            finally:
+                exe = C.c_void_p()
+                rc = self.L.tfr_graph_end_capture(cap.cuda_stream, C.byref(exe))
+            check(rc)
+        torch.cuda.current_stream(self.device).wait_stream(cap)
+        return exe
+
+    def run_stream_steps(self, n_steps, use_graph=True, pipeline=None):
+        """Runs n_steps train steps on batches drawn by the device-resident index stream, starting at the current
+        batch_cursor.  With use_graph every step is ONE replay of a captured CUDA graph (no per-step host work
+        besides the launch).  With pipeline the graph of step t also assembles and sorts batch t+1 on a side stream
+        (two buffer sets, two graphs alternating).  Returns the buffer set of the LAST step (logits / infer of the
+        pre-update tables)."""
         B = self.stream_B
-        bufs = self.stream_buffers(B)
+        if n_steps <= 0:
+            return self.stream_buffers(B, 0)
+        if pipeline is None:
+            # measured (tools/timeline.py): sorting the next batch ahead pays when the table pass is short (ML-1M
+            # shape: 67 -> 45 us/step); under a long pass it only competes with it (ML-25M shape: 215 vs 214 us)
+            pipeline = 24 * (self.U + self.I) * (self.d + 1) < 64e6
         with torch.cuda.device(self.device):
-            if not use_graph:
-                for _ in range(n_steps):
-                    self._enqueue_stream_step(B, bufs)
-                return bufs
-            g = self._graphs.get(B)
-            if g is None:
-                self.workspace(B)
-                cap = torch.cuda.Stream(device=self.device)
-                cap.wait_stream(torch.cuda.current_stream(self.device))
-                with torch.cuda.stream(cap):
-                    check(self.L.tfr_graph_begin_capture(cap.cuda_stream))
-                    try:
+            if not pipeline:
+                bufs = self.stream_buffers(B, 0)
+                self._primed = None
+                if not use_graph:
+                    for _ in range(n_steps):
                         self._enqueue_stream_step(B, bufs)
-                    finally:
-                        exe = C.c_void_p()
-                        rc = self.L.tfr_graph_end_capture(cap.cuda_stream, C.byref(exe))
-                    check(rc)
-                torch.cuda.current_stream(self.device).wait_stream(cap)
-                g = exe
-                self._graphs[B] = g
-            st = self._stream()
+                    return bufs
+                g = self._graphs.get((B, "plain"))
+                if g is None:
+                    self.workspace(B)
+                    g = self._graphs[(B, "plain")] = self._capture(lambda: self._enqueue_stream_step(B, bufs))
+                st = self._stream()
+                for _ in range(n_steps):
+                    check(self.L.tfr_graph_launch(g, st))
+                return bufs
+            for slot in (0, 1):
+                self.stream_buffers(B, slot)
+                self.workspace((B, slot))
+            slot = getattr(self, "_primed", None)
+            if slot is None:  # nothing assembled ahead for the batch at the cursor: prime set 0
+                slot = 0
+                self._prefetch(B, 0, 0, self._stream())
             for _ in range(n_steps):
-                check(self.L.tfr_graph_launch(g, st))
-        return bufs
+                if use_graph:
+                    g = self._graphs.get((B, "pipe", slot))
+                    if g is None:
+                        s_ = slot
+                        g = self._graphs[(B, "pipe", slot)] = self._capture(lambda: self._enqueue_pipelined_step(B, s_))
+                    check(self.L.tfr_graph_launch(g, self._stream()))
+                else:
+                    self._enqueue_pipelined_step(B, slot)
+                slot = 1 - slot
+            self._primed = slot  # set `slot` now holds the batch at the (advanced) cursor
+            return self.stream_buffers(B, 1 - slot)
 
     # ---- state access ------------------------------------------------------------------------------------
     def opt_scalars(self):
@@ -332,3 +408,4 @@ class SvdEngine:
             off = getattr(OptScalars, field).offset
             t = torch.tensor([val], dtype=dt).view(torch.uint8)
             self.opt[off:off + t.numel()].copy_(t)
+        check(self.L.tfr_svd_begin_step(self.opt.data_ptr(), self._stream()))  # lr_t from the restored beta powers

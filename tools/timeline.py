@@ -17,6 +17,7 @@ def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "ml25m_d128_b65536"
     overlap = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     use_graph = (sys.argv[3] != "eager") if len(sys.argv) > 3 else True
+    pipeline = (sys.argv[4] == "pipe") if len(sys.argv) > 4 else True
     w = bench.WORKLOADS[name]
     cols = bench.make_columns(w)
     eng = SvdEngine(w["U"], w["I"], w["d"], bench.LR, bench.REG, device_init_seed=1)
@@ -26,13 +27,13 @@ def main():
     np.random.seed(1)
     eng.set_index_stream(np.random.randint(0, len(cols[0]), (reps + 8) * B), B)
     eng.enable_timeline()
-    eng.run_stream_steps(8, use_graph=use_graph)
+    eng.run_stream_steps(8, use_graph=use_graph, pipeline=pipeline)
     torch.cuda.synchronize()
     acc = {}
     for _ in range(reps):
         eng.reset_timeline()
         torch.cuda.synchronize()
-        eng.run_stream_steps(1, use_graph=use_graph)
+        eng.run_stream_steps(1, use_graph=use_graph, pipeline=pipeline)
         torch.cuda.synchronize()
         for k, (a, b) in eng.read_timeline().items():
             acc.setdefault(k, []).append((a, b))
@@ -45,11 +46,12 @@ def main():
             print("%-18s start %8.1f  end %8.1f  dur %8.1f" % (k, a, b, b - a))
     print("step span %.1f us" % end_all)
     eng.set_batch_cursor(0)
+    eng.run_stream_steps(1, use_graph=use_graph, pipeline=pipeline)
     import time
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    eng.run_stream_steps(reps + 8, use_graph=use_graph)
+    eng.run_stream_steps(reps + 6, use_graph=use_graph, pipeline=pipeline)
     torch.cuda.synchronize()
-    print("back-to-back: %.1f us/step (%s)" % ((time.perf_counter() - t0) / (reps + 8) * 1e6, "graph" if use_graph else "eager"))
+    print("back-to-back: %.1f us/step (%s)" % ((time.perf_counter() - t0) / (reps + 6) * 1e6, "graph" if use_graph else "eager"))
 
 
 if __name__ == "__main__":
