@@ -254,6 +254,18 @@ int tfr_fm_forward(int64_t n_rows, const int64_t* indptr, const int32_t* indices
                    const float* w0, const float* W, const float* V, int32_t dim, float* yhat, float* sums,
                    void* stream);
 
+/* ---- all-pairs scoring: replaces als3.py:110-113  M = U.V^T + W_user[:,None] + W_work[None,:] + bias -----------
+ * (and the per-user ranking of forward.py:47-61 for k = 1).  Outputs, each optional: scores [n_users, n_items]
+ * (row-major), best_score [n_users] / best_item [n_users] = the highest-scoring item of every user (lowest index on
+ * ties), computed in the GEMM epilogue so that the score matrix need not exist.  use_tensor_cores = 1: tcgen05
+ * (kind::tf32, TMEM accumulator, TMA loads), dim % 32 == 0 and dim <= 128; = 0: exact-fp32 CUDA-core kernel, any dim
+ * (needs tfr_allpairs_workspace_bytes of workspace when best_* are requested). */
+int64_t tfr_allpairs_workspace_bytes(int64_t n_users, int64_t n_items, int32_t dim, int32_t use_tensor_cores);
+int tfr_allpairs(const float* user_feat, const float* item_feat, const float* user_bias, const float* item_bias,
+                 const float* mu, int64_t n_users, int64_t n_items, int32_t dim, int32_t use_tensor_cores,
+                 float* scores, float* best_score, int32_t* best_item, void* workspace, int64_t workspace_bytes,
+                 void* stream);
+
 /* ---- CUDA-graph helpers (thin wrappers so that a ctypes host needs no CUDA bindings) ------------ */
 int tfr_graph_begin_capture(void* stream);
 int tfr_graph_end_capture(void* stream, void** graph_exec_out);

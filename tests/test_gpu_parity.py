@@ -539,3 +539,27 @@ def test_rmse_curves_match_oracle(B, epochs):
     assert g.shape == c.shape == (epochs, 2)
     assert np.max(np.abs(g - c)) <= 1e-3, np.max(np.abs(g - c))
     assert g[-1, 1] < g[0, 1]          # it learns: validation RMSE drops from the initial ~3.7
+
+
+# ---- all-pairs scoring (als3.py:110-113): tcgen05 tf32 GEMM with fused bias + top-1 consumer ----------------------
+@pytest.mark.parametrize("U,I,d,tc", [(300, 500, 128, True), (129, 127, 64, True), (128, 128, 32, True), (1000, 777, 96, True),
+                                      (300, 500, 128, False), (61, 45, 15, False), (200, 130, 20, False)])
+def test_allpairs_matches_oracle(U, I, d, tc):
+    tabs = init.init_tables(U, I, d, seed=4, bias_init="truncated_normal")
+    tabs["user_feat"] *= 25; tabs["item_feat"] *= 25        # O(0.5) factors: a dot of O(1..5), like a trained model
+    eng = SvdEngine(U, I, d, 1e-3, 0.05, tables=tabs)
+    ref = oracle.allpairs(tabs["user_feat"], tabs["item_feat"], tabs["user_bias"], tabs["item_bias"], float(tabs["mu"][0]))
+    out = eng.allpairs(want_scores=True, want_best=True, use_tensor_cores=tc)
+    got = out["scores"].cpu().numpy()
+    # tf32 keeps 10 mantissa bits of every factor: |error| <= ~2^-10 * sum |u_k v_k|; fp32 path: a few ulp
+    mag = np.abs(tabs["user_feat"]).astype(np.float64) @ np.abs(tabs["item_feat"]).astype(np.float64).T
+    tol = (2.0 ** -9 if tc else 1e-6) * mag + 1e-5
+    assert np.all(np.abs(got - ref) <= tol), float(np.max(np.abs(got - ref) / tol))
+    # the fused consumer: best item per user == argmax of the kernel's own scores (lowest index on ties)
+    bi = out["best_item"].cpu().numpy()
+    bs = out["best_score"].cpu().numpy()
+    assert np.array_equal(bi, got.argmax(axis=1).astype(np.int32))
+    assert np.array_equal(bs, got.max(axis=1))
+    # and without materialising the matrix
+    out2 = eng.allpairs(want_scores=False, want_best=True, use_tensor_cores=tc)
+    assert np.array_equal(out2["best_item"].cpu().numpy(), bi)

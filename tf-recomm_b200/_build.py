@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 SO = os.path.join(HERE, "libtfrecomm.so")
-SOURCES = ["svd_forward.cu", "dedup_sort.cu", "segsum.cu", "adam.cu", "fm.cu", "shard.cu", "capi.cu"]
+SOURCES = ["svd_forward.cu", "dedup_sort.cu", "segsum.cu", "adam.cu", "fm.cu", "shard.cu", "allpairs.cu", "capi.cu"]
 NVCC = os.environ.get("TFR_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC"]

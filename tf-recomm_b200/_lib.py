@@ -99,6 +99,8 @@ _PROTOS = {
     "tfr_svd_finish_step": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, C.POINTER(StepWs), i32, vp]),
     "tfr_shard_gather_rows": (C.c_int, [vp, vp, i64, i32, vp, i64, i32, i32, vp, vp, vp, vp]),
     "tfr_fm_forward": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
+    "tfr_allpairs_workspace_bytes": (i64, [i64, i64, i32, i32]),
+    "tfr_allpairs": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, i64, vp]),
     "tfr_graph_begin_capture": (C.c_int, [vp]),
     "tfr_graph_end_capture": (C.c_int, [vp, C.POINTER(vp)]),
     "tfr_graph_launch": (C.c_int, [vp, vp]),

@@ -1,0 +1,418 @@
+// K6: all-pairs scoring  M[u,i] = <U[u,:], V[i,:]> + W_user[u] + W_work[i] + bias
+// Replaces als3.py:110-113 (`self.U.dot(self.V.T) + W_user.reshape(-1,1) + W_work.reshape(1,-1) + bias`, then
+// indexing / ranking the rows; forward.py:47-61 ranks one user's row).  The only GEMM-shaped work of the path, so
+// the only place tensor cores are used (north_star).
+//
+// tcgen05 path (dim a multiple of 32, <= 128): one CTA owns 128 users; their rows are loaded ONCE by TMA
+// (cp.async.bulk.tensor, 128-byte swizzle) and stay in shared memory while the CTA sweeps the item table in tiles
+// of 128 items, double-buffered by a TMA producer warp.  Per tile one elected thread issues dim/8 tcgen05.mma
+// (kind::tf32: the fp32 tables are consumed as they are, no conversion pass) into one of two 128x128 fp32
+// accumulators in TMEM; eight epilogue warps read the other one back with tcgen05.ld (thread = user row), add the
+// biases and CONSUME the tile in registers: running best item per user (top-1 recommendation), and/or the scores
+// themselves if the caller wants the matrix.  With the fused consumer the 40 GB score matrix of the ML-25M shape
+// never exists.
+//
+// CUDA-core path (any dim): exact fp32, same outputs; also the reference for the tf32 tolerance in the tests.
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace tfr {
+
+constexpr int AP_BM = 128, AP_BN = 128, AP_KC = 32;      // tile: 128 users x 128 items, K chunks of 32 floats (128 B)
+constexpr int AP_CHUNK_BYTES = 128 * AP_KC * 4;           // one TMA box: 128 rows x 128 B = 16 KB
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LAB_DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "LAB_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major, 128-byte swizzle operand descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start address >> 4 in
+// bits [0,14); leading byte offset (unused for swizzled K-major) = 1 in [16,30); stride byte offset = 1024 B (one
+// 8-row swizzle atom) >> 4 in [32,46); version = 1 in [46,48); layout SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// instruction descriptor (InstrDescriptor): D = F32 (1 @ [4,6)), A = B = TF32 (2 @ [7,10), [10,13)), both K-major,
+// N >> 3 @ [17,23), M >> 4 @ [24,29)
+__host__ __device__ constexpr uint32_t ap_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation), warps 2..9 = epilogue.
+// An epilogue warp may only touch the TMEM lanes 32*(warp % 4) .. +31 (its quarter of the 128 user rows); two warps
+// share each quarter and split the tile's 128 item columns in halves.  Pipelines: item tiles double-buffered in
+// shared memory (full/empty mbarriers between TMA and MMA), accumulators double-buffered in TMEM (2 x 128 columns,
+// full/empty mbarriers between MMA and epilogue), so TMA, tensor cores and the epilogue of consecutive tiles overlap.
+constexpr int AP_THREADS = 320, AP_EPI_WARPS = 8;
+enum { BAR_A = 0, BAR_FULL_B = 1, BAR_EMPTY_B = 3, BAR_TMEM_FULL = 5, BAR_TMEM_EMPTY = 7, AP_NBARS = 9 };
+
+template <int KCHUNKS>
+__global__ void __launch_bounds__(AP_THREADS, 1)
+    allpairs_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const float* __restrict__ ub, const float* __restrict__ ib, const float* __restrict__ mu,
+                       int n_users, int n_items, float* __restrict__ scores, float* __restrict__ best_score,
+                       int32_t* __restrict__ best_item) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // swizzle atoms: 1024 B
+  uint8_t* sA = base;
+  uint8_t* sB[2] = {base + KCHUNKS * AP_CHUNK_BYTES, base + 2 * KCHUNKS * AP_CHUNK_BYTES};
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 3 * KCHUNKS * AP_CHUNK_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + AP_NBARS);
+  float* s_best = reinterpret_cast<float*>(tmem_slot + 4);       // [2][128] halves' best score per row
+  int32_t* s_besti = reinterpret_cast<int32_t*>(s_best + 256);   // [2][128]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * AP_BM;
+  const int n_tiles = (n_items + AP_BN - 1) / AP_BN;
+  constexpr uint32_t kTileBytes = KCHUNKS * AP_CHUNK_BYTES;
+  constexpr uint32_t kIdesc = ap_idesc(AP_BM, AP_BN);
+
+  if (tid == 0) {
+    mbar_init(&bars[BAR_A], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[BAR_FULL_B + i], 1);
+      mbar_init(&bars[BAR_EMPTY_B + i], 1);
+      mbar_init(&bars[BAR_TMEM_FULL + i], 1);
+      mbar_init(&bars[BAR_TMEM_EMPTY + i], AP_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // 256 TMEM columns = two 128x128 fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(&bars[BAR_A], kTileBytes);
+#pragma unroll
+      for (int c = 0; c < KCHUNKS; ++c) tma_load_2d(sA + c * AP_CHUNK_BYTES, &tmA, c * AP_KC, m0, &bars[BAR_A]);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        if (t >= 2) mbar_wait(&bars[BAR_EMPTY_B + buf], ((t >> 1) - 1) & 1);  // MMAs of tile t-2 have read the buffer
+        mbar_expect_tx(&bars[BAR_FULL_B + buf], kTileBytes);
+#pragma unroll
+        for (int c = 0; c < KCHUNKS; ++c)
+          tma_load_2d(sB[buf] + c * AP_CHUNK_BYTES, &tmB, c * AP_KC, t * AP_BN, &bars[BAR_FULL_B + buf]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread on behalf of the CTA =====
+    if (lane == 0) {
+      mbar_wait(&bars[BAR_A], 0);
+      const uint32_t a0 = smem_u32(sA);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1, acc = t & 1;
+        mbar_wait(&bars[BAR_FULL_B + buf], (t >> 1) & 1);
+        if (t >= 2) mbar_wait(&bars[BAR_TMEM_EMPTY + acc], ((t >> 1) - 1) & 1);  // epilogue drained accumulator acc
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t b0 = smem_u32(sB[buf]);
+#pragma unroll
+        for (int c = 0; c < KCHUNKS; ++c) {
+#pragma unroll
+          for (int k = 0; k < AP_KC / 8; ++k) {  // UMMA_K = 8 tf32 = 32 B inside the 128 B swizzle atom
+            const uint64_t da = umma_desc_sw128(a0 + c * AP_CHUNK_BYTES + k * 32);
+            const uint64_t db = umma_desc_sw128(b0 + c * AP_CHUNK_BYTES + k * 32);
+            umma_tf32(tmem + (uint32_t)(acc * AP_BN), da, db, kIdesc, (c | k) ? 1u : 0u);
+          }
+        }
+        umma_commit(&bars[BAR_EMPTY_B + buf]);     // shared-memory tile free once these MMAs have read it
+        umma_commit(&bars[BAR_TMEM_FULL + acc]);   // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> biases -> consume =====
+    const int ew = warp - 2;              // 0..7
+    const int quarter = warp & 3;         // TMEM lane quarter this warp may access
+    const int half = ew >> 2;             // which 64 of the tile's 128 columns
+    const int r_in_tile = quarter * 32 + lane;
+    const int row = m0 + r_in_tile;
+    const bool row_ok = row < n_users;
+    const float bu = row_ok ? ub[row] : 0.0f;
+    const float mu_ = *mu;
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains (column % 4)
+    int32_t besti[4] = {-1, -1, -1, -1};
+    for (int t = 0; t < n_tiles; ++t) {
+      const int acc = t & 1;
+      const int n0 = t * AP_BN + half * 64;
+      // this lane's two item biases of the warp's 64 columns; exchanged by shuffle below
+      const float ib0 = (n0 + lane < n_items) ? __ldg(ib + n0 + lane) : 0.0f;
+      const float ib1 = (n0 + 32 + lane < n_items) ? __ldg(ib + n0 + 32 + lane) : 0.0f;
+      mbar_wait(&bars[BAR_TMEM_FULL + acc], (t >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float v[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * AP_BN + half * 64 + j * 32), v);
+        const float ibj = j ? ib1 : ib0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int col = n0 + j * 32 + c;
+          const float bic = __shfl_sync(0xffffffffu, ibj, c);
+          float s = add_rn(v[c], bu);          // als3.py:112: ((U.V^T + W_user) + W_work) + bias
+          s = add_rn(s, bic);
+          s = add_rn(s, mu_);
+          const bool ok = row_ok && col < n_items;
+          if (scores && ok) scores[(size_t)row * n_items + col] = s;
+          if (ok && s > best[c & 3]) { best[c & 3] = s; besti[c & 3] = col; }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[BAR_TMEM_EMPTY + acc])) : "memory");
+    }
+    // merge the 4 chains (lower item index wins ties), then the two column halves through shared memory
+    float bs = best[0];
+    int32_t bi_ = besti[0];
+#pragma unroll
+    for (int q = 1; q < 4; ++q)
+      if (best[q] > bs || (best[q] == bs && besti[q] >= 0 && (bi_ < 0 || besti[q] < bi_))) { bs = best[q]; bi_ = besti[q]; }
+    s_best[half * 128 + r_in_tile] = bs;
+    s_besti[half * 128 + r_in_tile] = bi_;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid < 128) {
+    const int row = m0 + tid;
+    if (row < n_users) {
+      float bs = s_best[tid];
+      int32_t bi_ = s_besti[tid];
+      const float b1 = s_best[128 + tid];
+      const int32_t i1 = s_besti[128 + tid];
+      if (b1 > bs || (b1 == bs && i1 >= 0 && (bi_ < 0 || i1 < bi_))) { bs = b1; bi_ = i1; }
+      if (best_score) best_score[row] = bs;
+      if (best_item) best_item[row] = bi_;
+    }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ---- CUDA-core path: exact fp32, any dim --------------------------------------------------------------------
+// 64 users x 64 items per CTA, both tiles staged in shared memory (transposed, padded), 4x4 register blocking.
+__global__ void __launch_bounds__(256) allpairs_simt_kernel(const float* __restrict__ U, const float* __restrict__ V,
+                                                            const float* __restrict__ ub, const float* __restrict__ ib,
+                                                            const float* __restrict__ mu, int n_users, int n_items, int dim,
+                                                            float* __restrict__ scores, float* __restrict__ tile_best,
+                                                            int32_t* __restrict__ tile_best_item, int n_item_tiles) {
+  __shared__ float sU[32][65], sV[32][65];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < dim; k0 += 32) {
+    for (int e = threadIdx.x; e < 64 * 32; e += 256) {
+      const int r = e / 32, k = e % 32;
+      sU[k][r] = (m0 + r < n_users && k0 + k < dim) ? U[(size_t)(m0 + r) * dim + k0 + k] : 0.0f;
+      sV[k][r] = (n0 + r < n_items && k0 + k < dim) ? V[(size_t)(n0 + r) * dim + k0 + k] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sU[k][ty * 4 + i]; b[i] = sV[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float mu_ = *mu;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    float best = -INFINITY;
+    int32_t best_i = -1;
+    if (row < n_users) {
+      const float bu = ub[row];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = n0 + tx * 4 + j;
+        if (col < n_items) {
+          float s = add_rn(add_rn(add_rn(acc[i][j], bu), ib[col]), mu_);
+          if (scores) scores[(size_t)row * n_items + col] = s;
+          if (s > best) { best = s; best_i = col; }
+        }
+      }
+    }
+    // best over the 16 threads that share this row (tx = 0..15): lower item index wins ties
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o, 16);
+      const int32_t oi = __shfl_xor_sync(0xffffffffu, best_i, o, 16);
+      if (ob > best || (ob == best && oi >= 0 && (best_i < 0 || oi < best_i))) { best = ob; best_i = oi; }
+    }
+    if (tile_best && tx == 0 && row < n_users) {
+      tile_best[(size_t)row * n_item_tiles + blockIdx.x] = best;
+      tile_best_item[(size_t)row * n_item_tiles + blockIdx.x] = best_i;
+    }
+  }
+}
+
+__global__ void allpairs_best_reduce_kernel(const float* __restrict__ tile_best, const int32_t* __restrict__ tile_item,
+                                            int n_users, int n_item_tiles, float* __restrict__ best_score,
+                                            int32_t* __restrict__ best_item) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_users) return;
+  float best = -INFINITY;
+  int32_t bi = -1;
+  for (int t = 0; t < n_item_tiles; ++t) {  // tiles in item order: strict > keeps the lowest item on ties
+    const float s = tile_best[(size_t)row * n_item_tiles + t];
+    if (s > best) { best = s; bi = tile_item[(size_t)row * n_item_tiles + t]; }
+  }
+  if (best_score) best_score[row] = best;
+  if (best_item) best_item[row] = bi;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(CUtensorMap* map, const float* table, int64_t rows, int dim) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    TFR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from the driver");
+      return TFR_ERR_CUDA;
+    }
+    encode = (EncodeTiledFn)fn;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)dim * 4};
+  const cuuint32_t box[2] = {AP_KC, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(table), gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld dim %d)", (int)r, (long long)rows, dim);
+    return TFR_ERR_CUDA;
+  }
+  return TFR_OK;
+}
+
+}  // namespace tfr
+
+using namespace tfr;
+
+extern "C" int64_t tfr_allpairs_workspace_bytes(int64_t n_users, int64_t n_items, int32_t dim, int32_t use_tensor_cores) {
+  if (n_users < 0 || n_items < 0 || dim <= 0) return TFR_ERR_INVALID;
+  if (use_tensor_cores && dim % 32 == 0 && dim <= 128) return 256;
+  const int64_t tiles = (n_items + 63) / 64;
+  return 2 * align_up(n_users * tiles * 4, 256) + 256;
+}
+
+extern "C" int tfr_allpairs(const float* user_feat, const float* item_feat, const float* user_bias,
+                            const float* item_bias, const float* mu, int64_t n_users, int64_t n_items, int32_t dim,
+                            int32_t use_tensor_cores, float* scores, float* best_score, int32_t* best_item,
+                            void* workspace, int64_t workspace_bytes, void* stream) {
+  TFR_CHECK_ARG(n_users >= 0 && n_items >= 0 && dim > 0 && n_users < ((int64_t)1 << 31) && n_items < ((int64_t)1 << 31));
+  if (n_users == 0 || n_items == 0) return TFR_OK;
+  TFR_CHECK_ARG(user_feat && item_feat && user_bias && item_bias && mu && (scores || best_score || best_item));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tensor_cores) {
+    if (dim % 32 != 0 || dim > 128) {
+      set_error("tcgen05 all-pairs path needs dim %% 32 == 0 and dim <= 128 (got %d): pass use_tensor_cores = 0", dim);
+      return TFR_ERR_INVALID;
+    }
+    TFR_CHECK_ARG(((uintptr_t)user_feat % 16 == 0) && ((uintptr_t)item_feat % 16 == 0));
+    CUtensorMap ma, mb;
+    int rc;
+    if ((rc = make_map(&ma, user_feat, n_users, dim))) return rc;
+    if ((rc = make_map(&mb, item_feat, n_items, dim))) return rc;
+    const int kch = dim / 32;
+    const size_t smem = (size_t)3 * kch * AP_CHUNK_BYTES + 1024 + AP_NBARS * 8 + 16 + 2 * 256 * 4;
+    const unsigned grid = (unsigned)((n_users + AP_BM - 1) / AP_BM);
+#define TFR_AP_CASE(KC_)                                                                                      \
+  if (kch == KC_) {                                                                                           \
+    TFR_CUDA(cudaFuncSetAttribute(allpairs_tc_kernel<KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    allpairs_tc_kernel<KC_><<<grid, AP_THREADS, smem, st>>>(ma, mb, user_bias, item_bias, mu, (int)n_users, (int)n_items,   \
+                                                     scores, best_score, best_item);                          \
+  }
+    TFR_AP_CASE(1) TFR_AP_CASE(2) TFR_AP_CASE(3) TFR_AP_CASE(4)
+#undef TFR_AP_CASE
+    TFR_LAUNCH_CHECK();
+    return TFR_OK;
+  }
+  const int tiles = (int)((n_items + 63) / 64);
+  float* tile_best = nullptr;
+  int32_t* tile_item = nullptr;
+  if (best_score || best_item) {
+    if (!workspace || workspace_bytes < tfr_allpairs_workspace_bytes(n_users, n_items, dim, 0)) {
+      set_error("all-pairs workspace too small");
+      return TFR_ERR_WORKSPACE;
+    }
+    char* w = reinterpret_cast<char*>(align_up((int64_t)(uintptr_t)workspace, 256));
+    tile_best = reinterpret_cast<float*>(w);
+    tile_item = reinterpret_cast<int32_t*>(w + align_up(n_users * tiles * 4, 256));
+  }
+  dim3 grid((unsigned)tiles, (unsigned)((n_users + 63) / 64));
+  allpairs_simt_kernel<<<grid, 256, 0, st>>>(user_feat, item_feat, user_bias, item_bias, mu, (int)n_users, (int)n_items,
+                                             dim, scores, tile_best, tile_item, tiles);
+  TFR_LAUNCH_CHECK();
+  if (tile_best) {
+    allpairs_best_reduce_kernel<<<(unsigned)((n_users + 255) / 256), 256, 0, st>>>(tile_best, tile_item, (int)n_users,
+                                                                                   tiles, best_score, best_item);
+    TFR_LAUNCH_CHECK();
+  }
+  return TFR_OK;
+}

@@ -136,6 +136,26 @@ class SvdEngine:
                                          self.flags, logits.data_ptr(), infer.data_ptr(), self._stream()))
         return logits, infer
 
+    # ---- all-pairs scoring: als3.py:110-113 (+ forward.py:47-61 ranking for k = 1) ----------------------------
+    def allpairs(self, want_scores=False, want_best=True, use_tensor_cores=None):
+        """-> dict(scores [U, I] | None, best_score [U], best_item [U]); tensor cores (tcgen05, tf32) when dim % 32 == 0
+        and dim <= 128 unless use_tensor_cores=False (exact fp32 CUDA-core kernel)."""
+        if use_tensor_cores is None:
+            use_tensor_cores = self.d % 32 == 0 and self.d <= 128
+        dev = self.device
+        scores = torch.empty(self.U, self.I, dtype=torch.float32, device=dev) if want_scores else None
+        bs = torch.empty(self.U, dtype=torch.float32, device=dev) if want_best else None
+        bi = torch.empty(self.U, dtype=torch.int32, device=dev) if want_best else None
+        nbytes = check(self.L.tfr_allpairs_workspace_bytes(self.U, self.I, self.d, int(use_tensor_cores)))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(self.L.tfr_allpairs(self.t["user_feat"].data_ptr(), self.t["item_feat"].data_ptr(),
+                                      self.t["user_bias"].data_ptr(), self.t["item_bias"].data_ptr(),
+                                      self.t["mu"].data_ptr(), self.U, self.I, self.d, int(use_tensor_cores),
+                                      scores.data_ptr() if want_scores else None, bs.data_ptr() if want_best else None,
+                                      bi.data_ptr() if want_best else None, ws.data_ptr(), nbytes, self._stream()))
+        return dict(scores=scores, best_score=bs, best_item=bi)
+
     # ---- one train step on a device-resident batch: sess.run([train_op, logits, infer]), :70-72 -------------
     def train_step(self, users, items, rates, logits=None, infer=None):
         users, items, rates = self._dev_i32(users), self._dev_i32(items), self._dev_f32(rates)
