@@ -295,7 +295,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if args.gpus > 1 or world > 1:
-        from tf_recomm_b200 import sharded_bench
+        import bench_sharded as sharded_bench
         return sharded_bench.main(args)
     name = args.workload or "ml25m_d128_b65536"
     w = WORKLOADS[name]

@@ -63,9 +63,9 @@ def main(args):
         return
     import torch
     import torch.distributed as dist
-    from . import _lib
-    from ._lib import check
-    from .sharded import ShardedSvdEngine
+    from tf_recomm_b200 import _lib
+    from tf_recomm_b200._lib import check
+    from tf_recomm_b200.sharded import ShardedSvdEngine
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
     assert torch.cuda.is_available(), "bench.py needs CUDA devices; there is no CPU fallback"
     torch.cuda.set_device(local_rank)
@@ -173,7 +173,7 @@ def main(args):
 
 
 def eng_slice(B, world, rank):
-    from . import sharding
+    from tf_recomm_b200 import sharding
     return sharding.batch_slice(B, world, rank)
 
 

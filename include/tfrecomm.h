@@ -254,6 +254,28 @@ int tfr_fm_forward(int64_t n_rows, const int64_t* indptr, const int32_t* indices
                    const float* w0, const float* W, const float* V, int32_t dim, float* yhat, float* sums,
                    void* stream);
 
+/* ---- FM train step (BASELINE configs[2]): the SVD step's structure on CSR rows -- forward (sums kept), d cost/d yhat
+ * (squared error, or sigmoid-CE with TFR_LOSS_SIGMOID_CE), tf.unique-style dedup of the batch's feature ids, ordered
+ * segment sums of the per-non-zero gradients  g_V = e*(x*(sum - V*x)) + reg*V,  g_W = e*x (+ reg*W with TFR_REG_BIAS),
+ * ONE TF-Adam pass over V and W (or SGD), dense update of w0.  The reference trains its FM with libFM's MCMC sampler
+ * (fm.py:104-110,154-155: external binary, out of scope); this is the step north_star asks for instead.
+ * indptr[0] must be 0 (a batch is its own CSR matrix).  Caller-allocated scratch: rowof [nnz] (filled by the step:
+ * CSR row of every non-zero), sums [n_rows, dim], err [n_rows]; workspace: tfr_svd_step_workspace_bytes(nnz, dim).
+ * yhat comes from the PRE-update tables.  Rows without non-zeros are allowed (yhat = w0). */
+typedef struct {
+  int32_t n_feat, dim;
+  float *w0, *W, *V;                         /* [1], [n_feat], [n_feat, dim] */
+  float *m_w0, *v_w0, *m_W, *v_W, *m_V, *v_V; /* Adam slots; null in SGD mode  */
+  int32_t* slot;                             /* [n_feat], -1 between steps     */
+} tfr_fm_tables;
+int tfr_fm_segment_grads(const float* V, const float* W, int32_t* slot, int32_t n_feat, int32_t dim,
+                         const tfr_opt_scalars* opt, const float* sums, const float* err, const float* xval,
+                         const int32_t* rowof, int64_t nnz, const tfr_svd_step_ws* ws, void* stream);
+int tfr_fm_train_step(const tfr_fm_tables* t, tfr_opt_scalars* opt, int64_t n_rows, const int64_t* indptr,
+                      const int32_t* indices, const float* data, int32_t* rowof, int64_t nnz, const float* y,
+                      float* yhat, float* sums, float* err, int32_t flags, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+
 /* ---- all-pairs scoring: replaces als3.py:110-113  M = U.V^T + W_user[:,None] + W_work[None,:] + bias -----------
  * (and the per-user ranking of forward.py:47-61 for k = 1).  Outputs, each optional: scores [n_users, n_items]
  * (row-major), best_score [n_users] / best_item [n_users] = the highest-scoring item of every user (lowest index on

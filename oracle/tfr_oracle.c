@@ -403,10 +403,10 @@ ORC_API int orc_fm_train_step(orc_fm_state *s, int64_t n_rows, const int64_t *in
   float *gV = (float *)malloc((size_t)(nnz > 0 ? nnz : 1) * d * sizeof(float));
   float *gW = (float *)malloc((size_t)(nnz > 0 ? nnz : 1) * sizeof(float));
   orc_fm_forward(n_rows, indptr, indices, data, s->w0, s->W, s->V, d, yhat, sums);
-  float g0 = 0.0f;
+  double g0_acc = 0.0; /* reduction order unspecified in TF/Eigen: order-independent value, as for the SVD's g_mu */
   for (int64_t r = 0; r < n_rows; ++r) {
     float e = orc_dloss(s->flags, yhat[r], y[r]);
-    g0 = g0 + e;
+    g0_acc += (double)e;
     for (int64_t p = indptr[r]; p < indptr[r + 1]; ++p) {
       const float x = data[p];
       const int32_t fi = indices[p];
@@ -423,6 +423,7 @@ ORC_API int orc_fm_train_step(orc_fm_state *s, int64_t n_rows, const int64_t *in
     }
   }
   if (yhat_out) memcpy(yhat_out, yhat, (size_t)n_rows * sizeof(float));
+  float g0 = (float)g0_acc;
   if (s->flags & ORC_OPT_SGD) {
     orc_sgd_scatter(s->V, d, indices + base, nnz, gV, s->lr);
     orc_sgd_scatter(s->W, 1, indices + base, nnz, gW, s->lr);

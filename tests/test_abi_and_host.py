@@ -46,6 +46,7 @@ int main(void) {
   printf("%zu %zu %zu %zu\n", offsetof(tfr_opt_scalars, global_step), offsetof(tfr_opt_scalars, batch_cursor),
          offsetof(tfr_opt_scalars, se_ring), offsetof(tfr_opt_scalars, timeline));
   printf("%zu %zu %zu\n", offsetof(tfr_svd_tables, mu), offsetof(tfr_svd_tables, user_slot), offsetof(tfr_svd_step_ws, sort_ws));
+  printf("%zu %zu %zu\n", sizeof(tfr_fm_tables), offsetof(tfr_fm_tables, w0), offsetof(tfr_fm_tables, slot));
   return 0;
 }'''
     import tempfile
@@ -59,7 +60,8 @@ int main(void) {
     exp = [C.sizeof(_lib.OptScalars), C.sizeof(_lib.SvdTables), C.sizeof(_lib.StepWs), C.sizeof(_lib.AdamTable),
            C.sizeof(_lib.SliceUpdate), _lib.OptScalars.global_step.offset, _lib.OptScalars.batch_cursor.offset,
            _lib.OptScalars.se_ring.offset, _lib.OptScalars.timeline.offset, _lib.SvdTables.mu.offset,
-           _lib.SvdTables.user_slot.offset, _lib.StepWs.sort_ws.offset]
+           _lib.SvdTables.user_slot.offset, _lib.StepWs.sort_ws.offset, C.sizeof(_lib.FmTables),
+           _lib.FmTables.w0.offset, _lib.FmTables.slot.offset]
     assert got == exp
 
 

@@ -56,6 +56,12 @@ class StepWs(C.Structure):
                 ("sort_ws", vp), ("sort_ws_bytes", i64), ("tile", i32), ("n_tiles", i32)]
 
 
+class FmTables(C.Structure):
+    """Mirror of tfr_fm_tables."""
+    _fields_ = [("n_feat", i32), ("dim", i32), ("w0", vp), ("W", vp), ("V", vp), ("m_w0", vp), ("v_w0", vp),
+                ("m_W", vp), ("v_W", vp), ("m_V", vp), ("v_V", vp), ("slot", vp)]
+
+
 class AdamTable(C.Structure):
     """Mirror of tfr_adam_table."""
     _fields_ = [("var", vp), ("m", vp), ("v", vp), ("rows", i64), ("width", i32), ("slot", vp), ("gsum", vp)]
@@ -99,6 +105,8 @@ _PROTOS = {
     "tfr_svd_finish_step": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, C.POINTER(StepWs), i32, vp]),
     "tfr_shard_gather_rows": (C.c_int, [vp, vp, i64, i32, vp, i64, i32, i32, vp, vp, vp, vp]),
     "tfr_fm_forward": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
+    "tfr_fm_segment_grads": (C.c_int, [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i64, C.POINTER(StepWs), vp]),
+    "tfr_fm_train_step": (C.c_int, [C.POINTER(FmTables), vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, vp, i64, vp]),
     "tfr_allpairs_workspace_bytes": (i64, [i64, i64, i32, i32]),
     "tfr_allpairs": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, i64, vp]),
     "tfr_graph_begin_capture": (C.c_int, [vp]),

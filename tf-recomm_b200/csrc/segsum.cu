@@ -34,6 +34,12 @@ struct SegSide {
   uint8_t* kind;  // per tile: TILE_MID | TILE_START (see segsum_fixup_kernel)
   int32_t* slot;  // [rows] row -> head index of its run (where its gsum lives); -1 between steps
   int32_t n_rows; // ids >= n_rows mark occurrences owned by another rank (row-sharded mode): skipped
+  // factorization-machine mode (xval != null): the sorted ids are FEATURE ids of the batch's non-zeros, position =
+  // index p of the non-zero; partner row = sums[rowof[p]] (the CSR row's sum_i V_i x_i), and
+  //   g_V = e_r * (x_p * (sums_r - V_f * x_p)) + reg * V_f        (Rendle 2010 eq. 4; forward.py:21-22's model)
+  //   g_W = e_r * x_p (+ reg * W_f if TFR_REG_BIAS)
+  const float* xval;      // [nnz] feature values
+  const int32_t* rowof;   // [nnz] CSR row of every non-zero
   int is_item;
 };
 
@@ -127,18 +133,25 @@ __global__ void __launch_bounds__(256) segsum_tiles_kernel(SegSide su, SegSide s
     // lane-parallel metadata fetch for up to L entries
     const int64_t k = kb + lane;
     int32_t my_id = -1, my_partner = 0;
-    float my_e = 0.0f;
+    float my_e = 0.0f, my_x = 1.0f;
     if (k < k1) {
       my_id = s.sid[k];
       const int32_t b = s.spos[k];
-      my_e = err[b];
-      my_partner = s.partner ? s.partner[b] : b;  // row-sharded mode: partner rows are gathered by position
+      if (s.xval) {  // FM: b is a non-zero; its error and "partner" (the row's sums) come from its CSR row
+        my_partner = s.rowof[b];
+        my_e = err[my_partner];
+        my_x = s.xval[b];
+      } else {
+        my_e = err[b];
+        my_partner = s.partner ? s.partner[b] : b;  // row-sharded mode: partner rows are gathered by position
+      }
     }
     const int cnt = (int)min((int64_t)L, k1 - kb);
     for (int j = 0; j < cnt; ++j) {
       const int32_t id = __shfl_sync(gmask, my_id, j, L);
       const float e = __shfl_sync(gmask, my_e, j, L);
       const int32_t pid = __shfl_sync(gmask, my_partner, j, L);
+      const float xv = __shfl_sync(gmask, my_x, j, L);
       if (id >= s.n_rows) {  // sorted to the end: nothing of mine follows
         if (cur >= 0) flush(kb + j);
         cur = -1;
@@ -169,7 +182,10 @@ __global__ void __launch_bounds__(256) segsum_tiles_kernel(SegSide su, SegSide s
 #pragma unroll
           for (int c = 0; c < VEC; ++c) {
             float g;
-            if (!s.is_item) {
+            if (s.xval) {
+              const float tt = sub_rn(p.v[c], mul_rn(own[q].v[c], xv));
+              g = mul_rn(e, mul_rn(xv, tt));
+            } else if (!s.is_item) {
               g = mul_rn(e, abs_item ? fabsf(p.v[c]) : p.v[c]);
             } else {
               g = mul_rn(e, p.v[c]);
@@ -184,7 +200,8 @@ __global__ void __launch_bounds__(256) segsum_tiles_kernel(SegSide su, SegSide s
           }
         }
       }
-      float gb = reg_bias ? add_rn(e, mul_rn(reg, own_b)) : e;
+      float gb = s.xval ? mul_rn(e, xv) : e;
+      if (reg_bias) gb = add_rn(gb, mul_rn(reg, own_b));
       if (sgd) gb = mul_rn(lr, gb);
       acc_b = add_rn(acc_b, gb);
     }
@@ -263,34 +280,23 @@ __global__ void __launch_bounds__(256) segsum_fixup_kernel(SegSide su, SegSide s
 
 using namespace tfr;
 
-extern "C" int tfr_svd_segment_grads(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
-                                     const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, void* stream) {
-  TFR_CHECK_ARG(t && opt && users && items && ws && B > 0 && t->dim > 0 && t->user_slot && t->item_slot);
-  const int dim = t->dim;
+static int launch_segsum(const SegSide& su, const SegSide& si, int n_sides, const tfr_opt_scalars* opt,
+                         const float* err, int64_t B, int dim, cudaStream_t st) {
   const RowGeom g = row_geom(dim);
   const int units = (dim / g.vec + g.lanes - 1) / g.lanes;
   const int n_tiles = (int)((B + SEG_TILE - 1) / SEG_TILE);
-  const bool gathered = t->g_user_feat != nullptr;
-  TFR_CHECK_ARG(!gathered || t->g_item_feat);
-  SegSide su{ws->su_ids, ws->su_pos, gathered ? nullptr : items, t->user_feat,
-             gathered ? t->g_item_feat : t->item_feat, t->user_bias,
-             ws->gsum_uf, ws->gsum_ub, ws->cont_uf, ws->cont_ub, ws->tail_uf, ws->tail_ub, ws->kind_u, t->user_slot, t->user_num, 0};
-  SegSide si{ws->si_ids, ws->si_pos, gathered ? nullptr : users, t->item_feat,
-             gathered ? t->g_user_feat : t->user_feat, t->item_bias,
-             ws->gsum_if, ws->gsum_ib, ws->cont_if, ws->cont_ib, ws->tail_if, ws->tail_ib, ws->kind_i, t->item_slot, t->item_num, 1};
   int cw = 1;
   while (cw < dim / g.vec && cw < 256) cw <<= 1;
   const int G = 256 / cw;
   const size_t fix_smem = ((size_t)G * dim + G) * sizeof(float);
-  dim3 fix_grid((unsigned)n_tiles, 2);
+  dim3 fix_grid((unsigned)n_tiles, (unsigned)n_sides);
   const int groups_per_cta = 256 / g.lanes;
-  dim3 grid((unsigned)((n_tiles + groups_per_cta - 1) / groups_per_cta), 2);
-  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((n_tiles + groups_per_cta - 1) / groups_per_cta), (unsigned)n_sides);
 #define TFR_SEG_CASE(V, LL, UU)                                                                                   \
   if (g.vec == V && g.lanes == LL && units == UU) {                                                               \
     TFR_PREP((segsum_tiles_kernel<V, LL, UU>));                                                                    \
     TFR_PREP((segsum_fixup_kernel<V>));                                                                            \
-    segsum_tiles_kernel<V, LL, UU><<<grid, 256, 0, st>>>(su, si, opt, ws->err, B, dim, n_tiles);                  \
+    segsum_tiles_kernel<V, LL, UU><<<grid, 256, 0, st>>>(su, si, opt, err, B, dim, n_tiles);                      \
     TFR_LAUNCH_CHECK();                                                                                            \
     segsum_fixup_kernel<V><<<fix_grid, 256, fix_smem, st>>>(su, si, opt, B, dim, n_tiles, cw);                    \
     TFR_LAUNCH_CHECK();                                                                                            \
@@ -303,4 +309,32 @@ extern "C" int tfr_svd_segment_grads(const tfr_svd_tables* t, const tfr_opt_scal
 #undef TFR_SEG_CASE
   set_error("unsupported dim %d (vec %d lanes %d units %d)", dim, g.vec, g.lanes, units);
   return TFR_ERR_INVALID;
+}
+
+extern "C" int tfr_svd_segment_grads(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
+                                     const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, void* stream) {
+  TFR_CHECK_ARG(t && opt && users && items && ws && B > 0 && t->dim > 0 && t->user_slot && t->item_slot);
+  const bool gathered = t->g_user_feat != nullptr;
+  TFR_CHECK_ARG(!gathered || t->g_item_feat);
+  SegSide su{ws->su_ids, ws->su_pos, gathered ? nullptr : items, t->user_feat,
+             gathered ? t->g_item_feat : t->item_feat, t->user_bias,
+             ws->gsum_uf, ws->gsum_ub, ws->cont_uf, ws->cont_ub, ws->tail_uf, ws->tail_ub, ws->kind_u, t->user_slot,
+             t->user_num, nullptr, nullptr, 0};
+  SegSide si{ws->si_ids, ws->si_pos, gathered ? nullptr : users, t->item_feat,
+             gathered ? t->g_user_feat : t->user_feat, t->item_bias,
+             ws->gsum_if, ws->gsum_ib, ws->cont_if, ws->cont_ib, ws->tail_if, ws->tail_ib, ws->kind_i, t->item_slot,
+             t->item_num, nullptr, nullptr, 1};
+  return launch_segsum(su, si, 2, opt, ws->err, B, t->dim, (cudaStream_t)stream);
+}
+
+// FM: one table of feature rows V [n_feat, dim] (+ linear weights W [n_feat]); the "batch" of the segment sums is
+// the batch's nnz non-zeros.  ws must be carved for B = nnz (the user-side buffers are used).
+extern "C" int tfr_fm_segment_grads(const float* V, const float* W, int32_t* slot, int32_t n_feat, int32_t dim,
+                                    const tfr_opt_scalars* opt, const float* sums, const float* err,
+                                    const float* xval, const int32_t* rowof, int64_t nnz, const tfr_svd_step_ws* ws,
+                                    void* stream) {
+  TFR_CHECK_ARG(V && W && slot && opt && sums && err && xval && rowof && ws && nnz > 0 && dim > 0 && n_feat > 0);
+  SegSide sf{ws->su_ids, ws->su_pos, nullptr, V, sums, W, ws->gsum_uf, ws->gsum_ub, ws->cont_uf, ws->cont_ub,
+             ws->tail_uf, ws->tail_ub, ws->kind_u, slot, n_feat, xval, rowof, 0};
+  return launch_segsum(sf, sf, 1, opt, err, nnz, dim, (cudaStream_t)stream);
 }
