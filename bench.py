@@ -192,17 +192,16 @@ def kernel_roofline(eng, w, cols, steps, torch, peak, peak_src):
     for s in range(steps):
         rows = rng.integers(0, len(cols[0]), B)
         du = eng._dev_i32(cols[0][rows]); di = eng._dev_i32(cols[1][rows]); dr = eng._dev_f32(cols[2][rows])
-        check(L.tfr_svd_begin_step(opt, st))
-        check(L.tfr_svd_fwd_err(tp, opt, du.data_ptr(), di.data_ptr(), dr.data_ptr(), B, logits.data_ptr(),
-                                infer.data_ptr(), C.byref(ws), st))
         check(L.tfr_dedup_sort_pairs(du.data_ptr(), U, ws.su_ids, ws.su_pos, di.data_ptr(), I, ws.si_ids,
                                      ws.si_pos, B, ws.sort_ws, ws.sort_ws_bytes, st))
-        check(L.tfr_svd_segment_grads(tp, opt, du.data_ptr(), di.data_ptr(), B, C.byref(ws), st))
+        check(L.tfr_svd_fwd_segment_grads(tp, opt, du.data_ptr(), di.data_ptr(), dr.data_ptr(), B, logits.data_ptr(),
+                                          infer.data_ptr(), eng.flags, C.byref(ws), st))
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         check(L.tfr_adam_stream_multi(tabs, 4, opt, 15, st))
         ev1.record()
-        check(L.tfr_svd_finish_step(tp, opt, du.data_ptr(), di.data_ptr(), B, C.byref(ws), _n_partials(d, B), st))
+        check(L.tfr_svd_finish_step(tp, opt, du.data_ptr(), di.data_ptr(), B, C.byref(ws),
+                                    L.tfr_svd_fused_n_partials(d, B), st))
         torch.cuda.synchronize()
         tot_ms += ev0.elapsed_time(ev1)
     bytes_launch = 24.0 * (U + I) * (d + 1)
@@ -331,13 +330,13 @@ def main():
                    % (r["bytes_step"] / 1e6) if r["bytes_step"] > 126e6 else
                    "working set %.1f MB is L2-resident by construction (launch-bound config)" % (r["bytes_step"] / 1e6),
                    "timing": "CUDA events around K replays of the captured step graph (each replay also assembles and "
-                             "sorts the NEXT batch on a side stream: 7 kernels per step either way)"},
+                             "sorts the NEXT batch on a side stream: 5 kernels per step -- assemble, id sort, forward+segment sums, fix-up, Adam pass whose last CTA ends the step)"},
         "hbm": {"algorithmic_bytes_per_step": r["bytes_step"], "achieved_gbs": r["hbm_gbs_step"],
                 "frac_of_measured_peak": r["hbm_gbs_step"] / r["peak"], "frac_of_nominal_8000": r["hbm_gbs_step"] / 8000.0,
                 "peak_gbs": r["peak"], "peak_source": r["peak_src"]},
         "epoch_s": steps_epoch * r["ms_per_step"] / 1e3,
         "roofline": r.get("roofline"), "cpu_baseline": cpu, "e2e": r.get("e2e"), "clocks": r["clocks"],
-        "gpu_launches": 7 * args.steps + 2,
+        "gpu_launches": 5 * args.steps + 2,
     }
     if not args.no_also and name == "ml25m_d128_b65536":
         a2 = argparse.Namespace(**vars(args))

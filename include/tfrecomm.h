@@ -70,7 +70,7 @@ typedef struct {
   double se_sum;         /* sum over the last step's batch of (rate - infer)^2, float64 like
                             svd_train_val.py:104 (np.power(train_rates - train_infer, 2))   */
   float g_mu;            /* last step's d cost / d bias_global (sum_b e_b)                   */
-  float pad_;
+  uint32_t ticket;       /* CTA arrival counter of the table pass (its last CTA ends the step); 0 between steps */
   double* se_ring;       /* optional device ring: se_ring[global_step % se_ring_len] = se_sum, so the
                             driver's trailing-window train RMSE (svd_train_val.py:59,104,108) needs one
                             read per epoch instead of one per step                            */
@@ -99,8 +99,12 @@ typedef struct {
   float* user_feat; /* user_features [U,dim] ops.py:29 */
   float* item_feat; /* item_features [I,dim] ops.py:31 */
   float *m_mu, *v_mu, *m_ub, *v_ub, *m_ib, *v_ib, *m_uf, *v_uf, *m_if, *v_if; /* null in SGD mode */
-  int32_t* user_slot; /* [U] -1 between steps; during a step: for the rows of this step's IndexedSlices, the */
-  int32_t* item_slot; /* [I] sorted index k of the run head whose gsum[k] is the row's summed gradient         */
+  /* row -> slot maps, initialised to -1 by the caller: (step stamp << 32 | k), stamp = low 32 bits of
+   * opt->global_step when the entry was written, k = sorted index of the run head whose gsum[k] is the row's summed
+   * gradient.  An entry counts only in the step that wrote it, so the maps are never reset (refill them with -1 if
+   * global_step is ever set backwards, e.g. when restoring a checkpoint). */
+  int64_t* user_slot; /* [U] */
+  int64_t* item_slot; /* [I] */
   /* Row-sharded mode (tables hold only this rank's rows, id mod G == rank).  When non-null, the
    * batch's gathered rows by BATCH POSITION ([B,dim] / [B], exchanged between ranks) replace the by-id gathers
    * of the forward and of the partner rows in the backward; the users/items arrays given to the step are then
@@ -152,7 +156,8 @@ int tfr_unique_first_occurrence(const int32_t* sorted_ids, const int32_t* sorted
  * the gathered rows, ops.py:81-89,140) -> TF sparse Adam over the WHOLE tables (A.4) / dense Adam on
  * bias_global (A.5), or scatter_sub SGD (ops.py:145).  logits/infer come from the PRE-update tables
  * (A.7).  users/items/rates are the assembled batch (device).  Advances opt->global_step,
- * beta powers and batch_cursor; leaves the slot maps at -1. */
+ * beta powers and batch_cursor.  Launches: [id sort] -> forward fused into the segment sums -> fix-up of runs that
+ * cross tiles -> ONE Adam pass whose last CTA ends the step. */
 int64_t tfr_svd_step_workspace_bytes(int64_t B, int32_t dim);
 /* The id-only half of a step, for the NEXT batch, to be run on a side stream under the current step's table pass:
  * tfr_svd_batch_assemble(batch_index) into users/items/rates + tfr_dedup_sort_pairs into `workspace`'s sorted-pair
@@ -188,6 +193,9 @@ typedef struct { /* carved out of the step workspace by tfr_svd_step_carve */
   float *cont_uf, *cont_if, *tail_uf, *tail_if; /* [n_tiles,dim] cross-tile partial sums */
   float *cont_ub, *cont_ib, *tail_ub, *tail_ib; /* [n_tiles]                          */
   uint8_t *kind_u, *kind_i;                     /* [n_tiles] tile classes for the fix-up */
+  int32_t *fix_list_u, *fix_list_i;             /* [n_tiles] tiles whose last run goes on into later tiles (work list) */
+  uint32_t* fix_count;  /* [4] list lengths (users, items), arrival ticket; lives in the first 256 bytes of sort_ws,
+                           which every id sort zeroes */
   void* sort_ws; int64_t sort_ws_bytes;
   int32_t tile, n_tiles;
 } tfr_svd_step_ws;
@@ -197,7 +205,14 @@ int tfr_svd_step_carve(void* workspace, int64_t workspace_bytes, int64_t B, int3
 int tfr_svd_fwd_err(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
                     const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
                     const tfr_svd_step_ws* ws, void* stream);
-/* start of a step on a caller-assembled batch: computes lr_t (tfr_svd_batch_assemble does it too) */
+/* forward + d cost/d logits + segment sums in ONE launch pair (tiles + fix-up): each side recomputes the logit from
+ * the rows it gathers for the gradient anyway.  Writes logits / infer (optional) and tfr_svd_fused_n_partials(dim, B)
+ * partials for tfr_svd_finish_step; ws->err is not written.  Not for row-sharded tables (g_* set). */
+int tfr_svd_fwd_segment_grads(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
+                              const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
+                              int32_t flags, const tfr_svd_step_ws* ws, void* stream);
+int tfr_svd_fused_n_partials(int32_t dim, int64_t B);
+/* recomputes lr_t from the beta powers (after restoring a checkpoint; a step leaves the next step's lr_t behind) */
 int tfr_svd_begin_step(tfr_opt_scalars* opt, void* stream);
 /* ordered segment sums of the per-occurrence gradients (never materialised): for every run of equal
  * ids in the sorted pairs, gsum[head k] = sum in batch order of (e_b*partner_row + reg*own_row). */
@@ -211,7 +226,7 @@ typedef struct {
   float *var, *m, *v;  /* [rows*width], 16-byte aligned */
   int64_t rows;
   int32_t width;
-  const int32_t* slot; /* [rows] row -> run-head index into gsum, -1 = not in the slice */
+  const int64_t* slot; /* [rows] row -> (stamp << 32 | run-head index into gsum); counts if stamp == step */
   const float* gsum;   /* [n, width] */
 } tfr_adam_table;
 int tfr_adam_stream_multi(const tfr_adam_table* tables, int32_t n_tables /* 1..4 */, const tfr_opt_scalars* opt,
@@ -232,8 +247,8 @@ int tfr_adam_touched(float* var, float* m, float* v, int32_t width, const int32_
                      const float* gsum, const tfr_opt_scalars* opt, void* stream);
 int tfr_sgd_apply(float* var, int32_t width, const int32_t* sorted_ids, int64_t n, const float* gsum,
                   void* stream);
-/* end of step: dense Adam/SGD on bias_global from the err partials (A.5), advance beta powers and
- * counters (TF: adam.py::_finish), reset the slot maps to -1. */
+/* end of step as a launch of its own: dense Adam/SGD on bias_global from the err partials (A.5), advance beta powers
+ * and counters (TF: adam.py::_finish).  tfr_svd_train_step folds this into the Adam pass.  users/items/B: unused. */
 int tfr_svd_finish_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
                         const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, int32_t n_partials,
                         void* stream);
@@ -266,9 +281,9 @@ typedef struct {
   int32_t n_feat, dim;
   float *w0, *W, *V;                         /* [1], [n_feat], [n_feat, dim] */
   float *m_w0, *v_w0, *m_W, *v_W, *m_V, *v_V; /* Adam slots; null in SGD mode  */
-  int32_t* slot;                             /* [n_feat], -1 between steps     */
+  int64_t* slot;                             /* [n_feat], as tfr_svd_tables' maps */
 } tfr_fm_tables;
-int tfr_fm_segment_grads(const float* V, const float* W, int32_t* slot, int32_t n_feat, int32_t dim,
+int tfr_fm_segment_grads(const float* V, const float* W, int64_t* slot, int32_t n_feat, int32_t dim,
                          const tfr_opt_scalars* opt, const float* sums, const float* err, const float* xval,
                          const int32_t* rowof, int64_t nnz, const tfr_svd_step_ws* ws, void* stream);
 int tfr_fm_train_step(const tfr_fm_tables* t, tfr_opt_scalars* opt, int64_t n_rows, const int64_t* indptr,

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libtfrecomm.so")
+SO_PATH = os.path.join(HERE, os.environ.get("TFR_SO_NAME", "libtfrecomm.so"))  # TFR_SO_NAME: A/B builds
 
 ABS_ITEM, LOSS_SIGMOID_CE, REG_BIAS, OPT_SGD = 1, 2, 4, 8
 README_FLAGS = 0
@@ -32,7 +32,7 @@ class OptScalars(C.Structure):
                 ("one_minus_beta1", f32), ("one_minus_beta2", f32),
                 ("flags", i32), ("var_mask", i32),
                 ("global_step", i64), ("batch_cursor", i64), ("se_sum", C.c_double),
-                ("g_mu", f32), ("pad_", f32), ("se_ring", vp), ("se_ring_len", i64), ("timeline", vp)]
+                ("g_mu", f32), ("ticket", C.c_uint32), ("se_ring", vp), ("se_ring_len", i64), ("timeline", vp)]
 
 
 class SvdTables(C.Structure):
@@ -52,7 +52,7 @@ class StepWs(C.Structure):
                 ("gsum_uf", vp), ("gsum_if", vp), ("gsum_ub", vp), ("gsum_ib", vp),
                 ("cont_uf", vp), ("cont_if", vp), ("tail_uf", vp), ("tail_if", vp),
                 ("cont_ub", vp), ("cont_ib", vp), ("tail_ub", vp), ("tail_ib", vp),
-                ("kind_u", vp), ("kind_i", vp),
+                ("kind_u", vp), ("kind_i", vp), ("fix_list_u", vp), ("fix_list_i", vp), ("fix_count", vp),
                 ("sort_ws", vp), ("sort_ws_bytes", i64), ("tile", i32), ("n_tiles", i32)]
 
 
@@ -96,6 +96,8 @@ _PROTOS = {
                                                vp]),
     "tfr_svd_step_carve": (C.c_int, [vp, i64, i64, i32, C.POINTER(StepWs)]),
     "tfr_svd_fwd_err": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, i64, vp, vp, C.POINTER(StepWs), vp]),
+    "tfr_svd_fwd_segment_grads": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, i64, vp, vp, i32, C.POINTER(StepWs), vp]),
+    "tfr_svd_fused_n_partials": (C.c_int, [i32, i64]),
     "tfr_svd_begin_step": (C.c_int, [vp, vp]),
     "tfr_svd_segment_grads": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, C.POINTER(StepWs), vp]),
     "tfr_adam_stream_multi": (C.c_int, [C.POINTER(AdamTable), i32, vp, i32, vp]),

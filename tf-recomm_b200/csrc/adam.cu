@@ -46,98 +46,176 @@ __device__ __forceinline__ void adam_grad(float& var, float& m, float& v, float 
 // against 6.0 TB/s for the in-order pass).
 struct StreamTab {
   float *var, *m, *v;
-  const int32_t* slot;
+  const int64_t* slot;  // (step stamp << 32 | run-head index); valid only if the stamp is this step's
   const float* gsum;
   uint32_t n;        // floats
   uint32_t width;    // floats per row
   uint32_t unit_end; // exclusive end of this table's units in the concatenated unit space
 };
+// end-of-step work folded into the pass (the last CTA to finish does it): dense Adam on bias_global from the
+// forward's per-CTA partials + the step scalars (what finish_step_kernel does as a launch of its own)
+struct FinishArgs {
+  tfr_opt_scalars* opt;  // writable alias of the kernel's (read-only) scalars: written by ONE warp after every CTA
+                         // has arrived, i.e. after every read of the step's scalars
+  float *mu, *m_mu, *v_mu;
+  const float* partials;
+  const double* se_partials;
+  int n_partials;  // 0 = no end-of-step work in this launch
+};
 struct StreamArgs {
   StreamTab t[4];
   int n_tabs;
   uint32_t total_units;
+  FinishArgs fin;
 };
+
+// one warp: fold the per-CTA partials in a fixed order, update bias_global (TF: training_ops.cc ApplyAdam, A.5),
+// advance beta powers / lr_t / counters (TF: adam.py::_finish), record the step's float64 squared-error sum
+__device__ __noinline__ void finish_step_scalars(float* mu, float* m_mu, float* v_mu, tfr_opt_scalars* opt,
+                                                    const float* partials, const double* se_partials, int n_partials) {
+  float a = 0.0f;
+  double se = 0.0;
+  const int ln = threadIdx.x & 31;
+  for (int j = ln; j < n_partials; j += 32) { a = add_rn(a, partials[j]); se += se_partials[j]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a = add_rn(a, __shfl_xor_sync(0xffffffffu, a, o));
+    se += __shfl_xor_sync(0xffffffffu, se, o);
+  }
+  if (ln == 0) {
+    const float g = a;  // d cost / d bias_global = sum_b e_b  (A.3)
+    opt->g_mu = g;
+    opt->se_sum = se;
+    if (opt->se_ring && opt->se_ring_len > 0) opt->se_ring[opt->global_step % opt->se_ring_len] = se;
+    const bool sgd = opt->flags & TFR_OPT_SGD;
+    if (opt->var_mask & TFR_VAR_MU) {
+      if (sgd) {
+        *mu = sub_rn(*mu, mul_rn(opt->lr, g));
+      } else {  // TF: training_ops.cc ApplyAdam (A.5)
+        float alpha = sqrt_rn(sub_rn(1.0f, opt->beta2_power));
+        alpha = mul_rn(opt->lr, alpha);
+        alpha = div_rn(alpha, sub_rn(1.0f, opt->beta1_power));
+        float mm = *m_mu, vv = *v_mu;
+        mm = add_rn(mm, mul_rn(sub_rn(g, mm), opt->one_minus_beta1));
+        vv = add_rn(vv, mul_rn(sub_rn(mul_rn(g, g), vv), opt->one_minus_beta2));
+        *m_mu = mm;
+        *v_mu = vv;
+        *mu = sub_rn(*mu, div_rn(mul_rn(mm, alpha), add_rn(sqrt_rn(vv), opt->eps)));
+      }
+    }
+    if (!sgd) {  // TF: adam.py::_finish
+      opt->beta1_power = mul_rn(opt->beta1_power, opt->beta1);
+      opt->beta2_power = mul_rn(opt->beta2_power, opt->beta2);
+      // lr_t of the NEXT step (TF: _apply_sparse_shared recomputes it from the advanced powers), so that a step
+      // needs no kernel in front of the forward
+      float tt = sqrt_rn(sub_rn(1.0f, opt->beta2_power));
+      opt->lr_t = div_rn(mul_rn(opt->lr, tt), sub_rn(1.0f, opt->beta1_power));
+    }
+    opt->global_step += 1;
+    opt->batch_cursor += 1;
+  }
+}
 
 template <int UNROLL>
 __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_constant__ StreamArgs a,
                                                                 const tfr_opt_scalars* __restrict__ opt, int tl_slot) {
   TlScope tl_scope(opt, tl_slot);
   const AdamK k = load_k(opt);
+  const uint32_t stamp = (uint32_t)opt->global_step;
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < a.total_units; q0 += stride * UNROLL) {
-    float4 x[UNROLL], y[UNROLL], z[UNROLL], g[UNROLL];
-    uint32_t lu[UNROLL];
-    int tab[UNROLL];
-    bool full[UNROLL];
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  // Table after table (no barrier in between: a thread that runs out of units of one table moves on to the next), so
+  // that everything about the table -- pointers, row width, slot map -- is loop-invariant.
+#pragma unroll 1
+  for (int tb = 0; tb < a.n_tabs; ++tb) {
+    const StreamTab& t = a.t[tb];
+    if ((t.width & 3u) == 0u) {
+      // rows of whole 16-byte units: a unit lies in one row, so one slot-map lookup decides between TF's two cases --
+      // a row of this step's slice (scatter-added gradient) or a row that only decays (m*b1, v*b2: exactly what TF's
+      // table-wide assign computes; adam_grad with g = 0 would differ in the sign of a zero)
+      const uint32_t n4 = t.n >> 2;
+      const uint32_t upr = t.width >> 2;  // units per row
+      const int sh = (upr & (upr - 1u)) == 0u ? 31 - __clz(upr) : -1;
+      const float4* __restrict__ pv = reinterpret_cast<const float4*>(t.var);
+      const float4* __restrict__ pm = reinterpret_cast<const float4*>(t.m);
+      const float4* __restrict__ pz = reinterpret_cast<const float4*>(t.v);
+#pragma unroll 1
+      for (uint32_t q0 = gtid; q0 < n4; q0 += stride * UNROLL) {
+        float4 x[UNROLL], y[UNROLL], z[UNROLL], g[UNROLL];
+        bool has[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const uint32_t q = q0 + u * stride;
-      tab[u] = -1;
-      if (q >= a.total_units) continue;
-      int tb = 0;
-      uint32_t begin = 0;
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-        if (tb == i && i + 1 < a.n_tabs && q >= a.t[i].unit_end) { begin = a.t[i].unit_end; tb = i + 1; }
-      tab[u] = tb;
-      lu[u] = q - begin;
-      const StreamTab& t = a.t[tb];
-      full[u] = lu[u] * 4u + 3u < t.n;
-      if (full[u]) {
-        x[u] = ld_stream_f4(reinterpret_cast<const float4*>(t.var) + lu[u]);
-        y[u] = ld_stream_f4(reinterpret_cast<const float4*>(t.m) + lu[u]);
-        z[u] = ld_stream_f4(reinterpret_cast<const float4*>(t.v) + lu[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      g[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      if (tab[u] < 0) continue;
-      const StreamTab& t = a.t[tab[u]];
-      if (!t.slot) continue;
-      const uint32_t e0 = lu[u] * 4u;
-      if ((t.width & 3u) == 0u) {  // the unit lies in one row
-        const uint32_t row = e0 / t.width;
-        const int32_t sl = t.slot[row];
-        if (sl >= 0) g[u] = *reinterpret_cast<const float4*>(t.gsum + (size_t)sl * t.width + (e0 - row * t.width));
-      } else {                     // dim 15, bias tables: every float has its own row
-        float gg[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t e = e0 + j;
-          if (e < t.n) {
-            const uint32_t row = e / t.width;
-            const int32_t sl = t.slot[row];
-            if (sl >= 0) gg[j] = t.gsum[(size_t)sl * t.width + (e - row * t.width)];
+        for (int u = 0; u < UNROLL; ++u) {
+          const uint32_t q = q0 + u * stride;
+          if (q < n4) {
+            x[u] = ld_stream_f4(pv + q);
+            y[u] = ld_stream_f4(pm + q);
+            z[u] = ld_stream_f4(pz + q);
           }
         }
-        g[u] = make_float4(gg[0], gg[1], gg[2], gg[3]);
-      }
-    }
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      if (tab[u] < 0) continue;
-      const StreamTab& t = a.t[tab[u]];
-      if (full[u]) {
-        adam_grad(x[u].x, y[u].x, z[u].x, g[u].x, k);
-        adam_grad(x[u].y, y[u].y, z[u].y, g[u].y, k);
-        adam_grad(x[u].z, y[u].z, z[u].z, g[u].z, k);
-        adam_grad(x[u].w, y[u].w, z[u].w, g[u].w, k);
-        st_stream_f4(reinterpret_cast<float4*>(t.var) + lu[u], x[u]);
-        st_stream_f4(reinterpret_cast<float4*>(t.m) + lu[u], y[u]);
-        st_stream_f4(reinterpret_cast<float4*>(t.v) + lu[u], z[u]);
-      } else {  // the table's last, partial unit
-        const float gg[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t e = lu[u] * 4u + j;
-          if (e < t.n) {
-            float p = t.var[e], q = t.m[e], r = t.v[e];
-            adam_grad(p, q, r, gg[j], k);
-            t.var[e] = p; t.m[e] = q; t.v[e] = r;
+        for (int u = 0; u < UNROLL; ++u) {
+          const uint32_t q = q0 + u * stride;
+          has[u] = false;
+          if (q < n4 && t.slot) {
+            const uint32_t row = sh >= 0 ? (q >> sh) : (q / upr);
+            const int64_t sl = t.slot[row];
+            has[u] = (uint32_t)(sl >> 32) == stamp;
+            if (has[u])
+              g[u] = *reinterpret_cast<const float4*>(t.gsum + (size_t)(uint32_t)sl * t.width + ((q - row * upr) << 2));
           }
         }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const uint32_t q = q0 + u * stride;
+          if (q >= n4) continue;
+          if (has[u]) {
+            adam_grad(x[u].x, y[u].x, z[u].x, g[u].x, k);
+            adam_grad(x[u].y, y[u].y, z[u].y, g[u].y, k);
+            adam_grad(x[u].z, y[u].z, z[u].z, g[u].z, k);
+            adam_grad(x[u].w, y[u].w, z[u].w, g[u].w, k);
+          } else {
+            adam_decay(x[u].x, y[u].x, z[u].x, k);
+            adam_decay(x[u].y, y[u].y, z[u].y, k);
+            adam_decay(x[u].z, y[u].z, z[u].z, k);
+            adam_decay(x[u].w, y[u].w, z[u].w, k);
+          }
+          st_stream_f4(reinterpret_cast<float4*>(t.var) + q, x[u]);
+          st_stream_f4(reinterpret_cast<float4*>(t.m) + q, y[u]);
+          st_stream_f4(reinterpret_cast<float4*>(t.v) + q, z[u]);
+        }
       }
+    } else {
+      // dim 15 rows, bias tables (width 1): every float has its own row -- small tables, scalar path
+#pragma unroll 1
+      for (uint32_t e = gtid; e < t.n; e += stride) {
+        float p = ld_stream_f1(t.var + e), q = ld_stream_f1(t.m + e), r = ld_stream_f1(t.v + e);
+        bool hs = false;
+        float gg = 0.0f;
+        if (t.slot) {
+          const uint32_t row = t.width == 1u ? e : e / t.width;
+          const int64_t sl = t.slot[row];
+          hs = (uint32_t)(sl >> 32) == stamp;
+          if (hs) gg = t.gsum[(size_t)(uint32_t)sl * t.width + (e - row * t.width)];
+        }
+        if (hs) adam_grad(p, q, r, gg, k); else adam_decay(p, q, r, k);
+        st_stream_f1(t.var + e, p);
+        st_stream_f1(t.m + e, q);
+        st_stream_f1(t.v + e, r);
+      }
+    }
+  }
+  if (a.fin.n_partials > 0) {  // the last CTA to get here ends the step (every CTA has read lr_t and the stamp by now)
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = atomicAdd(&a.fin.opt->ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {
+      finish_step_scalars(a.fin.mu, a.fin.m_mu, a.fin.v_mu, a.fin.opt, a.fin.partials, a.fin.se_partials,
+                          a.fin.n_partials);
+      if (threadIdx.x == 0) a.fin.opt->ticket = 0;
     }
   }
 }
@@ -243,63 +321,13 @@ __global__ void __launch_bounds__(256) adam_slice_kernel(SliceSide s0, SliceSide
   }
 }
 
-// ---- end of step ----------------------------------------------------------------------------------
-// every CTA resets the slot-map entries of its part of the batch to -1; CTA 0 / warp 0 folds the per-CTA
-// partials in a fixed order, applies the dense update of bias_global and advances the step scalars.
-__global__ void __launch_bounds__(256) finish_step_kernel(tfr_svd_tables t, tfr_opt_scalars* opt,
-                                                          const int32_t* __restrict__ users,
-                                                          const int32_t* __restrict__ items, int64_t B,
-                                                          const float* __restrict__ partials,
-                                                          const double* __restrict__ se_partials, int n_partials) {
+// ---- end of step (as a launch of its own: SGD mode, no trained table, the piecewise API) ---------------------
+// The row -> slot maps carry the step's stamp, so nothing has to be reset between steps.
+__global__ void __launch_bounds__(32) finish_step_kernel(tfr_svd_tables t, tfr_opt_scalars* opt,
+                                                         const float* __restrict__ partials,
+                                                         const double* __restrict__ se_partials, int n_partials) {
   TlScope tl_scope(opt, TFR_TL_FINISH);
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) {  // ids >= the table size mark occurrences owned by another rank (row-sharded mode)
-    const int32_t u = users[b], i = items[b];
-    if (u < t.user_num) t.user_slot[u] = -1;
-    if (i < t.item_num) t.item_slot[i] = -1;
-  }
-  if (blockIdx.x == 0 && threadIdx.x < 32) {
-    float a = 0.0f;
-    double se = 0.0;
-    for (int j = threadIdx.x; j < n_partials; j += 32) { a = add_rn(a, partials[j]); se += se_partials[j]; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a = add_rn(a, __shfl_xor_sync(0xffffffffu, a, o));
-      se += __shfl_xor_sync(0xffffffffu, se, o);
-    }
-    if (threadIdx.x == 0) {
-      const float g = a;  // d cost / d bias_global = sum_b e_b  (A.3)
-      opt->g_mu = g;
-      opt->se_sum = se;
-      if (opt->se_ring && opt->se_ring_len > 0) opt->se_ring[opt->global_step % opt->se_ring_len] = se;
-      const bool sgd = opt->flags & TFR_OPT_SGD;
-      if (opt->var_mask & TFR_VAR_MU) {
-        if (sgd) {
-          *t.mu = sub_rn(*t.mu, mul_rn(opt->lr, g));
-        } else {  // TF: training_ops.cc ApplyAdam (A.5)
-          float alpha = sqrt_rn(sub_rn(1.0f, opt->beta2_power));
-          alpha = mul_rn(opt->lr, alpha);
-          alpha = div_rn(alpha, sub_rn(1.0f, opt->beta1_power));
-          float mm = *t.m_mu, vv = *t.v_mu;
-          mm = add_rn(mm, mul_rn(sub_rn(g, mm), opt->one_minus_beta1));
-          vv = add_rn(vv, mul_rn(sub_rn(mul_rn(g, g), vv), opt->one_minus_beta2));
-          *t.m_mu = mm;
-          *t.v_mu = vv;
-          *t.mu = sub_rn(*t.mu, div_rn(mul_rn(mm, alpha), add_rn(sqrt_rn(vv), opt->eps)));
-        }
-      }
-      if (!sgd) {  // TF: adam.py::_finish
-        opt->beta1_power = mul_rn(opt->beta1_power, opt->beta1);
-        opt->beta2_power = mul_rn(opt->beta2_power, opt->beta2);
-        // lr_t of the NEXT step (TF: _apply_sparse_shared recomputes it from the advanced powers), so that a step
-        // needs no kernel in front of the forward
-        float tt = sqrt_rn(sub_rn(1.0f, opt->beta2_power));
-        opt->lr_t = div_rn(mul_rn(opt->lr, tt), sub_rn(1.0f, opt->beta1_power));
-      }
-      opt->global_step += 1;
-      opt->batch_cursor += 1;
-    }
-  }
+  finish_step_scalars(t.mu, t.m_mu, t.v_mu, opt, partials, se_partials, n_partials);
 }
 
 __global__ void opt_init_kernel(tfr_opt_scalars* opt, float lr, float reg, float beta1, float beta2, float eps,
@@ -312,7 +340,7 @@ __global__ void opt_init_kernel(tfr_opt_scalars* opt, float lr, float reg, float
   opt->lr_t = div_rn(mul_rn(lr, tt), sub_rn(1.0f, beta1));
   opt->flags = flags; opt->var_mask = var_mask;
   opt->global_step = 0; opt->batch_cursor = 0;
-  opt->se_sum = 0.0; opt->g_mu = 0.0f; opt->pad_ = 0.0f;
+  opt->se_sum = 0.0; opt->g_mu = 0.0f; opt->ticket = 0u;
   opt->se_ring = nullptr; opt->se_ring_len = 0; opt->timeline = nullptr;
 }
 
@@ -329,9 +357,10 @@ extern "C" int tfr_opt_init(tfr_opt_scalars* opt_dev, float lr, float reg, float
 }
 
 static int launch_stream_chunks(const StreamTab* chunks, int n_chunks, const tfr_opt_scalars* opt, int tl_slot,
-                                cudaStream_t st) {
+                                cudaStream_t st, const FinishArgs* fin) {
   StreamArgs a;
   memset(&a, 0, sizeof(a));
+  if (fin) a.fin = *fin;
   uint64_t units = 0;
   for (int i = 0; i < n_chunks; ++i) {
     a.t[i] = chunks[i];
@@ -340,8 +369,10 @@ static int launch_stream_chunks(const StreamTab* chunks, int n_chunks, const tfr
   }
   a.n_tabs = n_chunks;
   a.total_units = (uint32_t)units;
-  // persistent grid: 2 CTAs x 512 threads x 64 registers per SM, 2 units per thread and trip: 5.9 TB/s in situ.
-  // (3 x 256 leaves room for another kernel's CTAs beside it but measures 7 % slower: TFR_STREAM_* to experiment.)
+  // persistent grid: 2 CTAs x 448 threads x 64 registers per SM, 2 units per thread and trip.  448, not 512: two
+  // CTAs of 512 threads take the whole register file, and the id sort of the NEXT batch (8K registers per CTA,
+  // forked under this pass) could then only start when the pass drains -- which puts it on the critical path.
+  // (3 x 256 also leaves room but measures 7 % slower: TFR_STREAM_* to experiment.)
   static int cfg_ctas = -1, cfg_unroll = 0, cfg_threads = 512;
   if (cfg_ctas < 0) {
     const char* e1 = getenv("TFR_STREAM_CTAS_PER_SM");
@@ -349,7 +380,7 @@ static int launch_stream_chunks(const StreamTab* chunks, int n_chunks, const tfr
     const char* e3 = getenv("TFR_STREAM_THREADS");
     cfg_ctas = e1 ? atoi(e1) : 2;
     cfg_unroll = e2 ? atoi(e2) : 2;
-    cfg_threads = e3 ? atoi(e3) : 512;
+    cfg_threads = e3 ? atoi(e3) : 448;
   }
   int64_t grid = ((int64_t)units + cfg_threads * cfg_unroll - 1) / (cfg_threads * cfg_unroll);
   const int64_t cap = (int64_t)sm_count() * cfg_ctas;
@@ -365,8 +396,21 @@ static int launch_stream_chunks(const StreamTab* chunks, int n_chunks, const tfr
   return TFR_OK;
 }
 
+namespace tfr {
+// fin != null: the pass's last launch also ends the step (see FinishArgs); returns 1 if it did, 0 if no launch
+// was issued (nothing to stream), negative on error.
+int adam_stream_multi_impl(const tfr_adam_table* tables, int32_t n_tables, tfr_opt_scalars* opt, int32_t tl_slot,
+                           void* stream, const FinishArgs* fin);
+}
+
 extern "C" int tfr_adam_stream_multi(const tfr_adam_table* tables, int32_t n_tables, const tfr_opt_scalars* opt,
                                      int32_t tl_slot, void* stream) {
+  const int rc = adam_stream_multi_impl(tables, n_tables, const_cast<tfr_opt_scalars*>(opt), tl_slot, stream, nullptr);
+  return rc < 0 ? rc : TFR_OK;
+}
+
+int tfr::adam_stream_multi_impl(const tfr_adam_table* tables, int32_t n_tables, tfr_opt_scalars* opt, int32_t tl_slot,
+                                void* stream, const FinishArgs* fin) {
   TFR_CHECK_ARG(tables && n_tables >= 1 && n_tables <= 4 && opt && tl_slot >= 0 && tl_slot < TFR_TL_SLOTS);
   // The kernel indexes floats with 32 bits: a table of >= 2^32 floats (the 50M x 128 user shard of configs[4] at
   // G = 2) is cut into row ranges, and launches are split so that one launch covers < 2^32 units.
@@ -396,7 +440,7 @@ extern "C" int tfr_adam_stream_multi(const tfr_adam_table* tables, int32_t n_tab
       c.unit_end = 0;
       const uint64_t cu = ((uint64_t)c.n + 3) / 4;
       if (np == 4 || pending_units + cu >= ((uint64_t)1 << 32)) {
-        int rc = launch_stream_chunks(pending, np, opt, tl_slot, st);
+        int rc = launch_stream_chunks(pending, np, opt, tl_slot, st, nullptr);
         if (rc) return rc;
         np = 0;
         pending_units = 0;
@@ -405,8 +449,11 @@ extern "C" int tfr_adam_stream_multi(const tfr_adam_table* tables, int32_t n_tab
       pending_units += cu;
     }
   }
-  if (np) return launch_stream_chunks(pending, np, opt, tl_slot, st);
-  return TFR_OK;
+  if (np) {
+    const int rc = launch_stream_chunks(pending, np, opt, tl_slot, st, fin);
+    return rc < 0 ? rc : 1;
+  }
+  return 0;
 }
 
 extern "C" int tfr_adam_slice_multi(const tfr_slice_update* sides, int32_t n_sides, int32_t width, int64_t n,
@@ -459,11 +506,27 @@ extern "C" int tfr_sgd_apply(float* var, int32_t width, const int32_t* sorted_id
 extern "C" int tfr_svd_finish_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
                                    const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, int32_t n_partials,
                                    void* stream) {
-  TFR_CHECK_ARG(t && opt && users && items && ws && B > 0 && n_partials > 0 && n_partials <= TFR_MAX_PARTIALS);
+  (void)users; (void)items; (void)B;  // kept in the signature: the slot maps are stamped, nothing to reset per id
+  TFR_CHECK_ARG(t && opt && ws && n_partials > 0 && n_partials <= TFR_MAX_PARTIALS && t->mu);
   TFR_PREP(finish_step_kernel);
-  finish_step_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*t, opt, users, items, B,
-                                                                                  ws->partials, ws->se_partials,
-                                                                                  n_partials);
+  finish_step_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*t, opt, ws->partials, ws->se_partials, n_partials);
   TFR_LAUNCH_CHECK();
   return TFR_OK;
 }
+
+namespace tfr {
+// the Adam pass of a step with the end-of-step work folded into its last CTA (falls back to the finish launch when
+// there is nothing to stream)
+int adam_pass_and_finish(const tfr_adam_table* tabs, int nt, const tfr_svd_tables* t, tfr_opt_scalars* opt,
+                         const tfr_svd_step_ws* ws, int n_partials, int tl_slot, void* stream) {
+  TFR_CHECK_ARG(n_partials > 0 && n_partials <= TFR_MAX_PARTIALS);
+  int rc = 0;
+  if (nt > 0) {
+    const FinishArgs fin{opt, t->mu, t->m_mu, t->v_mu, ws->partials, ws->se_partials, n_partials};
+    rc = adam_stream_multi_impl(tabs, nt, opt, tl_slot, stream, &fin);
+    if (rc < 0) return rc;
+  }
+  if (rc == 0) return tfr_svd_finish_step(t, opt, nullptr, nullptr, 0, ws, n_partials, stream);
+  return TFR_OK;
+}
+}  // namespace tfr

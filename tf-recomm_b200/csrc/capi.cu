@@ -31,6 +31,10 @@ int sm_count() {
 }
 
 int fwd_err_n_partials(int dim, int64_t B);
+int svd_segment_grads_impl(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
+                           const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, int flags_host, void* stream);
+int adam_pass_and_finish(const tfr_adam_table* tabs, int nt, const tfr_svd_tables* t, tfr_opt_scalars* opt,
+                         const tfr_svd_step_ws* ws, int n_partials, int tl_slot, void* stream);
 
 void prep_kernel(const void* fn) {
   static std::mutex mu;
@@ -116,8 +120,11 @@ static int64_t carve(char* base, int64_t B, int32_t dim, tfr_svd_step_ws* o) {
   w.tail_ib = (float*)take(n_tiles * 4);
   w.kind_u = (uint8_t*)take(n_tiles);
   w.kind_i = (uint8_t*)take(n_tiles);
+  w.fix_list_u = (int32_t*)take(n_tiles * 4);
+  w.fix_list_i = (int32_t*)take(n_tiles * 4);
   w.sort_ws_bytes = tfr_dedup_workspace_bytes(B);
   w.sort_ws = take(w.sort_ws_bytes);
+  w.fix_count = base ? reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(w.sort_ws) + 64) : nullptr;
   w.tile = kTile;
   w.n_tiles = (int32_t)n_tiles;
   if (o) *o = w;
@@ -166,6 +173,10 @@ static int run_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t
   cudaStream_t s0 = (cudaStream_t)stream;
   cudaStream_t sorts = (n_side > 0 && !presorted) ? (cudaStream_t)side_streams[0] : s0;
   const int dim = t->dim;
+  // Single-table mode: the forward is fused into the segment sums.  Row-sharded mode (g_* set): every rank needs
+  // every occurrence's error, the local tiles only visit the occurrences of local rows -> separate forward.
+  const bool fused = t->g_user_feat == nullptr;
+  const int n_partials = fused ? tfr_svd_fused_n_partials(dim, B) : fwd_err_n_partials(dim, B);
   if (!(phases & 1)) goto phase2;
   if (sorts != s0) {
     if (!g_ev[0])
@@ -178,12 +189,16 @@ static int run_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t
                                                   (int64_t)t->item_num + 1, ws.si_ids, ws.si_pos, B, ws.sort_ws,
                                                   ws.sort_ws_bytes, opt, sorts)))
     return rc;
-  if ((rc = tfr_svd_fwd_err(t, opt, users, items, rates, B, logits, infer, &ws, s0))) return rc;
+  if (!fused && (rc = tfr_svd_fwd_err(t, opt, users, items, rates, B, logits, infer, &ws, s0))) return rc;
   if (sorts != s0) {
     TFR_CUDA(cudaEventRecord(g_ev[1], sorts));
     TFR_CUDA(cudaStreamWaitEvent(s0, g_ev[1], 0));
   }
-  if ((rc = tfr_svd_segment_grads(t, opt, users, items, B, &ws, s0))) return rc;
+  if (fused) {
+    if ((rc = tfr_svd_fwd_segment_grads(t, opt, users, items, rates, B, logits, infer, flags, &ws, s0))) return rc;
+  } else {
+    if ((rc = svd_segment_grads_impl(t, opt, users, items, B, &ws, flags, s0))) return rc;
+  }
 phase2:
   if (!(phases & 2)) return TFR_OK;
   if (!sgd) {
@@ -193,8 +208,9 @@ phase2:
     if (var_mask & TFR_VAR_IF) tabs[nt++] = tfr_adam_table{t->item_feat, t->m_if, t->v_if, t->item_num, dim, t->item_slot, ws.gsum_if};
     if (var_mask & TFR_VAR_UB) tabs[nt++] = tfr_adam_table{t->user_bias, t->m_ub, t->v_ub, t->user_num, 1, t->user_slot, ws.gsum_ub};
     if (var_mask & TFR_VAR_IB) tabs[nt++] = tfr_adam_table{t->item_bias, t->m_ib, t->v_ib, t->item_num, 1, t->item_slot, ws.gsum_ib};
-    if (nt && (rc = tfr_adam_stream_multi(tabs, nt, opt, TFR_TL_STREAM_UF, s0))) return rc;
-  } else {
+    return adam_pass_and_finish(tabs, nt, t, opt, &ws, n_partials, TFR_TL_STREAM_UF, s0);
+  }
+  {
     tfr_slice_update sides[2];
     int ns = 0;
     if (var_mask & (TFR_VAR_UF | TFR_VAR_UB))
@@ -207,7 +223,7 @@ phase2:
                                      ws.si_ids, ws.gsum_if, ws.gsum_ib};
     if (ns && (rc = tfr_adam_slice_multi(sides, ns, dim, B, opt, 1, TFR_TL_TOUCHED_U, s0))) return rc;
   }
-  return tfr_svd_finish_step(t, opt, users, items, B, &ws, fwd_err_n_partials(dim, B), s0);
+  return tfr_svd_finish_step(t, opt, users, items, B, &ws, n_partials, s0);
 }
 
 extern "C" int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,

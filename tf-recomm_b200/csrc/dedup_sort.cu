@@ -267,7 +267,8 @@ extern "C" int tfr_dedup_sort_pairs_tl(const int32_t* ids_a, int64_t max_id_a, i
   int n_passes = (bits + RADIX_BITS_MAX - 1) / RADIX_BITS_MAX;
   int digit_bits = (bits + n_passes - 1) / n_passes;
   int bpp = sort_bpp(n);
-  TFR_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned int), (cudaStream_t)stream));
+  // the whole 256-byte header: the grid barrier and the fix-up work-list counters the segment sums keep at +64
+  TFR_CUDA(cudaMemsetAsync(barrier, 0, 256, (cudaStream_t)stream));
   TFR_PREP(dedup_sort_kernel);
   dedup_sort_kernel<<<2 * bpp, SORT_THREADS, 0, (cudaStream_t)stream>>>(pa, pb, bpp, n_passes, digit_bits, hist, opt,
                                                                         barrier);

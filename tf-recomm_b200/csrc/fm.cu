@@ -9,6 +9,9 @@
 
 namespace tfr {
 
+int adam_pass_and_finish(const tfr_adam_table* tabs, int nt, const tfr_svd_tables* t, tfr_opt_scalars* opt,
+                         const tfr_svd_step_ws* ws, int n_partials, int tl_slot, void* stream);
+
 template <int VEC, int L, int UNITS>
 __global__ void __launch_bounds__(256) fm_forward_kernel(int64_t n_rows, const int64_t* __restrict__ indptr,
                                                          const int32_t* __restrict__ indices,
@@ -157,20 +160,18 @@ extern "C" int tfr_fm_train_step(const tfr_fm_tables* t, tfr_opt_scalars* opt, i
     return rc;
   if ((rc = tfr_fm_segment_grads(t->V, t->W, t->slot, t->n_feat, t->dim, opt, sums, err, data, rowof, nnz, &ws, stream)))
     return rc;
-  if (!sgd) {
-    tfr_adam_table tabs[2] = {{t->V, t->m_V, t->v_V, t->n_feat, t->dim, t->slot, ws.gsum_uf},
-                              {t->W, t->m_W, t->v_W, t->n_feat, 1, t->slot, ws.gsum_ub}};
-    if ((rc = tfr_adam_stream_multi(tabs, 2, opt, TFR_TL_STREAM_UF, stream))) return rc;
-  } else {
-    tfr_slice_update side{t->V, nullptr, nullptr, t->W, nullptr, nullptr, ws.su_ids, ws.gsum_uf, ws.gsum_ub};
-    if ((rc = tfr_adam_slice_multi(&side, 1, t->dim, nnz, opt, 1, TFR_TL_TOUCHED_U, stream))) return rc;
-  }
-  // w0 is to the FM what bias_global is to the SVD: dense gradient sum_r e_r, same end-of-step kernel
+  // w0 is to the FM what bias_global is to the SVD: dense gradient sum_r e_r, same end-of-step arithmetic
   tfr_svd_tables fin;
   memset(&fin, 0, sizeof(fin));
   fin.user_num = fin.item_num = t->n_feat;
   fin.dim = t->dim;
   fin.mu = t->w0; fin.m_mu = t->m_w0; fin.v_mu = t->v_w0;
-  fin.user_slot = fin.item_slot = t->slot;
+  if (!sgd) {
+    tfr_adam_table tabs[2] = {{t->V, t->m_V, t->v_V, t->n_feat, t->dim, t->slot, ws.gsum_uf},
+                              {t->W, t->m_W, t->v_W, t->n_feat, 1, t->slot, ws.gsum_ub}};
+    return adam_pass_and_finish(tabs, 2, &fin, opt, &ws, (int)grid, TFR_TL_STREAM_UF, stream);
+  }
+  tfr_slice_update side{t->V, nullptr, nullptr, t->W, nullptr, nullptr, ws.su_ids, ws.gsum_uf, ws.gsum_ub};
+  if ((rc = tfr_adam_slice_multi(&side, 1, t->dim, nnz, opt, 1, TFR_TL_TOUCHED_U, stream))) return rc;
   return tfr_svd_finish_step(&fin, opt, indices, indices, nnz, &ws, (int)grid, stream);
 }

@@ -60,9 +60,10 @@ class SvdEngine:
                 for n in TABLE_NAMES:
                     self.slots["m_" + n] = torch.zeros_like(self.t[n])
                     self.slots["v_" + n] = torch.zeros_like(self.t[n])
-            # row -> slot maps (-1 between steps): where a slice row finds its summed gradient during a step
-            self.user_slot = torch.full((self.U,), -1, dtype=torch.int32, device=dev)
-            self.item_slot = torch.full((self.I,), -1, dtype=torch.int32, device=dev)
+            # row -> slot maps: (step stamp << 32 | index of the row's summed gradient); an entry counts only in the
+            # step that wrote it, so nothing is reset between steps
+            self.user_slot = torch.full((self.U,), -1, dtype=torch.int64, device=dev)
+            self.item_slot = torch.full((self.I,), -1, dtype=torch.int64, device=dev)
             self.opt = torch.zeros(C.sizeof(OptScalars), dtype=torch.uint8, device=dev)
             # side stream for the id sort (runs next to the forward): see tfr_svd_train_step
             self.side_streams = [torch.cuda.Stream(device=dev)]
@@ -77,6 +78,7 @@ class SvdEngine:
         self.se_ring = None
         self.overlap = True
         self._primed = None
+        self.graph_steps = 8   # steps per captured graph in run_stream_steps (pipelined mode)
 
     # ---- plumbing ---------------------------------------------------------------------------------------
     def _n_side(self):
@@ -299,6 +301,8 @@ class SvdEngine:
         # bandwidth-bound and barely notices them, while the latency-bound gathers of phase 1 would slow down
         # beside them); at the start of the step when the tables are small and the pass is a few microseconds.
         small = 24 * (self.U + self.I) * (self.d + 1) < 64e6
+        if getattr(self, "prefetch_at_start", None) is not None:
+            small = bool(self.prefetch_at_start)
         if small:
             side.wait_stream(main)
             self._prefetch(B, 1 - slot, 1, side.cuda_stream)
@@ -346,9 +350,9 @@ class SvdEngine:
         if n_steps <= 0:
             return self.stream_buffers(B, 0)
         if pipeline is None:
-            # measured (tools/timeline.py): sorting the next batch ahead pays when the table pass is short (ML-1M
-            # shape: 67 -> 45 us/step); under a long pass it only competes with it (ML-25M shape: 215 vs 214 us)
-            pipeline = 24 * (self.U + self.I) * (self.d + 1) < 64e6
+            # the forward is fused into the segment sums, which need the sorted ids: sorting the next batch ahead takes
+            # the sort off the critical path at every table size
+            pipeline = True
         with torch.cuda.device(self.device):
             if not pipeline:
                 bufs = self.stream_buffers(B, 0)
@@ -372,7 +376,24 @@ class SvdEngine:
             if slot is None:  # nothing assembled ahead for the batch at the cursor: prime set 0
                 slot = 0
                 self._prefetch(B, 0, 0, self._stream())
-            for _ in range(n_steps):
+            # graphs of `self.graph_steps` consecutive steps (an even count, so that a graph ends on the buffer set it
+            # began with): one launch per graph_steps steps instead of one per step -- the ~9 us between two graph
+            # launches is paid once per graph.  The remainder runs as single-step graphs.
+            K = max(2, int(getattr(self, "graph_steps", 8)) // 2 * 2)
+            done = 0
+            while done < n_steps:
+                if use_graph and n_steps - done >= K:
+                    g = self._graphs.get((B, "pipe", slot, K))
+                    if g is None:
+                        s_ = slot
+
+                        def many():
+                            for i in range(K):
+                                self._enqueue_pipelined_step(B, (s_ + i) & 1)
+                        g = self._graphs[(B, "pipe", slot, K)] = self._capture(many)
+                    check(self.L.tfr_graph_launch(g, self._stream()))
+                    done += K
+                    continue
                 if use_graph:
                     g = self._graphs.get((B, "pipe", slot))
                     if g is None:
@@ -382,6 +403,7 @@ class SvdEngine:
                 else:
                     self._enqueue_pipelined_step(B, slot)
                 slot = 1 - slot
+                done += 1
             self._primed = slot  # set `slot` now holds the batch at the (advanced) cursor
             return self.stream_buffers(B, 1 - slot)
 
@@ -393,6 +415,12 @@ class SvdEngine:
     @property
     def global_step(self):
         return int(self.opt_scalars().global_step)
+
+    def live_slots(self):
+        """How many slot-map entries carry the CURRENT step's stamp (0 between steps: a step's entries die when
+        global_step advances)."""
+        stamp = self.global_step & 0xffffffff
+        return sum(int((((m >> 32) & 0xffffffff) == stamp).sum()) for m in (self.user_slot, self.item_slot))
 
     def get_tables(self):
         out = {n: self.t[n].detach().cpu().numpy().copy() for n in TABLE_NAMES}
@@ -423,6 +451,8 @@ class SvdEngine:
             if not self.sgd and ("m_" + n) in z.files:
                 self.slots["m_" + n].copy_(torch.from_numpy(z["m_" + n].reshape(self.t[n].shape)))
                 self.slots["v_" + n].copy_(torch.from_numpy(z["v_" + n].reshape(self.t[n].shape)))
+        self.user_slot.fill_(-1)  # global_step is about to change: stale stamps must not become valid again
+        self.item_slot.fill_(-1)
         for field, val, dt in (("beta1_power", z["__opt__"][0], torch.float32), ("beta2_power", z["__opt__"][1], torch.float32),
                                ("global_step", z["__step__"][0], torch.int64)):
             off = getattr(OptScalars, field).offset

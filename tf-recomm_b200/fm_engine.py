@@ -41,7 +41,7 @@ class FmEngine:
                 for n in FM_TABLE_NAMES:
                     self.slots["m_" + n] = torch.zeros_like(self.t[n])
                     self.slots["v_" + n] = torch.zeros_like(self.t[n])
-            self.slot = torch.full((self.F,), -1, dtype=torch.int32, device=dev)
+            self.slot = torch.full((self.F,), -1, dtype=torch.int64, device=dev)
             self.opt = torch.zeros(C.sizeof(OptScalars), dtype=torch.uint8, device=dev)
             s = FmTables()
             s.n_feat, s.dim = self.F, self.d

@@ -22,6 +22,10 @@ def main():
     cols = bench.make_columns(w)
     eng = SvdEngine(w["U"], w["I"], w["d"], bench.LR, bench.REG, device_init_seed=1)
     eng.overlap = overlap
+    if os.environ.get("TFR_PREFETCH_AT_START"):
+        eng.prefetch_at_start = int(os.environ["TFR_PREFETCH_AT_START"])
+    if os.environ.get("TFR_GRAPH_STEPS"):
+        eng.graph_steps = int(os.environ["TFR_GRAPH_STEPS"])
     eng.set_train_data(*cols)
     B, reps = w["B"], 12
     np.random.seed(1)
@@ -49,9 +53,14 @@ def main():
     eng.run_stream_steps(1, use_graph=use_graph, pipeline=pipeline)
     import time
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    eng.run_stream_steps(reps + 6, use_graph=use_graph, pipeline=pipeline)
+    nb = 64
+    eng.set_index_stream(np.random.randint(0, len(cols[0]), (nb + 8) * B), B)
+    eng.run_stream_steps(nb, use_graph=use_graph, pipeline=pipeline)
+    eng.set_batch_cursor(0)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    eng.run_stream_steps(nb, use_graph=use_graph, pipeline=pipeline)
     torch.cuda.synchronize()
-    print("back-to-back: %.1f us/step (%s)" % ((time.perf_counter() - t0) / (reps + 6) * 1e6, "graph" if use_graph else "eager"))
+    print("back-to-back: %.1f us/step (%s)" % ((time.perf_counter() - t0) / nb * 1e6, "graph" if use_graph else "eager"))
 
 
 if __name__ == "__main__":
