@@ -16,6 +16,25 @@
 
 namespace tfr {
 
+// cache hints of the streaming accesses (TFR_STREAM_LD / TFR_STREAM_ST: 0 = .cs, 1 = default, 2 = .cg, 3 = .lu / .wt).
+// Measured on B200 at the ML-25M shape (tools/pass_bench.py): loads .cg or .lu 131.5 us per pass against 140 us with
+// .cs and 135-138 us with the default; the store hint makes no difference (.cs kept: evict-first, so the pass does not
+// push the batch's gathered rows out of L2).  Default: ld = .cg, st = .cs.
+__device__ __forceinline__ float4 ld_hint_f4(const float4* p, int h) {
+  float4 r;
+  if (h == 0) return ld_stream_f4(p);
+  if (h == 1) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  else if (h == 2) asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  else asm volatile("ld.global.lu.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_hint_f4(float4* p, const float4& v, int h) {
+  if (h == 0) { st_stream_f4(p, v); return; }
+  if (h == 1) asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  else if (h == 2) asm volatile("st.global.cg.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  else asm volatile("st.global.wt.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 struct AdamK {
   float b1, b2, lr_t, eps, omb1, omb2;
 };
@@ -67,6 +86,8 @@ struct StreamArgs {
   int n_tabs;
   uint32_t total_units;
   FinishArgs fin;
+  int ld_hint, st_hint;
+  int copy_only;  // experiment (TFR_STREAM_COPY_ONLY=1): same loads and stores, no arithmetic -- the memory ceiling
 };
 
 // one warp: fold the per-CTA partials in a fixed order, update bias_global (TF: training_ops.cc ApplyAdam, A.5),
@@ -147,9 +168,9 @@ __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_
         for (int u = 0; u < UNROLL; ++u) {
           const uint32_t q = q0 + u * stride;
           if (q < n4) {
-            x[u] = ld_stream_f4(pv + q);
-            y[u] = ld_stream_f4(pm + q);
-            z[u] = ld_stream_f4(pz + q);
+            x[u] = ld_hint_f4(pv + q, a.ld_hint);
+            y[u] = ld_hint_f4(pm + q, a.ld_hint);
+            z[u] = ld_hint_f4(pz + q, a.ld_hint);
           }
         }
 #pragma unroll
@@ -168,7 +189,8 @@ __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_
         for (int u = 0; u < UNROLL; ++u) {
           const uint32_t q = q0 + u * stride;
           if (q >= n4) continue;
-          if (has[u]) {
+          if (a.copy_only) {
+          } else if (has[u]) {
             adam_grad(x[u].x, y[u].x, z[u].x, g[u].x, k);
             adam_grad(x[u].y, y[u].y, z[u].y, g[u].y, k);
             adam_grad(x[u].z, y[u].z, z[u].z, g[u].z, k);
@@ -179,9 +201,9 @@ __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_
             adam_decay(x[u].z, y[u].z, z[u].z, k);
             adam_decay(x[u].w, y[u].w, z[u].w, k);
           }
-          st_stream_f4(reinterpret_cast<float4*>(t.var) + q, x[u]);
-          st_stream_f4(reinterpret_cast<float4*>(t.m) + q, y[u]);
-          st_stream_f4(reinterpret_cast<float4*>(t.v) + q, z[u]);
+          st_hint_f4(reinterpret_cast<float4*>(t.var) + q, x[u], a.st_hint);
+          st_hint_f4(reinterpret_cast<float4*>(t.m) + q, y[u], a.st_hint);
+          st_hint_f4(reinterpret_cast<float4*>(t.v) + q, z[u], a.st_hint);
         }
       }
     } else {
@@ -369,6 +391,12 @@ static int launch_stream_chunks(const StreamTab* chunks, int n_chunks, const tfr
   }
   a.n_tabs = n_chunks;
   a.total_units = (uint32_t)units;
+  static int copy_only = -1;
+  if (copy_only < 0) copy_only = getenv("TFR_STREAM_COPY_ONLY") ? atoi(getenv("TFR_STREAM_COPY_ONLY")) : 0;
+  a.copy_only = copy_only;
+  static int ldh = -1, sth = -1;
+  if (ldh < 0) { ldh = getenv("TFR_STREAM_LD") ? atoi(getenv("TFR_STREAM_LD")) : 2; sth = getenv("TFR_STREAM_ST") ? atoi(getenv("TFR_STREAM_ST")) : 0; }
+  a.ld_hint = ldh; a.st_hint = sth;
   // persistent grid: 2 CTAs x 448 threads x 64 registers per SM, 2 units per thread and trip.  448, not 512: two
   // CTAs of 512 threads take the whole register file, and the id sort of the NEXT batch (8K registers per CTA,
   // forked under this pass) could then only start when the pass drains -- which puts it on the critical path.

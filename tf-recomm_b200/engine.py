@@ -168,8 +168,7 @@ class SvdEngine:
             infer = torch.empty(B, dtype=torch.float32, device=self.device)
         ws = self.workspace(B)
         with torch.cuda.device(self.device):
-            st = self._stream()
-            check(self.L.tfr_svd_begin_step(self.opt.data_ptr(), st))
+            st = self._stream()  # (lr_t of this step was left behind by the previous step's finish / tfr_opt_init)
             check(self.L.tfr_svd_train_step(C.byref(self.tables_struct), self.opt.data_ptr(), users.data_ptr(),
                                             items.data_ptr(), rates.data_ptr(), B, logits.data_ptr(),
                                             infer.data_ptr(), self.flags, self.var_mask, ws.data_ptr(), ws.numel(),
@@ -193,6 +192,27 @@ class SvdEngine:
         hi[:B] = users  # value cast float64 -> int32, like TF feeding an int32 placeholder (A.7)
         hi[B:] = items
         stg["h_rates"].numpy()[:] = rates
+        if getattr(self, "host_step_graph", True):
+            # H2D of the batch, the step and the D2H of the fetched predictions as ONE captured graph (the staging
+            # buffers are persistent, so their addresses can be baked in): one launch + one sync per sess.run
+            g = self._graphs.get((B, "host"))
+            if g is None:
+                self.workspace(B)
+
+                def body():
+                    stg["d_ids"].copy_(stg["h_ids"], non_blocking=True)
+                    stg["d_rates"].copy_(stg["h_rates"], non_blocking=True)
+                    self.train_step(stg["d_ids"][:B], stg["d_ids"][B:], stg["d_rates"], logits=stg["d_out"][:B],
+                                    infer=stg["d_out"][B:])
+                    stg["h_out"].copy_(stg["d_out"], non_blocking=True)
+                g = self._graphs[(B, "host")] = self._capture(body)
+            with torch.cuda.device(self.device):
+                check(self.L.tfr_graph_launch(g, self._stream()))
+            if not fetch:
+                return None
+            torch.cuda.current_stream(self.device).synchronize()
+            out = stg["h_out"].numpy()
+            return out[:B].copy(), out[B:].copy()
         stg["d_ids"].copy_(stg["h_ids"], non_blocking=True)
         stg["d_rates"].copy_(stg["h_rates"], non_blocking=True)
         self.train_step(stg["d_ids"][:B], stg["d_ids"][B:], stg["d_rates"], logits=stg["d_out"][:B],
@@ -310,7 +330,12 @@ class SvdEngine:
         if not small:
             side.wait_stream(main)
             self._prefetch(B, 1 - slot, 1, side.cuda_stream)
+        hook = getattr(self, "timing_hook", None)   # bench.py: event-record nodes around the table pass, in situ
+        if hook:
+            hook("pass_begin", slot, main)
         phase(2)                      # Adam pass + finish
+        if hook:
+            hook("pass_end", slot, main)
         main.wait_stream(side)
 
     def stream_buffers(self, B, slot=0):
@@ -369,43 +394,53 @@ class SvdEngine:
                 for _ in range(n_steps):
                     check(self.L.tfr_graph_launch(g, st))
                 return bufs
-            for slot in (0, 1):
-                self.stream_buffers(B, slot)
-                self.workspace((B, slot))
-            slot = getattr(self, "_primed", None)
-            if slot is None:  # nothing assembled ahead for the batch at the cursor: prime set 0
-                slot = 0
-                self._prefetch(B, 0, 0, self._stream())
-            # graphs of `self.graph_steps` consecutive steps (an even count, so that a graph ends on the buffer set it
-            # began with): one launch per graph_steps steps instead of one per step -- the ~9 us between two graph
-            # launches is paid once per graph.  The remainder runs as single-step graphs.
-            K = max(2, int(getattr(self, "graph_steps", 8)) // 2 * 2)
-            done = 0
-            while done < n_steps:
-                if use_graph and n_steps - done >= K:
-                    g = self._graphs.get((B, "pipe", slot, K))
-                    if g is None:
-                        s_ = slot
+            return self._run_pipelined(B, n_steps, use_graph, launch=True)
 
-                        def many():
-                            for i in range(K):
-                                self._enqueue_pipelined_step(B, (s_ + i) & 1)
-                        g = self._graphs[(B, "pipe", slot, K)] = self._capture(many)
+    def prepare_stream_graphs(self, n_steps):
+        """Captures (without running anything) every graph run_stream_steps(n_steps) is going to replay from the current
+        state, so that no capture / instantiation falls into a timed region."""
+        with torch.cuda.device(self.device):
+            self._run_pipelined(self.stream_B, n_steps, True, launch=False)
+
+    def _pipe_graph(self, B, slot, K):
+        """Graph of K consecutive pipelined steps beginning on buffer set `slot` (K = 1, or an even count so that the
+        graph ends on the set it began with)."""
+        key = (B, "pipe", slot, K)
+        g = self._graphs.get(key)
+        if g is None:
+            def many():
+                for i in range(K):
+                    self._enqueue_pipelined_step(B, (slot + i) & 1)
+            g = self._graphs[key] = self._capture(many)
+        return g
+
+    def _run_pipelined(self, B, n_steps, use_graph, launch):
+        for slot in (0, 1):
+            self.stream_buffers(B, slot)
+            self.workspace((B, slot))
+        slot = getattr(self, "_primed", None)
+        if slot is None:  # nothing assembled ahead for the batch at the cursor: prime set 0
+            slot = 0
+            if launch:
+                self._prefetch(B, 0, 0, self._stream())
+        # graphs of `self.graph_steps` consecutive steps: one launch per graph_steps steps instead of one per step --
+        # the gap between two graph launches is paid once per graph.  The remainder runs as single-step graphs.
+        K = max(2, int(getattr(self, "graph_steps", 8)) // 2 * 2)
+        done = 0
+        while done < n_steps:
+            k = K if (use_graph and n_steps - done >= K) else 1
+            if use_graph:
+                g = self._pipe_graph(B, slot, k)
+                if launch:
                     check(self.L.tfr_graph_launch(g, self._stream()))
-                    done += K
-                    continue
-                if use_graph:
-                    g = self._graphs.get((B, "pipe", slot))
-                    if g is None:
-                        s_ = slot
-                        g = self._graphs[(B, "pipe", slot)] = self._capture(lambda: self._enqueue_pipelined_step(B, s_))
-                    check(self.L.tfr_graph_launch(g, self._stream()))
-                else:
-                    self._enqueue_pipelined_step(B, slot)
+            elif launch:
+                self._enqueue_pipelined_step(B, slot)
+            if k == 1:
                 slot = 1 - slot
-                done += 1
+            done += k
+        if launch:
             self._primed = slot  # set `slot` now holds the batch at the (advanced) cursor
-            return self.stream_buffers(B, 1 - slot)
+        return self.stream_buffers(B, 1 - slot)
 
     # ---- state access ------------------------------------------------------------------------------------
     def opt_scalars(self):

@@ -20,13 +20,18 @@ from tf_recomm_b200.engine import SvdEngine  # noqa: E402
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "ml25m_d128_b65536"
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-    w = bench.WORKLOADS[name]
-    cols = bench.make_columns(w)
-    eng = SvdEngine(w["U"], w["I"], w["d"], bench.LR, bench.REG, device_init_seed=1)
-    eng.set_train_data(*cols)
-    np.random.seed(1)
-    eng.set_index_stream(np.random.randint(0, len(cols[0]), 6 * w["B"]), w["B"])
-    eng.run_stream_steps(4, use_graph=False)
+    if "," in name:  # "U,I,d": tables of that size, no training data (the pass alone at scale)
+        U, I, d = (int(x) for x in name.split(","))
+        w = dict(U=U, I=I, d=d, B=65536)
+        eng = SvdEngine(U, I, d, bench.LR, bench.REG, device_init_seed=1)
+    else:
+        w = bench.WORKLOADS[name]
+        cols = bench.make_columns(w)
+        eng = SvdEngine(w["U"], w["I"], w["d"], bench.LR, bench.REG, device_init_seed=1)
+        eng.set_train_data(*cols)
+        np.random.seed(1)
+        eng.set_index_stream(np.random.randint(0, len(cols[0]), 6 * w["B"]), w["B"])
+        eng.run_stream_steps(4, use_graph=False)
     torch.cuda.synchronize()
     if os.environ.get("TFR_PASS_WARM_STATE", "1") == "1":
         # steady-state optimizer slots: every row has been touched (m, v in the normal range).  With the all-zero
@@ -34,9 +39,9 @@ def main():
         g = torch.Generator(device=eng.device); g.manual_seed(3)
         for n_, t_ in eng.slots.items():
             if n_.startswith("m_"):
-                t_.copy_(torch.randn(t_.shape, generator=g, device=eng.device) * 1e-2)
+                t_.normal_(0.0, 1e-2, generator=g)
             else:
-                t_.copy_(torch.rand(t_.shape, generator=g, device=eng.device) * 1e-2 + 1e-6)
+                t_.uniform_(1e-6, 1e-2, generator=g)
     ws = eng.step_ws(w["B"])
     tabs = bench._adam_tables(eng, ws, _lib)
     st = torch.cuda.current_stream().cuda_stream
