@@ -147,7 +147,7 @@ def reference_arm(args, w, name):
                                    "host threads; TensorFlow itself is absent" % (n, w["B"], cores)},
         "e2e": {"value": val, "unit": "ratings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -170,6 +170,7 @@ def _adam_tables(eng, ws, _lib):
                                                         ("item_bias", eng.I, 1, eng.item_slot, ws.gsum_ib))):
         arr[k].var, arr[k].m, arr[k].v = T[tab].data_ptr(), S["m_" + tab].data_ptr(), S["v_" + tab].data_ptr()
         arr[k].rows, arr[k].width, arr[k].slot, arr[k].gsum = rows, width, slot.data_ptr(), gsum
+        arr[k].stride = (eng.feat_stride if width > 1 else 0)
     return arr
 
 
@@ -289,7 +290,28 @@ def run_workload(name, args, torch, with_e2e=True, with_roofline=True, sample_cl
     return res
 
 
+def _claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version banner to
+    stdout): point file descriptor 1 at stderr for the whole run and keep the real stdout for the JSON line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
+JSON_OUT = None
+
+
+def emit(line):
+    out = JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global JSON_OUT
+    JSON_OUT = _claim_stdout()
+    sys.modules.setdefault("bench", sys.modules[__name__])  # bench_sharded / tools `import bench`: this very module
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -357,7 +379,7 @@ def main():
                         "readme_epoch_s": README_EPOCH_S["ml1m_d15_b10000"],
                         "vs_baseline": ra["value"] / PUBLISHED_RATINGS_PER_S["ml1m_d15_b10000"],
                         "e2e": ra.get("e2e"), "note": "launch/L2-bound: 5.2 MB/step, HBM fraction not meaningful"}
-    print(json.dumps(line))
+    emit(line)
 
 
 if __name__ == "__main__":

@@ -59,7 +59,7 @@ def main(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         if rank == 0:
-            print(json.dumps(reference_line(args, max(world, args.gpus), bench)))
+            bench.emit(reference_line(args, max(world, args.gpus), bench))
         return
     import torch
     import torch.distributed as dist
@@ -167,7 +167,7 @@ def main(args):
                     "steps": n_e2e, "path": "ShardedSvdEngine.train_step_from_slices with pinned host slices"},
             "clocks": clocks, "gpu_launches": (2 + 6) * steps,
         }
-        print(json.dumps(line))
+        bench.emit(line)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -202,6 +202,7 @@ def timed_local_step(eng, bufs, rates, torch, _lib, check):
                                                         ("item_bias", eng.I_loc, 1, e.item_slot, ws.gsum_ib))):
         arr[k].var, arr[k].m, arr[k].v = T[tab].data_ptr(), S["m_" + tab].data_ptr(), S["v_" + tab].data_ptr()
         arr[k].rows, arr[k].width, arr[k].slot, arr[k].gsum = rows, width, slot.data_ptr(), gsum
+        arr[k].stride = (e.feat_stride if width > 1 else 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     check(L.tfr_adam_stream_multi(arr, 4, opt, 15, st))

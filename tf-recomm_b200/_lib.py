@@ -37,7 +37,7 @@ class OptScalars(C.Structure):
 
 class SvdTables(C.Structure):
     """Mirror of tfr_svd_tables (host struct of device pointers, passed by pointer)."""
-    _fields_ = [("user_num", i32), ("item_num", i32), ("dim", i32), ("pad_", i32),
+    _fields_ = [("user_num", i32), ("item_num", i32), ("dim", i32), ("feat_stride", i32),
                 ("mu", vp), ("user_bias", vp), ("item_bias", vp), ("user_feat", vp), ("item_feat", vp),
                 ("m_mu", vp), ("v_mu", vp), ("m_ub", vp), ("v_ub", vp), ("m_ib", vp), ("v_ib", vp),
                 ("m_uf", vp), ("v_uf", vp), ("m_if", vp), ("v_if", vp),
@@ -64,13 +64,14 @@ class FmTables(C.Structure):
 
 class AdamTable(C.Structure):
     """Mirror of tfr_adam_table."""
-    _fields_ = [("var", vp), ("m", vp), ("v", vp), ("rows", i64), ("width", i32), ("slot", vp), ("gsum", vp)]
+    _fields_ = [("var", vp), ("m", vp), ("v", vp), ("rows", i64), ("width", i32), ("slot", vp), ("gsum", vp),
+                ("stride", i64)]
 
 
 class SliceUpdate(C.Structure):
     """Mirror of tfr_slice_update."""
     _fields_ = [("var", vp), ("m", vp), ("v", vp), ("bvar", vp), ("bm", vp), ("bv", vp), ("sorted_ids", vp),
-                ("gsum", vp), ("bgsum", vp)]
+                ("gsum", vp), ("bgsum", vp), ("stride", i64)]
 
 
 # name -> (restype, argtypes).  Every symbol include/tfrecomm.h declares is listed here; the CPU test
@@ -105,12 +106,13 @@ _PROTOS = {
     "tfr_adam_slice_multi": (C.c_int, [C.POINTER(SliceUpdate), i32, i32, i64, vp, i32, i32, vp]),
     "tfr_sgd_apply": (C.c_int, [vp, i32, vp, i64, vp, vp]),
     "tfr_svd_finish_step": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, C.POINTER(StepWs), i32, vp]),
-    "tfr_shard_gather_rows": (C.c_int, [vp, vp, i64, i32, vp, i64, i32, i32, vp, vp, vp, vp]),
+    "tfr_experiment_interleaved_pass": (C.c_int, [vp, i64, i32, vp, i32, vp]),
+    "tfr_shard_gather_rows": (C.c_int, [vp, vp, i64, i32, i64, vp, i64, i32, i32, vp, vp, vp, vp]),
     "tfr_fm_forward": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
     "tfr_fm_segment_grads": (C.c_int, [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i64, C.POINTER(StepWs), vp]),
     "tfr_fm_train_step": (C.c_int, [C.POINTER(FmTables), vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, vp, i64, vp]),
     "tfr_allpairs_workspace_bytes": (i64, [i64, i64, i32, i32]),
-    "tfr_allpairs": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, i64, vp]),
+    "tfr_allpairs": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, i64, i64, i32, vp, vp, vp, vp, i64, vp]),
     "tfr_graph_begin_capture": (C.c_int, [vp]),
     "tfr_graph_end_capture": (C.c_int, [vp, C.POINTER(vp)]),
     "tfr_graph_launch": (C.c_int, [vp, vp]),

@@ -67,8 +67,10 @@ struct StreamTab {
   float *var, *m, *v;
   const int64_t* slot;  // (step stamp << 32 | run-head index); valid only if the stamp is this step's
   const float* gsum;
-  uint32_t n;        // floats
+  uint32_t n;        // floats (rows * width)
   uint32_t width;    // floats per row
+  uint32_t stride;   // floats between consecutive rows of var (and of m, of v): width, or 3*width when var | m | v of a
+                     // row are interleaved (m = var + width, v = var + 2*width) -- then ONE stream is read and written
   uint32_t unit_end; // exclusive end of this table's units in the concatenated unit space
 };
 // end-of-step work folded into the pass (the last CTA to finish does it): dense Adam on bias_global from the
@@ -157,20 +159,26 @@ __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_
       const uint32_t n4 = t.n >> 2;
       const uint32_t upr = t.width >> 2;  // units per row
       const int sh = (upr & (upr - 1u)) == 0u ? 31 - __clz(upr) : -1;
-      const float4* __restrict__ pv = reinterpret_cast<const float4*>(t.var);
-      const float4* __restrict__ pm = reinterpret_cast<const float4*>(t.m);
-      const float4* __restrict__ pz = reinterpret_cast<const float4*>(t.v);
+      const uint32_t spr = t.stride >> 2;   // units between consecutive rows
+      const bool dense = spr == upr;        // plain [rows][width] arrays: unit q is at offset q
+      float4* const pv = reinterpret_cast<float4*>(t.var);
+      float4* const pm = reinterpret_cast<float4*>(t.m);
+      float4* const pz = reinterpret_cast<float4*>(t.v);
 #pragma unroll 1
       for (uint32_t q0 = gtid; q0 < n4; q0 += stride * UNROLL) {
         float4 x[UNROLL], y[UNROLL], z[UNROLL], g[UNROLL];
         bool has[UNROLL];
+        size_t at[UNROLL];
+        uint32_t row[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
           const uint32_t q = q0 + u * stride;
           if (q < n4) {
-            x[u] = ld_hint_f4(pv + q, a.ld_hint);
-            y[u] = ld_hint_f4(pm + q, a.ld_hint);
-            z[u] = ld_hint_f4(pz + q, a.ld_hint);
+            row[u] = sh >= 0 ? (q >> sh) : (q / upr);
+            at[u] = dense ? (size_t)q : (size_t)row[u] * spr + (q - row[u] * upr);
+            x[u] = ld_hint_f4(pv + at[u], a.ld_hint);
+            y[u] = ld_hint_f4(pm + at[u], a.ld_hint);
+            z[u] = ld_hint_f4(pz + at[u], a.ld_hint);
           }
         }
 #pragma unroll
@@ -178,11 +186,10 @@ __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_
           const uint32_t q = q0 + u * stride;
           has[u] = false;
           if (q < n4 && t.slot) {
-            const uint32_t row = sh >= 0 ? (q >> sh) : (q / upr);
-            const int64_t sl = t.slot[row];
+            const int64_t sl = t.slot[row[u]];
             has[u] = (uint32_t)(sl >> 32) == stamp;
             if (has[u])
-              g[u] = *reinterpret_cast<const float4*>(t.gsum + (size_t)(uint32_t)sl * t.width + ((q - row * upr) << 2));
+              g[u] = *reinterpret_cast<const float4*>(t.gsum + (size_t)(uint32_t)sl * t.width + ((q - row[u] * upr) << 2));
           }
         }
 #pragma unroll
@@ -201,28 +208,29 @@ __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_
             adam_decay(x[u].z, y[u].z, z[u].z, k);
             adam_decay(x[u].w, y[u].w, z[u].w, k);
           }
-          st_hint_f4(reinterpret_cast<float4*>(t.var) + q, x[u], a.st_hint);
-          st_hint_f4(reinterpret_cast<float4*>(t.m) + q, y[u], a.st_hint);
-          st_hint_f4(reinterpret_cast<float4*>(t.v) + q, z[u], a.st_hint);
+          st_hint_f4(pv + at[u], x[u], a.st_hint);
+          st_hint_f4(pm + at[u], y[u], a.st_hint);
+          st_hint_f4(pz + at[u], z[u], a.st_hint);
         }
       }
     } else {
       // dim 15 rows, bias tables (width 1): every float has its own row -- small tables, scalar path
 #pragma unroll 1
       for (uint32_t e = gtid; e < t.n; e += stride) {
-        float p = ld_stream_f1(t.var + e), q = ld_stream_f1(t.m + e), r = ld_stream_f1(t.v + e);
+        const uint32_t row = t.width == 1u ? e : e / t.width;
+        const size_t at = (size_t)row * t.stride + (e - row * t.width);
+        float p = ld_stream_f1(t.var + at), q = ld_stream_f1(t.m + at), r = ld_stream_f1(t.v + at);
         bool hs = false;
         float gg = 0.0f;
         if (t.slot) {
-          const uint32_t row = t.width == 1u ? e : e / t.width;
           const int64_t sl = t.slot[row];
           hs = (uint32_t)(sl >> 32) == stamp;
           if (hs) gg = t.gsum[(size_t)(uint32_t)sl * t.width + (e - row * t.width)];
         }
         if (hs) adam_grad(p, q, r, gg, k); else adam_decay(p, q, r, k);
-        st_stream_f1(t.var + e, p);
-        st_stream_f1(t.m + e, q);
-        st_stream_f1(t.v + e, r);
+        st_stream_f1(t.var + at, p);
+        st_stream_f1(t.m + at, q);
+        st_stream_f1(t.v + at, r);
       }
     }
   }
@@ -242,6 +250,46 @@ __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_
   }
 }
 
+// ---- layout experiment: the same update on an INTERLEAVED table T[rows][3][width] (var row | m row | v row) -----------
+// One read stream and one write stream instead of three and three.  tools/pass_bench.py --interleaved times it.
+template <int UNROLL>
+__global__ void __launch_bounds__(512, 2) adam_interleaved_kernel(float* __restrict__ T, uint32_t rows, uint32_t upr,
+                                                               const tfr_opt_scalars* __restrict__ opt, int copy_only) {
+  const AdamK k = load_k(opt);
+  const uint32_t n_units = rows * upr;  // units of var (= of m, of v)
+  const uint32_t stride = gridDim.x * blockDim.x;
+  float4* base = reinterpret_cast<float4*>(T);
+  for (uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < n_units; q0 += stride * UNROLL) {
+    float4 x[UNROLL], y[UNROLL], z[UNROLL];
+    size_t at[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const uint32_t q = q0 + u * stride;
+      if (q < n_units) {
+        const uint32_t row = q / upr, c = q - row * upr;
+        at[u] = (size_t)row * 3u * upr + c;
+        x[u] = ld_hint_f4(base + at[u], 2);
+        y[u] = ld_hint_f4(base + at[u] + upr, 2);
+        z[u] = ld_hint_f4(base + at[u] + 2u * upr, 2);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const uint32_t q = q0 + u * stride;
+      if (q >= n_units) continue;
+      if (!copy_only) {
+        adam_decay(x[u].x, y[u].x, z[u].x, k);
+        adam_decay(x[u].y, y[u].y, z[u].y, k);
+        adam_decay(x[u].z, y[u].z, z[u].z, k);
+        adam_decay(x[u].w, y[u].w, z[u].w, k);
+      }
+      st_stream_f4(base + at[u], x[u]);
+      st_stream_f4(base + at[u] + upr, y[u]);
+      st_stream_f4(base + at[u] + 2u * upr, z[u]);
+    }
+  }
+}
+
 // ---- slice rows: one lane group per ENT consecutive sorted entries; run heads act --------------------------
 // Both tables' slices (users, items) in ONE launch (blockIdx.y).  A group first decides which of its ENT
 // entries are run heads, then issues the loads of all of them together (up to 4*ENT 16-byte requests per
@@ -252,6 +300,7 @@ struct SliceSide {
   const int32_t* sid;        // sorted ids
   const float* gsum;         // [n, width] summed gradient at run heads
   const float* bgsum;        // [n]
+  int64_t stride;            // floats between consecutive rows of var / m / v
 };
 constexpr int SLICE_ENT = 4;
 
@@ -302,7 +351,7 @@ __global__ void __launch_bounds__(256) adam_slice_kernel(SliceSide s0, SliceSide
 #pragma unroll
     for (int e = 0; e < SLICE_ENT; ++e) {
       if (!head[e]) continue;
-      const size_t off = (size_t)id[e] * width + (size_t)unit * VEC;
+      const size_t off = (size_t)id[e] * s.stride + (size_t)unit * VEC;
       const size_t goff = (size_t)(kk0 + e) * width + (size_t)unit * VEC;
       if constexpr (VEC == 4) {
         const float4 av = *reinterpret_cast<const float4*>(s.var + off);
@@ -323,7 +372,7 @@ __global__ void __launch_bounds__(256) adam_slice_kernel(SliceSide s0, SliceSide
 #pragma unroll
     for (int e = 0; e < SLICE_ENT; ++e) {
       if (!head[e]) continue;
-      const size_t off = (size_t)id[e] * width + (size_t)unit * VEC;
+      const size_t off = (size_t)id[e] * s.stride + (size_t)unit * VEC;
 #pragma unroll
       for (int c = 0; c < VEC; ++c) {
         if (sgd) a[e][c] = sub_rn(a[e][c], g[e][c]);  // ops.py:145 scatter_sub; gsum holds the sum of lr*g
@@ -452,15 +501,20 @@ int tfr::adam_stream_multi_impl(const tfr_adam_table* tables, int32_t n_tables, 
     TFR_CHECK_ARG(t.rows >= 0 && t.width > 0);
     if (t.rows == 0) continue;
     TFR_CHECK_ARG(t.var && t.m && t.v && (!t.slot || t.gsum));
-    TFR_CHECK_ARG(((uintptr_t)t.var % 16 == 0) && ((uintptr_t)t.m % 16 == 0) && ((uintptr_t)t.v % 16 == 0));
+    // rows of whole 16-byte units are streamed with 128-bit accesses; other widths (dim 15, biases) go scalar
+    TFR_CHECK_ARG(t.width % 4 != 0 ||
+                  (((uintptr_t)t.var % 16 == 0) && ((uintptr_t)t.m % 16 == 0) && ((uintptr_t)t.v % 16 == 0)));
+    const uint64_t rstride = t.stride ? (uint64_t)t.stride : (uint64_t)t.width;
+    TFR_CHECK_ARG(rstride >= (uint64_t)t.width && rstride < ((uint64_t)1 << 31) && (t.width % 4 != 0 || rstride % 4 == 0));
     TFR_CHECK_ARG(!t.gsum || t.width % 4 != 0 || (uintptr_t)t.gsum % 16 == 0);
     uint64_t rows_per_chunk = kMaxFloats / (uint64_t)t.width;
     rows_per_chunk -= rows_per_chunk % 4;  // keeps every chunk's first float 16-byte aligned for any width
     for (uint64_t r0 = 0; r0 < (uint64_t)t.rows; r0 += rows_per_chunk) {
       const uint64_t nr = ((uint64_t)t.rows - r0 < rows_per_chunk) ? (uint64_t)t.rows - r0 : rows_per_chunk;
       StreamTab c;
-      const uint64_t off = r0 * (uint64_t)t.width;
+      const uint64_t off = r0 * rstride;
       c.var = t.var + off; c.m = t.m + off; c.v = t.v + off;
+      c.stride = (uint32_t)rstride;
       c.slot = t.slot ? t.slot + r0 : nullptr;
       c.gsum = t.gsum;
       c.n = (uint32_t)(nr * (uint64_t)t.width);
@@ -484,6 +538,16 @@ int tfr::adam_stream_multi_impl(const tfr_adam_table* tables, int32_t n_tables, 
   return 0;
 }
 
+extern "C" int tfr_experiment_interleaved_pass(float* T, int64_t rows, int32_t width, const tfr_opt_scalars* opt,
+                                               int32_t copy_only, void* stream) {
+  TFR_CHECK_ARG(T && opt && rows > 0 && width > 0 && width % 4 == 0 && rows * (int64_t)(width / 4) < ((int64_t)1 << 32));
+  const int threads = getenv("TFR_STREAM_THREADS") ? atoi(getenv("TFR_STREAM_THREADS")) : 448;
+  adam_interleaved_kernel<2><<<2 * sm_count(), threads, 0, (cudaStream_t)stream>>>(T, (uint32_t)rows, (uint32_t)(width / 4),
+                                                                                opt, copy_only);
+  TFR_LAUNCH_CHECK();
+  return TFR_OK;
+}
+
 extern "C" int tfr_adam_slice_multi(const tfr_slice_update* sides, int32_t n_sides, int32_t width, int64_t n,
                                     const tfr_opt_scalars* opt, int32_t sgd, int32_t tl_slot, void* stream) {
   TFR_CHECK_ARG(sides && n_sides >= 1 && n_sides <= 2 && width > 0 && n >= 0 && tl_slot >= 0 && tl_slot < TFR_TL_SLOTS);
@@ -498,6 +562,7 @@ extern "C" int tfr_adam_slice_multi(const tfr_slice_update* sides, int32_t n_sid
     TFR_CHECK_ARG(!u.bvar || (u.bgsum && (sgd || (u.bm && u.bv))));
     ss[i].var = u.var; ss[i].m = u.m; ss[i].v = u.v; ss[i].bvar = u.bvar; ss[i].bm = u.bm; ss[i].bv = u.bv;
     ss[i].sid = u.sorted_ids; ss[i].gsum = u.gsum; ss[i].bgsum = u.bgsum;
+    ss[i].stride = u.stride ? u.stride : width;
   }
   const RowGeom g = row_geom(width);
   const int64_t groups = (n + SLICE_ENT - 1) / SLICE_ENT;
@@ -521,13 +586,13 @@ extern "C" int tfr_adam_slice_multi(const tfr_slice_update* sides, int32_t n_sid
 
 extern "C" int tfr_adam_touched(float* var, float* m, float* v, int32_t width, const int32_t* sorted_ids, int64_t n,
                                 const float* gsum, const tfr_opt_scalars* opt, void* stream) {
-  tfr_slice_update u{var, m, v, nullptr, nullptr, nullptr, sorted_ids, gsum, nullptr};
+  tfr_slice_update u{var, m, v, nullptr, nullptr, nullptr, sorted_ids, gsum, nullptr, 0};
   return tfr_adam_slice_multi(&u, 1, width, n, opt, 0, TFR_TL_SLOTS - 1, stream);
 }
 
 extern "C" int tfr_sgd_apply(float* var, int32_t width, const int32_t* sorted_ids, int64_t n, const float* gsum,
                              void* stream) {
-  tfr_slice_update u{var, nullptr, nullptr, nullptr, nullptr, nullptr, sorted_ids, gsum, nullptr};
+  tfr_slice_update u{var, nullptr, nullptr, nullptr, nullptr, nullptr, sorted_ids, gsum, nullptr, 0};
   return tfr_adam_slice_multi(&u, 1, width, n, nullptr, 1, TFR_TL_SLOTS - 1, stream);
 }
 

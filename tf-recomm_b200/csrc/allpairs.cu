@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
 __global__ void __launch_bounds__(256) allpairs_simt_kernel(const float* __restrict__ U, const float* __restrict__ V,
                                                             const float* __restrict__ ub, const float* __restrict__ ib,
                                                             const float* __restrict__ mu, int n_users, int n_items, int dim,
+                                                            int64_t us, int64_t is,  // floats between rows of U / V
                                                             float* __restrict__ scores, float* __restrict__ tile_best,
                                                             int32_t* __restrict__ tile_best_item, int n_item_tiles) {
   __shared__ float sU[32][65], sV[32][65];
@@ -257,8 +258,8 @@ __global__ void __launch_bounds__(256) allpairs_simt_kernel(const float* __restr
   for (int k0 = 0; k0 < dim; k0 += 32) {
     for (int e = threadIdx.x; e < 64 * 32; e += 256) {
       const int r = e / 32, k = e % 32;
-      sU[k][r] = (m0 + r < n_users && k0 + k < dim) ? U[(size_t)(m0 + r) * dim + k0 + k] : 0.0f;
-      sV[k][r] = (n0 + r < n_items && k0 + k < dim) ? V[(size_t)(n0 + r) * dim + k0 + k] : 0.0f;
+      sU[k][r] = (m0 + r < n_users && k0 + k < dim) ? U[(size_t)(m0 + r) * us + k0 + k] : 0.0f;
+      sV[k][r] = (n0 + r < n_items && k0 + k < dim) ? V[(size_t)(n0 + r) * is + k0 + k] : 0.0f;
     }
     __syncthreads();
 #pragma unroll 8
@@ -324,7 +325,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(CUtensorMap* map, const float* table, int64_t rows, int dim) {
+static int make_map(CUtensorMap* map, const float* table, int64_t rows, int dim, int64_t stride) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -337,7 +338,7 @@ static int make_map(CUtensorMap* map, const float* table, int64_t rows, int dim)
     encode = (EncodeTiledFn)fn;
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)dim * 4};
+  const cuuint64_t gstride[1] = {(cuuint64_t)stride * 4};  // row pitch: dim, or 3*dim for interleaved tables
   const cuuint32_t box[2] = {AP_KC, 128};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(table), gdim, gstride, box, estr,
@@ -363,8 +364,12 @@ extern "C" int64_t tfr_allpairs_workspace_bytes(int64_t n_users, int64_t n_items
 
 extern "C" int tfr_allpairs(const float* user_feat, const float* item_feat, const float* user_bias,
                             const float* item_bias, const float* mu, int64_t n_users, int64_t n_items, int32_t dim,
-                            int32_t use_tensor_cores, float* scores, float* best_score, int32_t* best_item,
-                            void* workspace, int64_t workspace_bytes, void* stream) {
+                            int64_t user_stride, int64_t item_stride, int32_t use_tensor_cores, float* scores,
+                            float* best_score, int32_t* best_item, void* workspace, int64_t workspace_bytes,
+                            void* stream) {
+  if (user_stride == 0) user_stride = dim;
+  if (item_stride == 0) item_stride = dim;
+  TFR_CHECK_ARG(user_stride >= dim && item_stride >= dim);
   TFR_CHECK_ARG(n_users >= 0 && n_items >= 0 && dim > 0 && n_users < ((int64_t)1 << 31) && n_items < ((int64_t)1 << 31));
   if (n_users == 0 || n_items == 0) return TFR_OK;
   TFR_CHECK_ARG(user_feat && item_feat && user_bias && item_bias && mu && (scores || best_score || best_item));
@@ -377,8 +382,8 @@ extern "C" int tfr_allpairs(const float* user_feat, const float* item_feat, cons
     TFR_CHECK_ARG(((uintptr_t)user_feat % 16 == 0) && ((uintptr_t)item_feat % 16 == 0));
     CUtensorMap ma, mb;
     int rc;
-    if ((rc = make_map(&ma, user_feat, n_users, dim))) return rc;
-    if ((rc = make_map(&mb, item_feat, n_items, dim))) return rc;
+    if ((rc = make_map(&ma, user_feat, n_users, dim, user_stride))) return rc;
+    if ((rc = make_map(&mb, item_feat, n_items, dim, item_stride))) return rc;
     const int kch = dim / 32;
     const size_t smem = (size_t)3 * kch * AP_CHUNK_BYTES + 1024 + AP_NBARS * 8 + 16 + 2 * 256 * 4;
     const unsigned grid = (unsigned)((n_users + AP_BM - 1) / AP_BM);
@@ -407,7 +412,7 @@ extern "C" int tfr_allpairs(const float* user_feat, const float* item_feat, cons
   }
   dim3 grid((unsigned)tiles, (unsigned)((n_users + 63) / 64));
   allpairs_simt_kernel<<<grid, 256, 0, st>>>(user_feat, item_feat, user_bias, item_bias, mu, (int)n_users, (int)n_items,
-                                             dim, scores, tile_best, tile_item, tiles);
+                                             dim, user_stride, item_stride, scores, tile_best, tile_item, tiles);
   TFR_LAUNCH_CHECK();
   if (tile_best) {
     allpairs_best_reduce_kernel<<<(unsigned)((n_users + 255) / 256), 256, 0, st>>>(tile_best, tile_item, (int)n_users,

@@ -204,10 +204,10 @@ phase2:
   if (!sgd) {
     tfr_adam_table tabs[4];
     int nt = 0;
-    if (var_mask & TFR_VAR_UF) tabs[nt++] = tfr_adam_table{t->user_feat, t->m_uf, t->v_uf, t->user_num, dim, t->user_slot, ws.gsum_uf};
-    if (var_mask & TFR_VAR_IF) tabs[nt++] = tfr_adam_table{t->item_feat, t->m_if, t->v_if, t->item_num, dim, t->item_slot, ws.gsum_if};
-    if (var_mask & TFR_VAR_UB) tabs[nt++] = tfr_adam_table{t->user_bias, t->m_ub, t->v_ub, t->user_num, 1, t->user_slot, ws.gsum_ub};
-    if (var_mask & TFR_VAR_IB) tabs[nt++] = tfr_adam_table{t->item_bias, t->m_ib, t->v_ib, t->item_num, 1, t->item_slot, ws.gsum_ib};
+    if (var_mask & TFR_VAR_UF) tabs[nt++] = tfr_adam_table{t->user_feat, t->m_uf, t->v_uf, t->user_num, dim, t->user_slot, ws.gsum_uf, t->feat_stride};
+    if (var_mask & TFR_VAR_IF) tabs[nt++] = tfr_adam_table{t->item_feat, t->m_if, t->v_if, t->item_num, dim, t->item_slot, ws.gsum_if, t->feat_stride};
+    if (var_mask & TFR_VAR_UB) tabs[nt++] = tfr_adam_table{t->user_bias, t->m_ub, t->v_ub, t->user_num, 1, t->user_slot, ws.gsum_ub, 0};
+    if (var_mask & TFR_VAR_IB) tabs[nt++] = tfr_adam_table{t->item_bias, t->m_ib, t->v_ib, t->item_num, 1, t->item_slot, ws.gsum_ib, 0};
     return adam_pass_and_finish(tabs, nt, t, opt, &ws, n_partials, TFR_TL_STREAM_UF, s0);
   }
   {
@@ -216,11 +216,11 @@ phase2:
     if (var_mask & (TFR_VAR_UF | TFR_VAR_UB))
       sides[ns++] = tfr_slice_update{(var_mask & TFR_VAR_UF) ? t->user_feat : nullptr, nullptr, nullptr,
                                      (var_mask & TFR_VAR_UB) ? t->user_bias : nullptr, nullptr, nullptr,
-                                     ws.su_ids, ws.gsum_uf, ws.gsum_ub};
+                                     ws.su_ids, ws.gsum_uf, ws.gsum_ub, t->feat_stride};
     if (var_mask & (TFR_VAR_IF | TFR_VAR_IB))
       sides[ns++] = tfr_slice_update{(var_mask & TFR_VAR_IF) ? t->item_feat : nullptr, nullptr, nullptr,
                                      (var_mask & TFR_VAR_IB) ? t->item_bias : nullptr, nullptr, nullptr,
-                                     ws.si_ids, ws.gsum_if, ws.gsum_ib};
+                                     ws.si_ids, ws.gsum_if, ws.gsum_ib, t->feat_stride};
     if (ns && (rc = tfr_adam_slice_multi(sides, ns, dim, B, opt, 1, TFR_TL_TOUCHED_U, s0))) return rc;
   }
   return tfr_svd_finish_step(t, opt, users, items, B, &ws, n_partials, s0);

@@ -167,11 +167,11 @@ extern "C" int tfr_fm_train_step(const tfr_fm_tables* t, tfr_opt_scalars* opt, i
   fin.dim = t->dim;
   fin.mu = t->w0; fin.m_mu = t->m_w0; fin.v_mu = t->v_w0;
   if (!sgd) {
-    tfr_adam_table tabs[2] = {{t->V, t->m_V, t->v_V, t->n_feat, t->dim, t->slot, ws.gsum_uf},
-                              {t->W, t->m_W, t->v_W, t->n_feat, 1, t->slot, ws.gsum_ub}};
+    tfr_adam_table tabs[2] = {{t->V, t->m_V, t->v_V, t->n_feat, t->dim, t->slot, ws.gsum_uf, 0},
+                              {t->W, t->m_W, t->v_W, t->n_feat, 1, t->slot, ws.gsum_ub, 0}};
     return adam_pass_and_finish(tabs, 2, &fin, opt, &ws, (int)grid, TFR_TL_STREAM_UF, stream);
   }
-  tfr_slice_update side{t->V, nullptr, nullptr, t->W, nullptr, nullptr, ws.su_ids, ws.gsum_uf, ws.gsum_ub};
+  tfr_slice_update side{t->V, nullptr, nullptr, t->W, nullptr, nullptr, ws.su_ids, ws.gsum_uf, ws.gsum_ub, 0};
   if ((rc = tfr_adam_slice_multi(&side, 1, t->dim, nnz, opt, 1, TFR_TL_TOUCHED_U, stream))) return rc;
   return tfr_svd_finish_step(&fin, opt, indices, indices, nnz, &ws, (int)grid, stream);
 }

@@ -34,6 +34,7 @@ struct SegSide {
   const int32_t* partner;  // the OTHER id column of the batch (items for the user table)
   const float* own_feat;   // this table's rows
   const float* partner_feat;
+  int64_t own_stride, partner_stride;  // floats between consecutive rows (dim, or 3*dim for interleaved tables)
   const float* own_bias;
   const float* partner_bias;  // fused forward only
   float *gsum, *gsum_b, *cont, *cont_b, *tail, *tail_b;
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(SEG_THREADS) segsum_tiles_kernel(SegSide su, S
           const int j = sb * P + jj;
           if (j < cnt) {
             const int32_t pid = __shfl_sync(gmask, my_partner, j, L);
-            const float* prow = s.partner_feat + (size_t)pid * dim;
+            const float* prow = s.partner_feat + (size_t)pid * s.partner_stride;
 #pragma unroll
             for (int q = 0; q < UNITS; ++q) {
               const int unit = lane + q * L;
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(SEG_THREADS) segsum_tiles_kernel(SegSide su, S
             }
             if ((newmask >> j) & 1u) {
               const int32_t id = __shfl_sync(gmask, my_id, j, L);
-              const float* orow = s.own_feat + (size_t)id * dim;
+              const float* orow = s.own_feat + (size_t)id * s.own_stride;
 #pragma unroll
               for (int q = 0; q < UNITS; ++q) {
                 const int unit = lane + q * L;
@@ -658,12 +659,13 @@ static int launch_segsum(const SegSide& su, const SegSide& si, int n_sides, cons
 static void svd_sides(const tfr_svd_tables* t, const int32_t* users, const int32_t* items, const tfr_svd_step_ws* ws,
                       SegSide* su, SegSide* si) {
   const bool gathered = t->g_user_feat != nullptr;
+  const int64_t fs = t->feat_stride ? t->feat_stride : t->dim, ps = gathered ? t->dim : fs;
   *su = SegSide{ws->su_ids, ws->su_pos, gathered ? nullptr : items, t->user_feat,
-                gathered ? t->g_item_feat : t->item_feat, t->user_bias, gathered ? t->g_item_bias : t->item_bias,
+                gathered ? t->g_item_feat : t->item_feat, fs, ps, t->user_bias, gathered ? t->g_item_bias : t->item_bias,
                 ws->gsum_uf, ws->gsum_ub, ws->cont_uf, ws->cont_ub, ws->tail_uf, ws->tail_ub, ws->kind_u, ws->fix_list_u,
                 ws->fix_count, t->user_slot, t->user_num, nullptr, nullptr, 0};
   *si = SegSide{ws->si_ids, ws->si_pos, gathered ? nullptr : users, t->item_feat,
-                gathered ? t->g_user_feat : t->user_feat, t->item_bias, gathered ? t->g_user_bias : t->user_bias,
+                gathered ? t->g_user_feat : t->user_feat, fs, ps, t->item_bias, gathered ? t->g_user_bias : t->user_bias,
                 ws->gsum_if, ws->gsum_ib, ws->cont_if, ws->cont_ib, ws->tail_if, ws->tail_ib, ws->kind_i, ws->fix_list_i,
                 ws->fix_count + 1, t->item_slot, t->item_num, nullptr, nullptr, 1};
 }
@@ -714,7 +716,7 @@ extern "C" int tfr_fm_segment_grads(const float* V, const float* W, int64_t* slo
                                     const float* xval, const int32_t* rowof, int64_t nnz, const tfr_svd_step_ws* ws,
                                     void* stream) {
   TFR_CHECK_ARG(V && W && slot && opt && sums && err && xval && rowof && ws && nnz > 0 && dim > 0 && n_feat > 0);
-  SegSide sf{ws->su_ids, ws->su_pos, nullptr, V, sums, W, nullptr, ws->gsum_uf, ws->gsum_ub, ws->cont_uf, ws->cont_ub,
+  SegSide sf{ws->su_ids, ws->su_pos, nullptr, V, sums, dim, dim, W, nullptr, ws->gsum_uf, ws->gsum_ub, ws->cont_uf, ws->cont_ub,
              ws->tail_uf, ws->tail_ub, ws->kind_u, ws->fix_list_u, ws->fix_count, slot, n_feat, xval, rowof, 0};
   return launch_segsum(sf, sf, 1, nullptr, opt, err, nnz, dim, true, ws->fix_count, (cudaStream_t)stream);
 }

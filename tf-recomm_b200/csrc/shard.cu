@@ -8,7 +8,8 @@ namespace tfr {
 template <int VEC, int L>
 __global__ void __launch_bounds__(256) shard_gather_rows_kernel(const float* __restrict__ feat,
                                                                 const float* __restrict__ bias, int rows_local,
-                                                                int dim, const int32_t* __restrict__ ids, int64_t B,
+                                                                int dim, int64_t fstride,
+                                                                const int32_t* __restrict__ ids, int64_t B,
                                                                 int n_ranks, int rank, float* __restrict__ out_feat,
                                                                 float* __restrict__ out_bias,
                                                                 int32_t* __restrict__ keys) {
@@ -22,10 +23,10 @@ __global__ void __launch_bounds__(256) shard_gather_rows_kernel(const float* __r
   for (int unit = lane; unit < n_units; unit += L) {
     if constexpr (VEC == 4) {
       float4 x = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      if (mine) x = ld_gather_f4(reinterpret_cast<const float4*>(feat + (size_t)local * dim) + unit);
+      if (mine) x = ld_gather_f4(reinterpret_cast<const float4*>(feat + (size_t)local * fstride) + unit);
       reinterpret_cast<float4*>(out_feat + (size_t)b * dim)[unit] = x;
     } else {
-      out_feat[(size_t)b * dim + unit] = mine ? ld_gather_f1(feat + (size_t)local * dim + unit) : 0.0f;
+      out_feat[(size_t)b * dim + unit] = mine ? ld_gather_f1(feat + (size_t)local * fstride + unit) : 0.0f;
     }
   }
   if (lane == 0) {
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(256) shard_gather_rows_kernel(const float* __r
 using namespace tfr;
 
 extern "C" int tfr_shard_gather_rows(const float* feat_local, const float* bias_local, int64_t rows_local, int32_t dim,
+                                     int64_t feat_stride,
                                      const int32_t* ids, int64_t B, int32_t n_ranks, int32_t rank, float* out_feat,
                                      float* out_bias, int32_t* local_keys, void* stream) {
   TFR_CHECK_ARG(B >= 0 && dim > 0 && n_ranks >= 1 && rank >= 0 && rank < n_ranks && rows_local >= 0 &&
@@ -52,7 +54,8 @@ extern "C" int tfr_shard_gather_rows(const float* feat_local, const float* bias_
 #define TFR_SG_CASE(V, LL)                                                                                        \
   if (g.vec == V && g.lanes == LL) {                                                                              \
     TFR_PREP((shard_gather_rows_kernel<V, LL>));                                                                  \
-    shard_gather_rows_kernel<V, LL><<<grid, 256, 0, st>>>(feat_local, bias_local, (int)rows_local, dim, ids, B,   \
+    shard_gather_rows_kernel<V, LL><<<grid, 256, 0, st>>>(feat_local, bias_local, (int)rows_local, dim,              \
+                                                          feat_stride ? feat_stride : (int64_t)dim, ids, B,   \
                                                           n_ranks, rank, out_feat, out_bias, local_keys);         \
     TFR_LAUNCH_CHECK();                                                                                            \
     return TFR_OK;                                                                                                 \

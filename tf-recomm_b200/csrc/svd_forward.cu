@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) svd_forward_kernel(tfr_svd_tables t, cons
   const float* __restrict__ itf = gathered ? t.g_item_feat : t.item_feat;
   const float* __restrict__ ubias = gathered ? t.g_user_bias : t.user_bias;
   const float* __restrict__ ibias = gathered ? t.g_item_bias : t.item_bias;
+  const size_t fs = (gathered || t.feat_stride == 0) ? (size_t)dim : (size_t)t.feat_stride;  // floats between rows
   float err_acc = 0.0f;
   double se_acc = 0.0;
 
@@ -110,8 +111,8 @@ __global__ void __launch_bounds__(256) svd_forward_kernel(tfr_svd_tables t, cons
         float4 a[R], q[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          a[r] = ld_gather_f4(reinterpret_cast<const float4*>(uf + (size_t)uu[r] * dim) + k);
-          q[r] = ld_gather_f4(reinterpret_cast<const float4*>(itf + (size_t)ii[r] * dim) + k);
+          a[r] = ld_gather_f4(reinterpret_cast<const float4*>(uf + (size_t)uu[r] * fs) + k);
+          q[r] = ld_gather_f4(reinterpret_cast<const float4*>(itf + (size_t)ii[r] * fs) + k);
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -127,8 +128,8 @@ __global__ void __launch_bounds__(256) svd_forward_kernel(tfr_svd_tables t, cons
         float a[R], q[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          a[r] = ld_gather_f1(uf + (size_t)uu[r] * dim + k);
-          q[r] = ld_gather_f1(itf + (size_t)ii[r] * dim + k);
+          a[r] = ld_gather_f1(uf + (size_t)uu[r] * fs + k);
+          q[r] = ld_gather_f1(itf + (size_t)ii[r] * fs + k);
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = add_rn(acc[r], mul_rn(a[r], abs_item ? fabsf(q[r]) : q[r]));

@@ -39,25 +39,46 @@ class SvdEngine:
         self.hyper = dict(lr=float(lr), reg=float(reg), beta1=float(beta1), beta2=float(beta2), eps=float(eps))
         dev = self.device
         with torch.cuda.device(dev):
-            self.t = {}
+            self.t, self.slots = {}, {}
+            # Feature tables (Adam mode): INTERLEAVED [rows][var | m | v][dim] -- the row of a parameter table and the
+            # rows of its two Adam slots are adjacent, so the table-wide pass reads and writes one stream instead of
+            # three (tfr_svd_tables.feat_stride = 3*dim).  self.t[...] / self.slots[...] are strided VIEWS of it with
+            # the reference's shapes [rows, dim].  SGD mode has no slots: plain [rows][dim].
+            self.feat_stride = 0 if self.sgd else 3 * self.d
+            for n, rows in (("user_feat", self.U), ("item_feat", self.I)):
+                if self.sgd:
+                    self.t[n] = torch.empty(rows, self.d, device=dev)
+                else:
+                    blk = torch.zeros(rows, 3, self.d, device=dev)
+                    self.t[n], self.slots["m_" + n], self.slots["v_" + n] = blk[:, 0], blk[:, 1], blk[:, 2]
             if tables is not None:
                 for n in TABLE_NAMES:
                     a = np.ascontiguousarray(tables[n], dtype=np.float32)
-                    self.t[n] = torch.from_numpy(a.reshape(-1) if n == "mu" else a).to(dev).contiguous()
+                    src = torch.from_numpy(a.reshape(-1) if n == "mu" else a)
+                    if n in self.t:
+                        assert tuple(src.shape) == tuple(self.t[n].shape), (n, src.shape, self.t[n].shape)
+                        self.t[n].copy_(src)
+                    else:
+                        self.t[n] = src.to(dev).contiguous()
             else:
                 g = torch.Generator(device=dev)
                 g.manual_seed(13575 if device_init_seed is None else int(device_init_seed))
                 self.t["mu"] = torch.zeros(1, device=dev)
                 self.t["user_bias"] = torch.zeros(self.U, device=dev)
                 self.t["item_bias"] = torch.zeros(self.I, device=dev)
-                self.t["user_feat"] = torch.empty(self.U, self.d, device=dev)
-                self.t["item_feat"] = torch.empty(self.I, self.d, device=dev)
                 for n in ("user_feat", "item_feat"):
-                    torch.nn.init.trunc_normal_(self.t[n], mean=0.0, std=0.02, a=-0.04, b=0.04, generator=g)
+                    # drawn contiguously, then copied into the strided view (trunc_normal_'s in-place math on a view of
+                    # a 100M-row table would materialise temporaries anyway); chunked to bound the extra memory
+                    rows = self.t[n].shape[0]
+                    step = max(1, min(rows, (1 << 28) // max(self.d, 1)))
+                    for r0 in range(0, rows, step):
+                        tmp = torch.empty(min(step, rows - r0), self.d, device=dev)
+                        torch.nn.init.trunc_normal_(tmp, mean=0.0, std=0.02, a=-0.04, b=0.04, generator=g)
+                        self.t[n][r0:r0 + tmp.shape[0]].copy_(tmp)
+                        del tmp
             assert self.t["user_feat"].shape == (self.U, self.d) and self.t["item_feat"].shape == (self.I, self.d)
-            self.slots = {}
             if not self.sgd:
-                for n in TABLE_NAMES:
+                for n in ("mu", "user_bias", "item_bias"):
                     self.slots["m_" + n] = torch.zeros_like(self.t[n])
                     self.slots["v_" + n] = torch.zeros_like(self.t[n])
             # row -> slot maps: (step stamp << 32 | index of the row's summed gradient); an entry counts only in the
@@ -91,6 +112,7 @@ class SvdEngine:
     def _fill_struct(self):
         s = SvdTables()
         s.user_num, s.item_num, s.dim = self.U, self.I, self.d
+        s.feat_stride = self.feat_stride
         s.mu, s.user_bias, s.item_bias = (self.t[n].data_ptr() for n in ("mu", "user_bias", "item_bias"))
         s.user_feat, s.item_feat = self.t["user_feat"].data_ptr(), self.t["item_feat"].data_ptr()
         if not self.sgd:
@@ -153,7 +175,8 @@ class SvdEngine:
         with torch.cuda.device(dev):
             check(self.L.tfr_allpairs(self.t["user_feat"].data_ptr(), self.t["item_feat"].data_ptr(),
                                       self.t["user_bias"].data_ptr(), self.t["item_bias"].data_ptr(),
-                                      self.t["mu"].data_ptr(), self.U, self.I, self.d, int(use_tensor_cores),
+                                      self.t["mu"].data_ptr(), self.U, self.I, self.d, self.feat_stride,
+                                      self.feat_stride, int(use_tensor_cores),
                                       scores.data_ptr() if want_scores else None, bs.data_ptr() if want_best else None,
                                       bi.data_ptr() if want_best else None, ws.data_ptr(), nbytes, self._stream()))
         return dict(scores=scores, best_score=bs, best_item=bi)

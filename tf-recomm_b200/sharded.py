@@ -67,9 +67,11 @@ class ShardedSvdEngine:
         """Step 2: this rank's half of the row exchange."""
         B, e, st = users.numel(), self.local, self.local._stream()
         check(self.L.tfr_shard_gather_rows(e.t["user_feat"].data_ptr(), e.t["user_bias"].data_ptr(), self.U_loc, self.d,
+                                           e.feat_stride,
                                            users.data_ptr(), B, self.world, self.rank, bufs["g_uf"].data_ptr(),
                                            bufs["g_ub"].data_ptr(), bufs["key_u"].data_ptr(), st))
         check(self.L.tfr_shard_gather_rows(e.t["item_feat"].data_ptr(), e.t["item_bias"].data_ptr(), self.I_loc, self.d,
+                                           e.feat_stride,
                                            items.data_ptr(), B, self.world, self.rank, bufs["g_if"].data_ptr(),
                                            bufs["g_ib"].data_ptr(), bufs["key_i"].data_ptr(), st))
 

@@ -44,6 +44,9 @@ def main():
                 t_.uniform_(1e-6, 1e-2, generator=g)
     ws = eng.step_ws(w["B"])
     tabs = bench._adam_tables(eng, ws, _lib)
+    if os.environ.get("TFR_PASS_NOSLOT"):
+        for k_ in range(4):
+            tabs[k_].slot = None
     st = torch.cuda.current_stream().cuda_stream
     opt = eng.opt.data_ptr()
     for _ in range(3):
@@ -62,6 +65,21 @@ def main():
         check(eng.L.tfr_adam_stream_multi(tabs, 4, opt, 15, st))
     e1.record()
     torch.cuda.synchronize()
+    if os.environ.get("TFR_PASS_INTERLEAVED"):
+        rows = w["U"] + w["I"]
+        T = torch.empty(rows, 3, w["d"], device=eng.device)
+        T[:, 0].normal_(0, 0.02); T[:, 1].normal_(0, 1e-2); T[:, 2].uniform_(1e-6, 1e-2)
+        for co in (1, 0):
+            for _ in range(3):
+                check(eng.L.tfr_experiment_interleaved_pass(T.data_ptr(), rows, w["d"], opt, co, st))
+            e0.record()
+            for _ in range(n):
+                check(eng.L.tfr_experiment_interleaved_pass(T.data_ptr(), rows, w["d"], opt, co, st))
+            e1.record()
+            torch.cuda.synchronize()
+            t_ = e0.elapsed_time(e1) * 1e3 / n
+            print("interleaved [rows][3][%d] %s: %.1f us = %.0f GB/s" % (w["d"], "copy-only" if co else "decay math", t_,
+                                                                         24.0 * rows * w["d"] / t_ / 1e3))
     bytes_ = 24.0 * (w["U"] + w["I"]) * (w["d"] + 1)
     b2b = e0.elapsed_time(e1) * 1e3 / n
     print("%s threads=%s ctas=%s unroll=%s: single median %.1f us (min %.1f), back-to-back %.1f us = %.0f GB/s" % (
