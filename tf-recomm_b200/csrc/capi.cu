@@ -31,6 +31,7 @@ int sm_count() {
 }
 
 int fwd_err_n_partials(int dim, int64_t B);
+int seg_tile(int64_t B, int dim);
 int svd_segment_grads_impl(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
                            const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, int flags_host, void* stream);
 int adam_pass_and_finish(const tfr_adam_table* tabs, int nt, const tfr_svd_tables* t, tfr_opt_scalars* opt,
@@ -87,7 +88,6 @@ extern "C" int tfr_opt_set_se_ring(tfr_opt_scalars* opt_dev, double* se_ring, in
 }
 
 // ---- step workspace ---------------------------------------------------------------------------------
-static constexpr int kTile = 32;
 
 static int64_t carve(char* base, int64_t B, int32_t dim, tfr_svd_step_ws* o) {
   int64_t off = 0;
@@ -96,6 +96,7 @@ static int64_t carve(char* base, int64_t B, int32_t dim, tfr_svd_step_ws* o) {
     off += align_up(bytes, 256);
     return p;
   };
+  const int kTile = seg_tile(B, dim);  // 32, 16 or 8 sorted entries per tile (segsum.cu)
   const int64_t n_tiles = (B + kTile - 1) / kTile;
   tfr_svd_step_ws w;
   memset(&w, 0, sizeof(w));

@@ -26,7 +26,7 @@
 
 namespace tfr {
 
-constexpr int SEG_TILE = 32;
+constexpr int SEG_TILE_MAX = 32;  // tiles of 32, 16 or 8 sorted entries: tfr::seg_tile(B, dim)
 
 struct SegSide {
   const int32_t* sid;      // sorted ids of this table
@@ -126,7 +126,7 @@ __device__ __forceinline__ Acc<VEC> lds_units(const float* row, int unit) {
 
 constexpr int SEG_THREADS = 128;  // CTA of the tiles kernel
 #ifndef SEG_PBASE
-#define SEG_PBASE 8
+#define SEG_PBASE 4
 #endif
 __host__ __device__ constexpr int seg_sub(int units, int lanes) {  // entries per staged sub-batch (<= lanes)
   int p = (SEG_PBASE / units) > 0 ? (SEG_PBASE / units) : 1;
@@ -181,7 +181,7 @@ template <int VEC, int L, int UNITS, bool FUSED, bool GENERIC>
 __global__ void __launch_bounds__(SEG_THREADS) segsum_tiles_kernel(SegSide su, SegSide si, FwdArgs fw,
                                                                    const tfr_opt_scalars* __restrict__ opt,
                                                                    const float* __restrict__ err, int64_t B, int dim,
-                                                                   int n_tiles) {
+                                                                   int n_tiles, int tile) {
   TlScope tl_scope(opt, TFR_TL_TILES);
   constexpr int P = seg_sub(UNITS, L);
   constexpr int SH = ilog2(L) - ilog2(P);  // lane l ends up with the dot of entry l >> SH of the sub-batch
@@ -208,8 +208,8 @@ __global__ void __launch_bounds__(SEG_THREADS) segsum_tiles_kernel(SegSide su, S
 
   const int64_t n_groups = (int64_t)gridDim.x * (SEG_THREADS / L);
   for (int64_t t = (int64_t)blockIdx.x * (SEG_THREADS / L) + threadIdx.x / L; t < n_tiles; t += n_groups) {
-    const int64_t k0 = t * SEG_TILE;
-    const int64_t k1 = min(k0 + SEG_TILE, B);
+    const int64_t k0 = t * tile;
+    const int64_t k1 = min(k0 + tile, B);
     const int32_t prev_id = k0 > 0 ? s.sid[k0 - 1] : -1;
     const int32_t next_id = k1 < B ? s.sid[k1] : -1;
     if (s.sid[k0] >= s.n_rows) {  // the whole tile belongs to other ranks
@@ -466,13 +466,16 @@ __global__ void __launch_bounds__(SEG_THREADS) segsum_tiles_kernel(SegSide su, S
 // thread groups add the cont rows j = g, g+G, g+2G, ... (each in increasing j), then group 0 adds
 // tail + p_0 + p_1 + ... + p_{G-1}: a fixed tree, so the result is deterministic (whatever the order of the list),
 // and a hot row with thousands of occurrences costs ~n/(32*G) dependent steps instead of n/32.
+// CTA of the fix-up.  Measured: 1024 threads (more groups per long run) made it 5x SLOWER -- most list entries are short
+// runs, and a CTA walks its entries one after the other with three block barriers each; many small CTAs win.
+constexpr int FIX_THREADS = 256;
 template <int VEC>
-__global__ void __launch_bounds__(256) segsum_fixup_kernel(SegSide su, SegSide si, const tfr_opt_scalars* __restrict__ opt,
-                                                           uint32_t* counters, int64_t B, int dim, int n_tiles, int cw) {
+__global__ void __launch_bounds__(FIX_THREADS) segsum_fixup_kernel(SegSide su, SegSide si, const tfr_opt_scalars* __restrict__ opt,
+                                                           uint32_t* counters, int64_t B, int dim, int n_tiles, int tile, int cw) {
   TlScope tl_scope(opt, TFR_TL_FIXUP);
   extern __shared__ float s_part[];  // [G][dim] (+ [G] bias partials)
   const SegSide s = blockIdx.y ? si : su;
-  const int G = 256 / cw;
+  const int G = min(FIX_THREADS / cw, 64);  // thread groups that share a run's partial rows (the rest idle)
   const int g = threadIdx.x / cw, c = threadIdx.x % cw;
   const int n_units = dim / VEC;
   __shared__ int s_t1, s_head;
@@ -490,8 +493,8 @@ __global__ void __launch_bounds__(256) segsum_fixup_kernel(SegSide su, SegSide s
       }
       if (threadIdx.x == 0) s_t1 = min(t1, n_tiles - 1);
     } else if (threadIdx.x < 64) {  // head of the run inside t0: ids are sorted, the run is the tile's suffix
-      static_assert(SEG_TILE == 32, "one warp looks at one tile");
-      const int64_t k0 = (int64_t)t0 * SEG_TILE, k1 = min(k0 + SEG_TILE, B);
+      static_assert(SEG_TILE_MAX <= 32, "one warp looks at one tile");
+      const int64_t k0 = (int64_t)t0 * tile, k1 = min(k0 + tile, B);
       const int64_t k = k0 + (threadIdx.x - 32);
       const int32_t last = s.sid[k1 - 1];
       const unsigned same = __ballot_sync(0xffffffffu, k < k1 && s.sid[k] == last);
@@ -499,17 +502,17 @@ __global__ void __launch_bounds__(256) segsum_fixup_kernel(SegSide su, SegSide s
     }
     __syncthreads();
     const int t1 = s_t1;
-    for (int unit = c; unit < n_units; unit += cw) {
+    for (int unit = c; unit < n_units && g < G; unit += cw) {
       Acc<VEC> acc;
 #pragma unroll
       for (int q = 0; q < VEC; ++q) acc.v[q] = 0.0f;
       int tt = t0 + 1 + g;
-      for (; tt + 3 * G <= t1; tt += 4 * G) {  // four independent loads in flight, added in increasing tile order
-        Acc<VEC> x[4];
+      for (; tt + 7 * G <= t1; tt += 8 * G) {  // eight independent loads in flight, added in increasing tile order
+        Acc<VEC> x[8];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) x[r] = load_units<VEC>(s.cont + (size_t)(tt + r * G) * dim, unit);
+        for (int r = 0; r < 8; ++r) x[r] = load_units<VEC>(s.cont + (size_t)(tt + r * G) * dim, unit);
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 8; ++r)
 #pragma unroll
           for (int q = 0; q < VEC; ++q) acc.v[q] = add_rn(acc.v[q], x[r].v[q]);
       }
@@ -521,15 +524,15 @@ __global__ void __launch_bounds__(256) segsum_fixup_kernel(SegSide su, SegSide s
 #pragma unroll
       for (int q = 0; q < VEC; ++q) s_part[(size_t)g * dim + unit * VEC + q] = acc.v[q];
     }
-    if (c == 0) {
+    if (c == 0 && g < G) {
       float ab = 0.0f;
       for (int tt = t0 + 1 + g; tt <= t1; tt += G) ab = add_rn(ab, s.cont_b[tt]);
       bias_part[g] = ab;
     }
     __syncthreads();
-    const int64_t a = (int64_t)t0 * SEG_TILE + s_head;  // sorted index of the run's head: where its gsum lives
+    const int64_t a = (int64_t)t0 * tile + s_head;  // sorted index of the run's head: where its gsum lives
     const int32_t id = s.sid[a];
-    for (int col = threadIdx.x; col < dim; col += 256) {
+    for (int col = threadIdx.x; col < dim; col += FIX_THREADS) {
       float tot = s.tail[(size_t)t0 * dim + col];
       for (int gg = 0; gg < G; ++gg) tot = add_rn(tot, s_part[(size_t)gg * dim + col]);
       s.gsum[(size_t)a * dim + col] = tot;
@@ -581,9 +584,30 @@ static SegGeom seg_geom(int dim) {
   g.units = u <= 1 ? 1 : (u <= 2 ? 2 : (u <= 4 ? 4 : u));
   return g;
 }
+// Tile size: a lane group walks its tile entry by entry (a chain of dependent instructions), so the kernel's time is
+// one tile's latency times the number of waves.  Pick the largest tile of 32 / 16 / 8 entries that still gives every SM
+// a dozen warps; smaller tiles mean more runs crossing tiles, i.e. more fix-up work.
+int seg_tile(int64_t B, int dim) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("TFR_SEG_TILE");
+    forced = e ? atoi(e) : 0;
+    if (forced != 8 && forced != 16 && forced != 32) forced = 0;
+  }
+  if (forced) return forced;
+  const SegGeom g = seg_geom(dim);
+  const int64_t groups_per_warp = 32 / g.lanes;
+  const int64_t want = (int64_t)sm_count() * 12;
+  for (int tile = 32; tile > 8; tile >>= 1) {
+    const int64_t warps = (2 * ((B + tile - 1) / tile) + groups_per_warp - 1) / groups_per_warp;
+    if (warps >= want) return tile;
+  }
+  return 8;
+}
 int segsum_grid_x(int dim, int64_t B) {  // CTAs per side = number of per-CTA partials of the fused forward
   const SegGeom g = seg_geom(dim);
-  const int64_t n_tiles = (B + SEG_TILE - 1) / SEG_TILE;
+  const int tile = seg_tile(B, dim);
+  const int64_t n_tiles = (B + tile - 1) / tile;
   const int64_t groups_per_cta = SEG_THREADS / g.lanes;
   int64_t gx = (n_tiles + groups_per_cta - 1) / groups_per_cta;
   if (gx > TFR_MAX_PARTIALS) gx = TFR_MAX_PARTIALS;
@@ -613,12 +637,13 @@ static int launch_segsum(const SegSide& su, const SegSide& si, int n_sides, cons
                          uint32_t* counters, cudaStream_t st) {
   const SegGeom g = seg_geom(dim);
   const int units = g.units;
-  const int n_tiles = (int)((B + SEG_TILE - 1) / SEG_TILE);
+  const int tile = seg_tile(B, dim);
+  const int n_tiles = (int)((B + tile - 1) / tile);
   int cw = 1;
-  while (cw < dim / g.vec && cw < 256) cw <<= 1;
-  const int G = 256 / cw;
+  while (cw < dim / g.vec && cw < FIX_THREADS) cw <<= 1;
+  const int G = FIX_THREADS / cw < 64 ? FIX_THREADS / cw : 64;
   const size_t fix_smem = ((size_t)G * dim + G) * sizeof(float);
-  dim3 fix_grid((unsigned)min(n_tiles, 2 * sm_count()), (unsigned)n_sides);
+  dim3 fix_grid((unsigned)min(n_tiles, 8 * sm_count()), (unsigned)n_sides);  // 8 resident CTAs per SM and side
   dim3 grid((unsigned)segsum_grid_x(dim, B), (unsigned)n_sides);
   const FwdArgs none{};
   const size_t smem = seg_smem_bytes(dim, g.lanes, units, g.vec);
@@ -627,7 +652,7 @@ static int launch_segsum(const SegSide& su, const SegSide& si, int n_sides, cons
   {                                                                                                                \
     if (int rc = prep_tiles((const void*)segsum_tiles_kernel<V, LL, UU, FU, GE>, smem)) return rc;                 \
     segsum_tiles_kernel<V, LL, UU, FU, GE><<<grid, SEG_THREADS, smem, st>>>(su, si, fw ? *fw : none, opt, err, B, dim, \
-                                                                            n_tiles);                              \
+                                                                            n_tiles, tile);                        \
   }
 #define TFR_SEG_CASE(V, LL, UU)                                                                                   \
   if (g.vec == V && g.lanes == LL && units == UU) {                                                               \
@@ -637,7 +662,7 @@ static int launch_segsum(const SegSide& su, const SegSide& si, int n_sides, cons
     else if (generic) TFR_SEG_LAUNCH(V, LL, UU, false, true)                                                       \
     else TFR_SEG_LAUNCH(V, LL, UU, false, false)                                                                   \
     TFR_LAUNCH_CHECK();                                                                                            \
-    segsum_fixup_kernel<V><<<fix_grid, 256, fix_smem, st>>>(su, si, opt, counters, B, dim, n_tiles, cw);          \
+    segsum_fixup_kernel<V><<<fix_grid, FIX_THREADS, fix_smem, st>>>(su, si, opt, counters, B, dim, n_tiles, tile, cw);    \
     TFR_LAUNCH_CHECK();                                                                                            \
     return TFR_OK;                                                                                                 \
   }
