@@ -176,34 +176,31 @@ def _adam_tables(eng, ws, _lib):
 
 def kernel_roofline(eng, w, cols, steps, torch, peak, peak_src):
     """Times the dominant kernel (adam_stream_multi_kernel: the whole-table TF-Adam pass, every row of all four
-    tables in one launch) live, IN SITU: the step graphs are captured once more with event-record nodes
-    (torch.cuda.Event(external=True)) on the main stream right before and after the pass, so the events bracket the
-    launch inside the same replayed graph the throughput is measured on -- the next batch's assemble + id sort run
-    beside it on the side stream, exactly as in the timed region."""
-    from tf_recomm_b200._lib import check
+    tables in one launch) live and IN SITU: complete pipelined steps are issued on the streams (same kernels, same
+    side-stream fork as the captured graph: the next batch's assemble + id sort run beside the pass) with CUDA events
+    recorded on the launching stream right before and right after the pass.  Stream-ordered events add almost
+    nothing; event-record NODES inside a captured graph measured ~20 us more for the same launch (node-to-node
+    latency on both sides), so the eager issue is used for this one number."""
     B, d, U, I = w["B"], w["d"], w["U"], w["I"]
-    ev = {(tag, slot): torch.cuda.Event(enable_timing=True, external=True)
-          for tag in ("pass_begin", "pass_end") for slot in (0, 1)}
-    eng.timing_hook = lambda tag, slot, stream: ev[(tag, slot)].record(stream)
+    pairs = []
+
+    def hook(tag, slot, stream):
+        if tag == "pass_begin":
+            pairs.append([torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)])
+            pairs[-1][0].record(stream)
+        else:
+            pairs[-1][1].record(stream)
+    eng.set_batch_cursor(0)
+    eng.run_stream_steps(2, use_graph=True)   # leaves a buffer set primed for the batch at the cursor
+    torch.cuda.synchronize()
+    eng.timing_hook = hook
     try:
-        graphs = [eng._capture(lambda s_=slot: eng._enqueue_pipelined_step(B, s_)) for slot in (0, 1)]
+        eng.run_stream_steps(max(steps, 4), use_graph=False)
     finally:
         eng.timing_hook = None
-    eng.set_batch_cursor(0)
-    eng.run_stream_steps(2, use_graph=True)   # leaves buffer set 0 primed for the batch at the cursor
     torch.cuda.synchronize()
-    st = torch.cuda.current_stream().cuda_stream
-    tot_ms, n = 0.0, 0
-    for s in range(2 * (max(steps, 2) // 2)):
-        slot = s & 1
-        check(eng.L.tfr_graph_launch(graphs[slot], st))
-        torch.cuda.synchronize()
-        if s >= 2:
-            tot_ms += ev[("pass_begin", slot)].elapsed_time(ev[("pass_end", slot)])
-            n += 1
-    for g in graphs:
-        eng.L.tfr_graph_destroy(g)
-    eng._primed = None
+    times = [p[0].elapsed_time(p[1]) for p in pairs[2:]]
+    tot_ms, n = float(sum(times)), len(times)
     bytes_launch = 24.0 * (U + I) * (d + 1)
     achieved = bytes_launch / (tot_ms / n / 1e3) / 1e9
     traffic, traffic_src = None, None
@@ -215,8 +212,8 @@ def kernel_roofline(eng, w, cols, steps, torch, peak, peak_src):
     return {"bound": "hbm", "kernel": "adam_stream_multi_kernel (TF-Adam pass over every row of all tables, one launch)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
             "bytes_per_launch": bytes_launch, "launch_ms": tot_ms / n, "launches_timed": n,
-            "how": "CUDA event-record nodes around the launch inside the replayed step graph (in situ, next batch's "
-                   "id sort running beside it)",
+            "how": "CUDA events on the launching stream right before / after the launch, inside complete pipelined "
+                   "steps (in situ: the next batch's assemble + id sort run beside it on the side stream)",
             "algorithmic_bytes": "24 B/param x (users+items) x (dim+1)", "traffic": traffic, "traffic_source": traffic_src}
 
 

@@ -1,0 +1,75 @@
+"""The reference's entry point on the GPU: `python svd_train_val.py` (svd_train_val.py:201-207) end to end, in the two
+ways this repo can run its step loop, and the checkpoint it leaves (svd_train_val.py:197-198, adaptive_test.py:40)."""
+import io
+import os
+import re
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(argv):
+    import svd_train_val
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        svd_train_val.main(argv)
+    return buf.getvalue()
+
+
+def _errors(text):
+    """(epoch, train rmse, val rmse) from the lines `  e TRAIN(size=../.., rmse=..) TEST(size=.., rmse=..) ..(s)`
+    (the reference's third print format, svd_train_val.py:180)."""
+    out = []
+    for line in text.splitlines():
+        m = re.match(r"^\s*(\d+) TRAIN\(size=\d+/\d+, rmse=([0-9.]+)\) TEST\(size=\d+, rmse=([0-9.]+)\)", line)
+        if m:
+            out.append((int(m.group(1)), float(m.group(2)), float(m.group(3))))
+    return out
+
+
+def test_driver_session_and_stream_modes_agree(tmp_path):
+    """--mode session feeds every batch through sess.run(feed_dict) like the reference; --mode stream replays captured
+    graphs on device-resident columns with the SAME index stream (np.random.seed(13575) + ShuffleIterator draws):
+    the reported train / val errors must coincide, and the RMSE must fall."""
+    common = ["--synthetic", "ml1m", "--ratings", "60000", "--epochs", "4", "--batch", "1000", "--dim", "15"]
+    a = _errors(_run(common + ["--mode", "session", "--checkpoint", str(tmp_path / "a.ckpt")]))
+    b = _errors(_run(common + ["--mode", "stream", "--checkpoint", str(tmp_path / "b.ckpt")]))
+    assert len(a) >= 4 and len(a) == len(b)
+    for (ea, ta, va), (eb, tb, vb) in zip(a, b):
+        assert ea == eb
+        assert ta == pytest.approx(tb, rel=2e-6) and va == pytest.approx(vb, rel=2e-6)
+    assert a[-1][2] < a[0][2]          # validation RMSE went down
+    za, zb = np.load(str(tmp_path / "a.ckpt")), np.load(str(tmp_path / "b.ckpt"))
+    for n in ("mu", "user_bias", "item_bias", "user_feat", "item_feat", "m_user_feat", "v_item_feat"):
+        assert np.array_equal(za[n], zb[n]), n   # same kernels, same batches: bit-identical tables
+    assert int(za["__step__"][0]) == int(zb["__step__"][0]) > 0
+
+
+def test_checkpoint_restore_continues_bit_identically(tmp_path):
+    """save -> restore into a fresh engine -> the next steps equal those of the engine that never stopped (interleaved
+    tables, stamped slot maps and the Adam scalars all survive the round trip)."""
+    from tf_recomm_b200 import init
+    from tf_recomm_b200.engine import SvdEngine
+    rng = np.random.default_rng(0)
+    U, I, d, B = 300, 200, 128, 2048
+    tabs = init.init_tables(U, I, d, seed=2)
+    eng = SvdEngine(U, I, d, 1e-3, 0.05, tables=tabs)
+    batches = [(rng.integers(0, U, B).astype(np.int32), rng.integers(0, I, B).astype(np.int32),
+                rng.integers(1, 6, B).astype(np.float32)) for _ in range(6)]
+    for b in batches[:3]:
+        eng.train_step(*b)
+    path = str(tmp_path / "fm.ckpt")
+    eng.save(path)
+    other = SvdEngine(U, I, d, 1e-3, 0.05, tables=init.init_tables(U, I, d, seed=9))
+    other.restore(path)
+    assert other.global_step == 3
+    for b in batches[3:]:
+        la, _ = eng.train_step(*b)
+        lb, _ = other.train_step(*b)
+        assert np.array_equal(la.cpu().numpy(), lb.cpu().numpy())
+    ta, tb = eng.get_tables(), other.get_tables()
+    for n in ta:
+        assert np.array_equal(ta[n], tb[n]), n
