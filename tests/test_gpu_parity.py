@@ -221,7 +221,11 @@ def test_segment_grads_vs_oracle(d, B, flags):
 
 
 @pytest.mark.parametrize("U,I,d,B,steps", [(50, 30, 15, 64, 25), (301, 157, 20, 500, 10), (6040, 3952, 15, 1000, 10),
-                                           (2000, 1000, 128, 4096, 6), (97, 61, 33, 200, 8)])
+                                           (2000, 1000, 128, 4096, 6), (97, 61, 33, 200, 8),
+                                           # ragged / extreme batches: a single occurrence, fewer than one tile, a batch
+                                           # beyond 1024 CTAs' worth of tiles (grid-stride over tiles), one row per table
+                                           (20, 10, 15, 1, 6), (20, 10, 128, 5, 6), (900, 700, 20, 300000, 2), (900, 700, 15, 300000, 2),
+                                           (1, 1, 4, 33, 5), (3000, 2000, 256, 2000, 3), (40, 30, 1, 100, 5)])
 def test_train_step_parity_readme_adam(U, I, d, B, steps):
     """README model: squared error + L2 on gathered embeddings + TF sparse Adam (whole-table decay)."""
     rng = np.random.default_rng(U + d)
@@ -232,7 +236,11 @@ def test_train_step_parity_readme_adam(U, I, d, B, steps):
         ref_logits, ref_infer = orc.train_step(users, items, rates)
         np.testing.assert_allclose(logits.cpu().numpy(), ref_logits, rtol=RTOL, atol=1e-6, err_msg="step %d" % s)
         np.testing.assert_allclose(infer.cpu().numpy(), ref_infer, rtol=RTOL, atol=1e-6)
-        assert_state_close(eng, orc, "step %d" % s)
+        # rows with hundreds of occurrences per step: the oracle adds them one after the other, the kernel tile by
+        # tile -- two fp32 orders of a ~n-term sum differ by ~sqrt(n)*eps of the LARGEST partial sum, which shows in
+        # the slots (m = (1-b1) * sum) when the terms cancel; the parameters stay within 1e-5 (as in
+        # test_duplicate_heavy_batches)
+        assert_state_close(eng, orc, "step %d" % s, slot_rtol=RTOL if B <= 100 * min(U, I) else 5e-5)
     sc = eng.opt_scalars()
     assert sc.global_step == steps == orc.global_step
     assert sc.beta1_power == pytest.approx(orc.s.beta1_power, rel=0, abs=0)   # same fp32 multiply chain
