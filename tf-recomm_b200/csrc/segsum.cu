@@ -462,47 +462,110 @@ __global__ void __launch_bounds__(SEG_THREADS) segsum_tiles_kernel(SegSide su, S
 }
 
 // Fix-up: a persistent grid walks the work list of TILE_START tiles.  A run that begins in tile t0 and ends in
-// tile t1 has the partial sums tail[t0], cont[t0+1], ..., cont[t1]; tiles t0+1..t1-1 are TILE_MID.  The CTA's G
-// thread groups add the cont rows j = g, g+G, g+2G, ... (each in increasing j), then group 0 adds
-// tail + p_0 + p_1 + ... + p_{G-1}: a fixed tree, so the result is deterministic (whatever the order of the list),
-// and a hot row with thousands of occurrences costs ~n/(32*G) dependent steps instead of n/32.
-// CTA of the fix-up.  Measured: 1024 threads (more groups per long run) made it 5x SLOWER -- most list entries are short
-// runs, and a CTA walks its entries one after the other with three block barriers each; many small CTAs win.
+// tile t1 has the partial sums tail[t0], cont[t0+1], ..., cont[t1]; tiles t0+1..t1-1 are TILE_MID.
+//  * Short chains (t1 - t0 <= FIX_SHORT, almost all of them) are summed by ONE WARP each, in tile order, eight
+//    partial rows in flight: no block barrier, thousands of chains side by side.
+//  * Long chains (a hot row with thousands of occurrences) are parked in the CTA's shared list and summed afterwards
+//    by the whole CTA: G thread groups add the cont rows j = g, g+G, g+2G, ... (each in increasing j), then
+//    tail + p_0 + ... + p_{G-1}.
+// Both are fixed functions of (t0, t1): the result does not depend on the order of the list or on which warp /
+// CTA picked an entry up.
 constexpr int FIX_THREADS = 256;
+constexpr int FIX_SHORT = 32;      // partial rows one warp sums on its own
+constexpr int FIX_LONG_CAP = 32;   // long chains a CTA can park (more: the warp sums them itself, slowly)
+
 template <int VEC>
 __global__ void __launch_bounds__(FIX_THREADS) segsum_fixup_kernel(SegSide su, SegSide si, const tfr_opt_scalars* __restrict__ opt,
-                                                           uint32_t* counters, int64_t B, int dim, int n_tiles, int tile, int cw) {
+                                                                   uint32_t* counters, int64_t B, int dim, int n_tiles,
+                                                                   int tile, int cw) {
   TlScope tl_scope(opt, TFR_TL_FIXUP);
   extern __shared__ float s_part[];  // [G][dim] (+ [G] bias partials)
+  __shared__ int s_long[FIX_LONG_CAP][2];
+  __shared__ int s_nlong;
   const SegSide s = blockIdx.y ? si : su;
-  const int G = min(FIX_THREADS / cw, 64);  // thread groups that share a run's partial rows (the rest idle)
-  const int g = threadIdx.x / cw, c = threadIdx.x % cw;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_units = dim / VEC;
-  __shared__ int s_t1, s_head;
+  const uint32_t stamp = (uint32_t)opt->global_step;
   const uint32_t n_fix = min(*s.fix_count, (uint32_t)n_tiles);
-  float* bias_part = s_part + (size_t)G * dim;
-  for (uint32_t w = blockIdx.x; w < n_fix; w += gridDim.x) {
-    const int t0 = s.fix_list[w];
-    if (threadIdx.x < 32) {  // t1 = first tile after t0 that is not TILE_MID
-      int t1 = -1;
-      for (int base = t0 + 1; t1 < 0; base += 32) {
-        const int tt = base + threadIdx.x;
-        const bool stop = tt >= n_tiles || !(s.kind[tt] & TILE_MID);
-        const unsigned m = __ballot_sync(0xffffffffu, stop);
-        if (m) t1 = base + __ffs(m) - 1;
-      }
-      if (threadIdx.x == 0) s_t1 = min(t1, n_tiles - 1);
-    } else if (threadIdx.x < 64) {  // head of the run inside t0: ids are sorted, the run is the tile's suffix
-      static_assert(SEG_TILE_MAX <= 32, "one warp looks at one tile");
-      const int64_t k0 = (int64_t)t0 * tile, k1 = min(k0 + tile, B);
-      const int64_t k = k0 + (threadIdx.x - 32);
-      const int32_t last = s.sid[k1 - 1];
-      const unsigned same = __ballot_sync(0xffffffffu, k < k1 && s.sid[k] == last);
-      if (threadIdx.x == 32) s_head = __ffs(same) - 1;
+  if (threadIdx.x == 0) s_nlong = 0;
+  __syncthreads();
+
+  // t1 = first tile after t0 that is not TILE_MID; head = sorted index of the run's first entry (ids are sorted:
+  // the run is the suffix of tile t0)
+  static_assert(SEG_TILE_MAX <= 32, "one warp looks at one tile");
+  auto chain_of = [&](int t0, int& t1, int64_t& head) {
+    const int64_t k0 = (int64_t)t0 * tile, k1 = min(k0 + tile, B);
+    const int32_t last = s.sid[k1 - 1];
+    const int64_t k = k0 + lane;
+    const unsigned same = __ballot_sync(0xffffffffu, k < k1 && s.sid[k] == last);
+    head = k0 + __ffs(same) - 1;
+    t1 = -1;
+    for (int base = t0 + 1; t1 < 0; base += 32) {
+      const int tt = base + lane;
+      const bool stop = tt >= n_tiles || !(s.kind[tt] & TILE_MID);
+      const unsigned m = __ballot_sync(0xffffffffu, stop);
+      if (m) t1 = base + __ffs(m) - 1;
     }
-    __syncthreads();
-    const int t1 = s_t1;
-    for (int unit = c; unit < n_units && g < G; unit += cw) {
+    t1 = min(t1, n_tiles - 1);
+  };
+  // one warp: tail[t0] + cont[t0+1] + ... + cont[t1], in that order
+  auto warp_chain = [&](int t0, int t1, int64_t head) {
+    for (int unit = lane; unit < n_units; unit += 32) {
+      Acc<VEC> acc = load_units<VEC>(s.tail + (size_t)t0 * dim, unit);
+      int tt = t0 + 1;
+      for (; tt + 7 <= t1; tt += 8) {
+        Acc<VEC> x[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) x[r] = load_units<VEC>(s.cont + (size_t)(tt + r) * dim, unit);
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc.v[q] = add_rn(acc.v[q], x[r].v[q]);
+      }
+      for (; tt <= t1; ++tt) {
+        const Acc<VEC> x = load_units<VEC>(s.cont + (size_t)tt * dim, unit);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc.v[q] = add_rn(acc.v[q], x.v[q]);
+      }
+      store_units<VEC>(s.gsum + (size_t)head * dim, unit, acc);
+    }
+    if (lane == 0) {
+      float tot = s.tail_b[t0];
+      for (int tt = t0 + 1; tt <= t1; ++tt) tot = add_rn(tot, s.cont_b[tt]);
+      s.gsum_b[head] = tot;
+      s.slot[s.sid[head]] = pack_slot(stamp, head);
+    }
+  };
+
+  const uint32_t n_warps = gridDim.x * (FIX_THREADS / 32);
+  for (uint32_t w = blockIdx.x * (FIX_THREADS / 32) + warp; w < n_fix; w += n_warps) {
+    const int t0 = s.fix_list[w];
+    int t1;
+    int64_t head;
+    chain_of(t0, t1, head);
+    if (t1 - t0 <= FIX_SHORT) {
+      warp_chain(t0, t1, head);
+    } else {
+      int at = FIX_LONG_CAP;
+      if (lane == 0) at = atomicAdd(&s_nlong, 1);
+      at = __shfl_sync(0xffffffffu, at, 0);
+      if (at < FIX_LONG_CAP) {
+        if (lane == 0) { s_long[at][0] = t0; s_long[at][1] = t1; }
+      } else {
+        warp_chain(t0, t1, head);  // the CTA's list is full: correct, just not parallel
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- the parked long chains, one after the other, by the whole CTA ----
+  const int n_long = min(s_nlong, FIX_LONG_CAP);
+  const int G = FIX_THREADS / cw;
+  const int g = threadIdx.x / cw, c = threadIdx.x % cw;
+  float* bias_part = s_part + (size_t)G * dim;
+  for (int e = 0; e < n_long; ++e) {
+    const int t0 = s_long[e][0], t1 = s_long[e][1];
+    for (int unit = c; unit < n_units; unit += cw) {
       Acc<VEC> acc;
 #pragma unroll
       for (int q = 0; q < VEC; ++q) acc.v[q] = 0.0f;
@@ -524,14 +587,17 @@ __global__ void __launch_bounds__(FIX_THREADS) segsum_fixup_kernel(SegSide su, S
 #pragma unroll
       for (int q = 0; q < VEC; ++q) s_part[(size_t)g * dim + unit * VEC + q] = acc.v[q];
     }
-    if (c == 0 && g < G) {
+    if (c == 0) {
       float ab = 0.0f;
       for (int tt = t0 + 1 + g; tt <= t1; tt += G) ab = add_rn(ab, s.cont_b[tt]);
       bias_part[g] = ab;
     }
     __syncthreads();
-    const int64_t a = (int64_t)t0 * tile + s_head;  // sorted index of the run's head: where its gsum lives
-    const int32_t id = s.sid[a];
+    // head of the run inside t0 (every thread finds it for itself: the tile's ids are one cached line)
+    const int64_t k0 = (int64_t)t0 * tile, k1 = min(k0 + tile, B);
+    const int32_t id = s.sid[k1 - 1];
+    int64_t a = k1 - 1;
+    while (a > k0 && s.sid[a - 1] == id) --a;
     for (int col = threadIdx.x; col < dim; col += FIX_THREADS) {
       float tot = s.tail[(size_t)t0 * dim + col];
       for (int gg = 0; gg < G; ++gg) tot = add_rn(tot, s_part[(size_t)gg * dim + col]);
@@ -541,9 +607,9 @@ __global__ void __launch_bounds__(FIX_THREADS) segsum_fixup_kernel(SegSide su, S
       float tot = s.tail_b[t0];
       for (int gg = 0; gg < G; ++gg) tot = add_rn(tot, bias_part[gg]);
       s.gsum_b[a] = tot;
-      s.slot[id] = pack_slot((uint32_t)opt->global_step, a);
+      s.slot[id] = pack_slot(stamp, a);
     }
-    __syncthreads();  // s_part / s_t1 are reused by the next list entry
+    __syncthreads();  // s_part is reused by the next long chain
   }
   // the last CTA to finish empties the work lists for the next use of this workspace
   if (threadIdx.x == 0) {
@@ -641,9 +707,10 @@ static int launch_segsum(const SegSide& su, const SegSide& si, int n_sides, cons
   const int n_tiles = (int)((B + tile - 1) / tile);
   int cw = 1;
   while (cw < dim / g.vec && cw < FIX_THREADS) cw <<= 1;
-  const int G = FIX_THREADS / cw < 64 ? FIX_THREADS / cw : 64;
+  const int G = FIX_THREADS / cw;
   const size_t fix_smem = ((size_t)G * dim + G) * sizeof(float);
-  dim3 fix_grid((unsigned)min(n_tiles, 8 * sm_count()), (unsigned)n_sides);  // 8 resident CTAs per SM and side
+  // a warp per list entry: at most one entry per tile, so (n_tiles + 7) / 8 CTAs of 8 warps cover any list in one trip
+  dim3 fix_grid((unsigned)min((n_tiles + 7) / 8, 4 * sm_count()), (unsigned)n_sides);
   dim3 grid((unsigned)segsum_grid_x(dim, B), (unsigned)n_sides);
   const FwdArgs none{};
   const size_t smem = seg_smem_bytes(dim, g.lanes, units, g.vec);
