@@ -90,13 +90,15 @@ __device__ __forceinline__ unsigned long long gtimer() {
 struct TlScope {
   unsigned long long* tl;
   int slot;
-  __device__ __forceinline__ TlScope(const tfr_opt_scalars* opt, int slot_) : tl(nullptr), slot(slot_) {
+  __device__ __forceinline__ TlScope(const tfr_opt_scalars* opt, int slot_, bool every_cta = false)
+      : tl(nullptr), slot(slot_) {
     if (opt) tl = reinterpret_cast<unsigned long long*>(opt->timeline);
     // sampled so that the stamps do not serialise on one address: entry = first CTAs, exit = every 64th CTA
-    // and the grid's last 8 (which are scheduled last), one warp each
+    // and the grid's last 8 (which are scheduled last), one warp each; every_cta: kernels whose CTAs finish at very
+    // different times (the fix-up: the CTA with the hottest row ends last, whatever its index)
     if (tl) {
       const unsigned bid = blockIdx.x + blockIdx.y * gridDim.x, nb = gridDim.x * gridDim.y;
-      sampled = bid + 8 >= nb || (bid & 63u) == 0;
+      sampled = every_cta || bid + 8 >= nb || (bid & 63u) == 0;
       if (bid < 4 && threadIdx.x == 0) atomicMin(tl + slot, gtimer());
     }
   }

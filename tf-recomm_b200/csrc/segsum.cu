@@ -478,7 +478,7 @@ template <int VEC>
 __global__ void __launch_bounds__(FIX_THREADS) segsum_fixup_kernel(SegSide su, SegSide si, const tfr_opt_scalars* __restrict__ opt,
                                                                    uint32_t* counters, int64_t B, int dim, int n_tiles,
                                                                    int tile, int cw) {
-  TlScope tl_scope(opt, TFR_TL_FIXUP);
+  TlScope tl_scope(opt, TFR_TL_FIXUP, true);
   extern __shared__ float s_part[];  // [G][dim] (+ [G] bias partials)
   __shared__ int s_long[FIX_LONG_CAP][2];
   __shared__ int s_nlong;
@@ -500,38 +500,50 @@ __global__ void __launch_bounds__(FIX_THREADS) segsum_fixup_kernel(SegSide su, S
     const unsigned same = __ballot_sync(0xffffffffu, k < k1 && s.sid[k] == last);
     head = k0 + __ffs(same) - 1;
     t1 = -1;
-    for (int base = t0 + 1; t1 < 0; base += 32) {
-      const int tt = base + lane;
-      const bool stop = tt >= n_tiles || !(s.kind[tt] & TILE_MID);
-      const unsigned m = __ballot_sync(0xffffffffu, stop);
-      if (m) t1 = base + __ffs(m) - 1;
+    for (int base = t0 + 1; t1 < 0; base += 128) {  // four loads per lane in flight: a hot row's chain is hundreds of tiles
+      bool stop[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int tt = base + 32 * r + lane;
+        stop[r] = tt >= n_tiles || !(s.kind[tt] & TILE_MID);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const unsigned m = __ballot_sync(0xffffffffu, stop[r]);
+        if (m && t1 < 0) t1 = base + 32 * r + __ffs(m) - 1;
+      }
     }
     t1 = min(t1, n_tiles - 1);
   };
-  // one warp: tail[t0] + cont[t0+1] + ... + cont[t1], in that order
+  // the chain's bias partials, summed by one warp: lane l adds cont_b[t0+1+l], cont_b[t0+1+l+32], ... then a
+  // butterfly over the lanes -- a fixed function of (t0, t1), and 32 loads in flight instead of a serial chain
+  auto warp_bias_sum = [&](int t0, int t1) {
+    float part = 0.0f;
+    for (int tt = t0 + 1 + lane; tt <= t1; tt += 32) part = add_rn(part, s.cont_b[tt]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part = add_rn(part, __shfl_xor_sync(0xffffffffu, part, o));
+    return add_rn(s.tail_b[t0], part);
+  };
+  // one warp: tail[t0] + cont[t0+1] + ... + cont[t1], in that order, eight rows in flight
   auto warp_chain = [&](int t0, int t1, int64_t head) {
     for (int unit = lane; unit < n_units; unit += 32) {
       Acc<VEC> acc = load_units<VEC>(s.tail + (size_t)t0 * dim, unit);
-      int tt = t0 + 1;
-      for (; tt + 7 <= t1; tt += 8) {
+      for (int tt = t0 + 1; tt <= t1; tt += 8) {
         Acc<VEC> x[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) x[r] = load_units<VEC>(s.cont + (size_t)(tt + r) * dim, unit);
+        for (int r = 0; r < 8; ++r)
+          if (tt + r <= t1) x[r] = load_units<VEC>(s.cont + (size_t)(tt + r) * dim, unit);
 #pragma unroll
         for (int r = 0; r < 8; ++r)
+          if (tt + r <= t1) {
 #pragma unroll
-          for (int q = 0; q < VEC; ++q) acc.v[q] = add_rn(acc.v[q], x[r].v[q]);
-      }
-      for (; tt <= t1; ++tt) {
-        const Acc<VEC> x = load_units<VEC>(s.cont + (size_t)tt * dim, unit);
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) acc.v[q] = add_rn(acc.v[q], x.v[q]);
+            for (int q = 0; q < VEC; ++q) acc.v[q] = add_rn(acc.v[q], x[r].v[q]);
+          }
       }
       store_units<VEC>(s.gsum + (size_t)head * dim, unit, acc);
     }
+    const float tot = warp_bias_sum(t0, t1);
     if (lane == 0) {
-      float tot = s.tail_b[t0];
-      for (int tt = t0 + 1; tt <= t1; ++tt) tot = add_rn(tot, s.cont_b[tt]);
       s.gsum_b[head] = tot;
       s.slot[s.sid[head]] = pack_slot(stamp, head);
     }
@@ -562,36 +574,29 @@ __global__ void __launch_bounds__(FIX_THREADS) segsum_fixup_kernel(SegSide su, S
   const int n_long = min(s_nlong, FIX_LONG_CAP);
   const int G = FIX_THREADS / cw;
   const int g = threadIdx.x / cw, c = threadIdx.x % cw;
-  float* bias_part = s_part + (size_t)G * dim;
   for (int e = 0; e < n_long; ++e) {
     const int t0 = s_long[e][0], t1 = s_long[e][1];
     for (int unit = c; unit < n_units; unit += cw) {
       Acc<VEC> acc;
 #pragma unroll
       for (int q = 0; q < VEC; ++q) acc.v[q] = 0.0f;
-      int tt = t0 + 1 + g;
-      for (; tt + 7 * G <= t1; tt += 8 * G) {  // eight independent loads in flight, added in increasing tile order
+      for (int tt = t0 + 1 + g; tt <= t1; tt += 8 * G) {  // eight rows in flight, added in increasing tile order
         Acc<VEC> x[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) x[r] = load_units<VEC>(s.cont + (size_t)(tt + r * G) * dim, unit);
+        for (int r = 0; r < 8; ++r)
+          if (tt + r * G <= t1) x[r] = load_units<VEC>(s.cont + (size_t)(tt + r * G) * dim, unit);
 #pragma unroll
         for (int r = 0; r < 8; ++r)
+          if (tt + r * G <= t1) {
 #pragma unroll
-          for (int q = 0; q < VEC; ++q) acc.v[q] = add_rn(acc.v[q], x[r].v[q]);
-      }
-      for (; tt <= t1; tt += G) {
-        const Acc<VEC> x = load_units<VEC>(s.cont + (size_t)tt * dim, unit);
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) acc.v[q] = add_rn(acc.v[q], x.v[q]);
+            for (int q = 0; q < VEC; ++q) acc.v[q] = add_rn(acc.v[q], x[r].v[q]);
+          }
       }
 #pragma unroll
       for (int q = 0; q < VEC; ++q) s_part[(size_t)g * dim + unit * VEC + q] = acc.v[q];
     }
-    if (c == 0) {
-      float ab = 0.0f;
-      for (int tt = t0 + 1 + g; tt <= t1; tt += G) ab = add_rn(ab, s.cont_b[tt]);
-      bias_part[g] = ab;
-    }
+    float bias_tot = 0.0f;
+    if (warp == FIX_THREADS / 32 - 1) bias_tot = warp_bias_sum(t0, t1);  // the last warp, beside its row work
     __syncthreads();
     // head of the run inside t0 (every thread finds it for itself: the tile's ids are one cached line)
     const int64_t k0 = (int64_t)t0 * tile, k1 = min(k0 + tile, B);
@@ -603,10 +608,8 @@ __global__ void __launch_bounds__(FIX_THREADS) segsum_fixup_kernel(SegSide su, S
       for (int gg = 0; gg < G; ++gg) tot = add_rn(tot, s_part[(size_t)gg * dim + col]);
       s.gsum[(size_t)a * dim + col] = tot;
     }
-    if (threadIdx.x == 0) {
-      float tot = s.tail_b[t0];
-      for (int gg = 0; gg < G; ++gg) tot = add_rn(tot, bias_part[gg]);
-      s.gsum_b[a] = tot;
+    if (threadIdx.x == FIX_THREADS - 32) {  // lane 0 of the warp that summed the bias partials
+      s.gsum_b[a] = bias_tot;
       s.slot[id] = pack_slot(stamp, a);
     }
     __syncthreads();  // s_part is reused by the next long chain
@@ -709,8 +712,9 @@ static int launch_segsum(const SegSide& su, const SegSide& si, int n_sides, cons
   while (cw < dim / g.vec && cw < FIX_THREADS) cw <<= 1;
   const int G = FIX_THREADS / cw;
   const size_t fix_smem = ((size_t)G * dim + G) * sizeof(float);
-  // a warp per list entry: at most one entry per tile, so (n_tiles + 7) / 8 CTAs of 8 warps cover any list in one trip
-  dim3 fix_grid((unsigned)min((n_tiles + 7) / 8, 4 * sm_count()), (unsigned)n_sides);
+  // a warp per list entry: at most one entry per tile, so n_tiles / (warps per CTA) CTAs cover any list in one trip
+  const int fix_warps = FIX_THREADS / 32;
+  dim3 fix_grid((unsigned)min((n_tiles + fix_warps - 1) / fix_warps, 4 * sm_count()), (unsigned)n_sides);
   dim3 grid((unsigned)segsum_grid_x(dim, B), (unsigned)n_sides);
   const FwdArgs none{};
   const size_t smem = seg_smem_bytes(dim, g.lanes, units, g.vec);
@@ -723,7 +727,7 @@ static int launch_segsum(const SegSide& su, const SegSide& si, int n_sides, cons
   }
 #define TFR_SEG_CASE(V, LL, UU)                                                                                   \
   if (g.vec == V && g.lanes == LL && units == UU) {                                                               \
-    TFR_PREP((segsum_fixup_kernel<V>));                                                                            \
+    if (int rc = prep_tiles((const void*)segsum_fixup_kernel<V>, fix_smem)) return rc; /* same carve-out as the tiles */ \
     if (fw && generic) TFR_SEG_LAUNCH(V, LL, UU, true, true)                                                       \
     else if (fw) TFR_SEG_LAUNCH(V, LL, UU, true, false)                                                            \
     else if (generic) TFR_SEG_LAUNCH(V, LL, UU, false, true)                                                       \
