@@ -45,7 +45,7 @@ void prep_kernel(const void* fn) {
   static int carve = -1;
   if (carve < 0) {
     const char* e = getenv("TFR_SMEM_CARVEOUT");
-    carve = e ? atoi(e) : 50;
+    carve = e ? atoi(e) : 62;  // 141 KB of shared memory: four CTAs of the segment-sum kernel (32 KB each) per SM
   }
   if (carve > 0) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   cudaGetLastError();

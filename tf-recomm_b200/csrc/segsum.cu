@@ -684,9 +684,8 @@ int segsum_grid_x(int dim, int64_t B) {  // CTAs per side = number of per-CTA pa
 }
 }  // namespace tfr
 
-// the tiles kernel stages rows in dynamic shared memory (up to 64 KB per CTA): opt in once per instantiation, and
-// take the largest carve-out so that three CTAs fit an SM (the kernel runs alone on its stream: the id-only work
-// of the next batch is scheduled under the table pass, not beside the tiles)
+// the tiles kernel stages rows in dynamic shared memory (32 KB per CTA at dim 128, up to 64 KB): opt in once per
+// instantiation
 static int prep_tiles(const void* fn, size_t smem) {
   static std::mutex mu;
   static std::map<const void*, size_t> done;
@@ -694,7 +693,13 @@ static int prep_tiles(const void* fn, size_t smem) {
   auto it = done.find(fn);
   if (it != done.end() && it->second >= smem) return TFR_OK;
   TFR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TFR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  static int carve = -2;
+  // the same carve-out as every other kernel of the step (common.cuh: prep_kernel), so that no SM has to be
+  // reconfigured between the pass, the tiles and the fix-up; TFR_TILES_CARVEOUT to experiment (100 = max shared)
+  if (carve == -2)
+    carve = getenv("TFR_TILES_CARVEOUT") ? atoi(getenv("TFR_TILES_CARVEOUT"))
+                                         : (getenv("TFR_SMEM_CARVEOUT") ? atoi(getenv("TFR_SMEM_CARVEOUT")) : 62);
+  TFR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   done[fn] = smem;
   return TFR_OK;
 }
