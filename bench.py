@@ -376,7 +376,46 @@ def main():
                         "readme_epoch_s": README_EPOCH_S["ml1m_d15_b10000"],
                         "vs_baseline": ra["value"] / PUBLISHED_RATINGS_PER_S["ml1m_d15_b10000"],
                         "e2e": ra.get("e2e"), "note": "launch/L2-bound: 5.2 MB/step, HBM fraction not meaningful"}
+        try:
+            line["also_fm"] = run_fm_workload(torch)
+        except Exception as exc:  # the headline line must not be lost to the secondary workload
+            line["also_fm"] = {"workload": "fm_ktm_d20_b10000", "error": repr(exc)}
     emit(line)
+
+
+def run_fm_workload(torch, epochs=12, warm_epochs=2):
+    """BASELINE configs[2]: fm.py's 2nd-order FM, dim 20, on synthetic one-hot user / item / skill features of the
+    ASSISTments shape (346,860 events, 4,217 + 26,688 + 123 features), mini-batches of 10,000 CSR rows in
+    file order, each batch's step one replayed graph.  Events / s over whole epochs, CUDA events."""
+    import pandas as pd
+    from tf_recomm_b200 import ktm
+    from tf_recomm_b200._lib import LOSS_SIGMOID_CE
+    from tf_recomm_b200.fm_engine import FmEngine
+    users, items, outcomes, q = ktm.make_ktm_events()
+    df = pd.DataFrame(dict(user=users, item=items, outcome=outcomes, wins=0, fails=0))
+    U, I = int(users.max()) + 1, q.shape[0]
+    X = ktm.df_to_sparse(df, ["users", "items", "skills"], U, I, q)
+    B = 10000
+    eng = FmEngine(X.shape[1], 20, 1e-2, 3e-2, flags=LOSS_SIGMOID_CE)
+    chunks = np.array_split(np.arange(X.shape[0]), int(np.ceil(X.shape[0] / B)))
+    batches = [eng.upload_csr(X[c], outcomes[c]) for c in chunks]
+    for _ in range(warm_epochs):
+        eng.run_epoch(batches)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(epochs):
+        eng.run_epoch(batches)
+    e1.record()
+    torch.cuda.synchronize()
+    secs = e0.elapsed_time(e1) / 1e3
+    n_steps = epochs * len(batches)
+    return {"workload": "fm_ktm_d20_b10000", "baseline_config": "configs[2]", "events": int(X.shape[0]),
+            "features": int(X.shape[1]), "nnz_per_row": float(X.nnz / X.shape[0]), "dim": 20, "batch": B,
+            "value": X.shape[0] * epochs / secs, "unit": "events/s", "ms_per_step": secs / n_steps * 1e3,
+            "epoch_s": secs / epochs, "steps": n_steps,
+            "model": "sigmoid cross-entropy + L2 + TF-Adam on (w0, W, V); libFM's MCMC (fm.py:104-110) is out of scope",
+            "note": "launch/L2-bound: 15.6 MB of tables"}
 
 
 if __name__ == "__main__":

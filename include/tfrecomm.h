@@ -43,7 +43,10 @@ enum {
   TFR_ABS_ITEM = 1,        /* ops.py:44     tf.abs(feat_items) in the dot                 */
   TFR_LOSS_SIGMOID_CE = 2, /* ops.py:125-126 summed sigmoid cross-entropy on the logits    */
   TFR_REG_BIAS = 4,        /* ops.py:85-89  L2 on the gathered biases as well              */
-  TFR_OPT_SGD = 8          /* ops.py:145    GradientDescentOptimizer (scatter_sub, no Adam) */
+  TFR_OPT_SGD = 8,         /* ops.py:145    GradientDescentOptimizer (scatter_sub, no Adam) */
+  /* host-side only (never stored in tfr_opt_scalars): the workspace already holds this batch's sorted
+   * (feature id, position) pairs -- a fixed CSR batch that is stepped every epoch is sorted once */
+  TFR_FM_PRESORTED = 256
 };
 /* var_list bits (ops.py:118,147-149; adaptive_test.py:28 trains the user side only) */
 enum { TFR_VAR_MU = 1, TFR_VAR_UB = 2, TFR_VAR_UF = 4, TFR_VAR_IB = 8, TFR_VAR_IF = 16, TFR_VAR_ALL = 31 };

@@ -14,6 +14,7 @@ README_FLAGS = 0
 FORK_FLAGS = ABS_ITEM | LOSS_SIGMOID_CE | REG_BIAS | OPT_SGD
 VAR_MU, VAR_UB, VAR_UF, VAR_IB, VAR_IF, VAR_ALL = 1, 2, 4, 8, 16, 31
 MAX_PARTIALS = 1024
+FM_PRESORTED = 256   # host-side flag of tfr_fm_train_step
 
 vp = C.c_void_p
 i64 = C.c_int64

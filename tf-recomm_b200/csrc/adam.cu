@@ -88,6 +88,10 @@ struct StreamArgs {
   int n_tabs;
   uint32_t total_units;
   FinishArgs fin;
+  // small tables (a few trips in all): the grid is PARTITIONED over the tables -- CTAs [cta_begin[i], cta_begin[i+1])
+  // stream table i -- instead of every CTA walking table after table, which costs one round of latencies per table
+  int partition;
+  uint32_t cta_begin[5];
   int ld_hint, st_hint;
   int copy_only;  // experiment (TFR_STREAM_COPY_ONLY=1): same loads and stores, no arithmetic -- the memory ceiling
 };
@@ -145,12 +149,23 @@ __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_
   TlScope tl_scope(opt, tl_slot);
   const AdamK k = load_k(opt);
   const uint32_t stamp = (uint32_t)opt->global_step;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  int tb0 = 0, tb1 = a.n_tabs;
+  if (a.partition) {
+    int mine = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+      if (i < a.n_tabs && blockIdx.x >= a.cta_begin[i]) mine = i;
+    tb0 = mine;
+    tb1 = mine + 1;
+    gtid = (blockIdx.x - a.cta_begin[mine]) * blockDim.x + threadIdx.x;
+    stride = (a.cta_begin[mine + 1] - a.cta_begin[mine]) * blockDim.x;
+  }
   // Table after table (no barrier in between: a thread that runs out of units of one table moves on to the next), so
   // that everything about the table -- pointers, row width, slot map -- is loop-invariant.
 #pragma unroll 1
-  for (int tb = 0; tb < a.n_tabs; ++tb) {
+  for (int tb = tb0; tb < tb1; ++tb) {
     const StreamTab& t = a.t[tb];
     if ((t.width & 3u) == 0u) {
       // rows of whole 16-byte units: a unit lies in one row, so one slot-map lookup decides between TF's two cases --
@@ -462,6 +477,30 @@ static int launch_stream_chunks(const StreamTab* chunks, int n_chunks, const tfr
   int64_t grid = ((int64_t)units + cfg_threads * cfg_unroll - 1) / (cfg_threads * cfg_unroll);
   const int64_t cap = (int64_t)sm_count() * cfg_ctas;
   if (cfg_ctas > 0 && grid > cap) grid = cap;
+  // small tables: one slice of the grid per table (work counted in thread-trips: a vector table does 4 floats per
+  // thread and trip, a scalar-path table one)
+  uint64_t total_floats = 0;
+  for (int i = 0; i < n_chunks; ++i) total_floats += chunks[i].n;
+  if (n_chunks > 1 && total_floats * 12 < ((uint64_t)32 << 20)) {
+    uint64_t work[4], total_work = 0;
+    for (int i = 0; i < n_chunks; ++i) {
+      work[i] = (chunks[i].width % 4 == 0) ? ((uint64_t)chunks[i].n + 3) / 4 : chunks[i].n;
+      total_work += work[i];
+    }
+    int64_t want = (int64_t)((total_work + cfg_threads - 1) / cfg_threads);
+    if (want > cap && cfg_ctas > 0) want = cap;
+    if (want < n_chunks) want = n_chunks;
+    uint32_t at = 0;
+    for (int i = 0; i < n_chunks; ++i) {
+      a.cta_begin[i] = at;
+      uint64_t share = (work[i] * (uint64_t)want + total_work - 1) / total_work;
+      if (share < 1) share = 1;
+      at += (uint32_t)share;
+    }
+    a.cta_begin[n_chunks] = at;
+    a.partition = 1;
+    grid = at;
+  }
   if (cfg_unroll >= 4) {
     TFR_PREP(adam_stream_multi_kernel<4>);
     adam_stream_multi_kernel<4><<<(unsigned)grid, cfg_threads, 0, st>>>(a, opt, tl_slot);

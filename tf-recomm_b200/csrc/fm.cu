@@ -155,7 +155,8 @@ extern "C" int tfr_fm_train_step(const tfr_fm_tables* t, tfr_opt_scalars* opt, i
   if (grid > TFR_MAX_PARTIALS) grid = TFR_MAX_PARTIALS;
   fm_err_kernel<<<(unsigned)grid, 256, 0, st>>>(opt, yhat, y, indptr, n_rows, err, rowof, ws.partials, ws.se_partials);
   TFR_LAUNCH_CHECK();
-  if ((rc = tfr_dedup_sort_pairs(indices, (int64_t)t->n_feat + 1, ws.su_ids, ws.su_pos, nullptr, 1, nullptr, nullptr,
+  if (!(flags & TFR_FM_PRESORTED) &&
+      (rc = tfr_dedup_sort_pairs(indices, (int64_t)t->n_feat + 1, ws.su_ids, ws.su_pos, nullptr, 1, nullptr, nullptr,
                                  nnz, ws.sort_ws, ws.sort_ws_bytes, stream)))
     return rc;
   if ((rc = tfr_fm_segment_grads(t->V, t->W, t->slot, t->n_feat, t->dim, opt, sums, err, data, rowof, nnz, &ws, stream)))

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import OPT_SGD, FmTables, OptScalars, TfrError, check
+from ._lib import FM_PRESORTED, OPT_SGD, FmTables, OptScalars, StepWs, TfrError, check
 
 FM_TABLE_NAMES = ("w0", "W", "V")
 
@@ -116,13 +116,22 @@ class FmEngine:
         return yhat
 
     # ---- one train step on a CSR batch; returns yhat of the PRE-update tables ------------------------------------
-    def _enqueue_step(self, batch, s):
+    def _enqueue_step(self, batch, s, presorted=False):
+        flags = self.flags | (FM_PRESORTED if presorted else 0)
         check(self.L.tfr_fm_train_step(C.byref(self.tables_struct), self.opt.data_ptr(), batch["n_rows"],
                                        batch["indptr"].data_ptr(), batch["indices"].data_ptr(),
                                        batch["data"].data_ptr(), s["rowof"].data_ptr(), batch["nnz"],
                                        batch["y"].data_ptr(), s["yhat"].data_ptr(), s["sums"].data_ptr(),
-                                       s["err"].data_ptr(), self.flags, s["ws"].data_ptr(), s["ws"].numel(),
+                                       s["err"].data_ptr(), flags, s["ws"].data_ptr(), s["ws"].numel(),
                                        self._stream()))
+
+    def _sort_once(self, batch, s):
+        """The batch's (feature id, position) pairs, sorted into its own scratch: a fixed CSR batch is sorted once,
+        every later step on it (tfr_fm_train_step with TFR_FM_PRESORTED) starts at the forward."""
+        ws = StepWs()
+        check(self.L.tfr_svd_step_carve(s["ws"].data_ptr(), s["ws"].numel(), batch["nnz"], self.d, C.byref(ws)))
+        check(self.L.tfr_dedup_sort_pairs(batch["indices"].data_ptr(), self.F + 1, ws.su_ids, ws.su_pos, None, 1, None,
+                                          None, batch["nnz"], ws.sort_ws, ws.sort_ws_bytes, self._stream()))
 
     def train_step(self, batch, y=None):
         if not isinstance(batch, dict):
@@ -147,12 +156,13 @@ class FmEngine:
                 if g is None:
                     proto = self._bufs(b["n_rows"], b["nnz"])
                     sc = b["_scratch"] = {n: torch.empty_like(v) for n, v in proto.items()}
+                    self._sort_once(b, sc)
                     cap = torch.cuda.Stream(device=self.device)
                     cap.wait_stream(torch.cuda.current_stream(self.device))
                     with torch.cuda.stream(cap):
                         check(self.L.tfr_graph_begin_capture(cap.cuda_stream))
                         try:
-                            self._enqueue_step(b, sc)
+                            self._enqueue_step(b, sc, presorted=True)
                         finally:
                             exe = C.c_void_p()
                             rc = self.L.tfr_graph_end_capture(cap.cuda_stream, C.byref(exe))
