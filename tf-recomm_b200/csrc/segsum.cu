@@ -475,7 +475,7 @@ constexpr int FIX_SHORT = 32;      // partial rows one warp sums on its own
 constexpr int FIX_LONG_CAP = 32;   // long chains a CTA can park (more: the warp sums them itself, slowly)
 
 template <int VEC>
-__global__ void __launch_bounds__(FIX_THREADS) segsum_fixup_kernel(SegSide su, SegSide si, const tfr_opt_scalars* __restrict__ opt,
+__global__ void __launch_bounds__(FIX_THREADS, 3) segsum_fixup_kernel(SegSide su, SegSide si, const tfr_opt_scalars* __restrict__ opt,
                                                                    uint32_t* counters, int64_t B, int dim, int n_tiles,
                                                                    int tile, int cw) {
   TlScope tl_scope(opt, TFR_TL_FIXUP, true);
@@ -524,17 +524,17 @@ __global__ void __launch_bounds__(FIX_THREADS) segsum_fixup_kernel(SegSide su, S
     for (int o = 16; o > 0; o >>= 1) part = add_rn(part, __shfl_xor_sync(0xffffffffu, part, o));
     return add_rn(s.tail_b[t0], part);
   };
-  // one warp: tail[t0] + cont[t0+1] + ... + cont[t1], in that order, eight rows in flight
+  // one warp: tail[t0] + cont[t0+1] + ... + cont[t1], in that order, four rows in flight
   auto warp_chain = [&](int t0, int t1, int64_t head) {
     for (int unit = lane; unit < n_units; unit += 32) {
       Acc<VEC> acc = load_units<VEC>(s.tail + (size_t)t0 * dim, unit);
-      for (int tt = t0 + 1; tt <= t1; tt += 8) {
-        Acc<VEC> x[8];
+      for (int tt = t0 + 1; tt <= t1; tt += 4) {
+        Acc<VEC> x[4];
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < 4; ++r)
           if (tt + r <= t1) x[r] = load_units<VEC>(s.cont + (size_t)(tt + r) * dim, unit);
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < 4; ++r)
           if (tt + r <= t1) {
 #pragma unroll
             for (int q = 0; q < VEC; ++q) acc.v[q] = add_rn(acc.v[q], x[r].v[q]);
@@ -719,7 +719,9 @@ static int launch_segsum(const SegSide& su, const SegSide& si, int n_sides, cons
   const size_t fix_smem = ((size_t)G * dim + G) * sizeof(float);
   // a warp per list entry: at most one entry per tile, so n_tiles / (warps per CTA) CTAs cover any list in one trip
   const int fix_warps = FIX_THREADS / 32;
-  dim3 fix_grid((unsigned)min((n_tiles + fix_warps - 1) / fix_warps, 4 * sm_count()), (unsigned)n_sides);
+  // (ncu: at 126 registers only two CTAs fit an SM and the grid ran in 3.5 waves; 64 registers spill and are slower;
+  // bounded to 85 registers = three CTAs per SM, the grid capped at one resident wave for both sides)
+  dim3 fix_grid((unsigned)min((n_tiles + fix_warps - 1) / fix_warps, 3 * sm_count() / n_sides), (unsigned)n_sides);
   dim3 grid((unsigned)segsum_grid_x(dim, B), (unsigned)n_sides);
   const FwdArgs none{};
   const size_t smem = seg_smem_bytes(dim, g.lanes, units, g.vec);
