@@ -73,3 +73,40 @@ def test_checkpoint_restore_continues_bit_identically(tmp_path):
     ta, tb = eng.get_tables(), other.get_tables()
     for n in ta:
         assert np.array_equal(ta[n], tb[n]), n
+
+
+def test_driver_fork_variant_reports_acc_auc_nll():
+    """The code as written (ops.py:44,85-89,125,145: |q| in the dot, sigmoid cross-entropy, bias L2, SGD) through the
+    reference's DISCRETE branch: accuracy / AUC / mean NLL per epoch (svd_train_val.py:94-98,138-143,156)."""
+    text = _run(["--synthetic", "ml1m", "--ratings", "40000", "--epochs", "3", "--batch", "500", "--dim", "20",
+                 "--variant", "fork", "--lr", "0.005", "--reg", "0.01", "--checkpoint", os.devnull])
+    rows = re.findall(r"^\s*(\d+) TRAIN\(size=\d+/\d+, macc=([0-9.]+), mauc=([0-9.]+), mnll=([0-9.]+)\) "
+                      r"TEST\(size=\d+, macc=([0-9.]+), auc=([0-9.]+), mnll=([0-9.]+)\)", text, flags=re.M)
+    assert len(rows) >= 3, text[-400:]
+    first, last = rows[0], rows[-1]
+    assert all(0.0 <= float(x) <= 1.0 for r in rows for x in (r[1], r[2], r[4], r[5]))
+    assert float(last[6]) < float(first[6])     # validation NLL fell
+    assert float(last[5]) > 0.5                 # validation AUC above chance
+
+
+def test_driver_reads_the_reference_csv_layout(tmp_path, monkeypatch):
+    """data/<name>/{train,val,test}.csv + config.yml (dataio.py:8-16,38-54): header-less user,item,outcome,wins,fails."""
+    import yaml
+    rng = np.random.default_rng(0)
+    folder = tmp_path / "data" / "tiny"
+    folder.mkdir(parents=True)
+    U, I = 40, 30
+    for name, n in (("train", 3000), ("val", 400), ("test", 400)):
+        u, i = rng.integers(0, U, n), rng.integers(0, I, n)
+        r = np.clip(np.rint(3.5 + 0.8 * np.sin(u) + 0.6 * np.cos(i) + rng.normal(0, 0.5, n)), 1, 5)
+        with open(folder / (name + ".csv"), "w") as f:
+            for k in range(n):
+                f.write("%d,%d,%d,0,0\n" % (u[k], i[k], r[k]))
+    with open(folder / "config.yml", "w") as f:
+        yaml.safe_dump(dict(USER_NUM=U, ITEM_NUM=I, NB_CLASSES=5, BATCH_SIZE=100), f)
+    monkeypatch.chdir(tmp_path)
+    rows = _errors(_run(["--dataset", "tiny", "--epochs", "5", "--batch", "100", "--dim", "8", "--lr", "0.01",
+                         "--checkpoint", str(tmp_path / "fm.ckpt")]))
+    assert len(rows) >= 5 and rows[-1][2] < rows[0][2]
+    z = np.load(str(tmp_path / "fm.ckpt"))
+    assert z["user_feat"].shape == (U, 8) and z["item_feat"].shape == (I, 8)
