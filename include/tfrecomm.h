@@ -321,6 +321,14 @@ int tfr_allpairs(const float* user_feat, const float* item_feat, const float* us
                  float* scores, float* best_score, int32_t* best_item, void* workspace, int64_t workspace_bytes,
                  void* stream);
 
+/* ---- host side of the feed_dict boundary: the columns a reference iterator yields (dataio.py:114-117: float64 views
+ * of one [B, ncols] matrix, ids included) packed into a pinned staging buffer in the device's types -- int32 ids
+ * (value cast, like TF feeding an int32 placeholder, A.7) followed by float32 rates: [users B | items B | rates B].
+ * HOST pointers; dtype codes: 0 = float64, 1 = float32, 2 = int32, 3 = int64; strides in BYTES.  No device work. */
+int tfr_host_pack_feed(const void* users_host, int32_t users_dtype, int64_t users_stride, const void* items_host,
+                       int32_t items_dtype, int64_t items_stride, const void* rates_host, int32_t rates_dtype,
+                       int64_t rates_stride, int64_t n, void* staging_host /* 12 * n bytes */);
+
 /* ---- CUDA-graph helpers (thin wrappers so that a ctypes host needs no CUDA bindings) ------------ */
 int tfr_graph_begin_capture(void* stream);
 int tfr_graph_end_capture(void* stream, void** graph_exec_out);

@@ -16,7 +16,7 @@ OBJ = OBJ + os.environ.get("TFR_OBJ_SUFFIX", "")
 SOURCES = ["svd_forward.cu", "dedup_sort.cu", "segsum.cu", "adam.cu", "fm.cu", "shard.cu", "allpairs.cu", "capi.cu"]
 NVCC = os.environ.get("TFR_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-         "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC"] + os.environ.get("TFR_EXTRA_NVCC_FLAGS", "").split()
+         "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-fopenmp"] + os.environ.get("TFR_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _deps_mtime():
@@ -44,8 +44,9 @@ def build(force=False, verbose=False):
         list(ex.map(cc, todo))
     objs = [os.path.join(OBJ, s[:-3] + ".o") for s in SOURCES]
     if todo or not os.path.exists(SO):
+        # -fopenmp: the host-side feed packing (tfr_host_pack_feed) splits a batch over a few threads
         subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++",
-                               "-o", SO] + objs)
+                               "-Xcompiler", "-fopenmp", "-o", SO] + objs)
     return SO
 
 

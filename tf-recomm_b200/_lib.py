@@ -114,6 +114,7 @@ _PROTOS = {
     "tfr_fm_train_step": (C.c_int, [C.POINTER(FmTables), vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, vp, i64, vp]),
     "tfr_allpairs_workspace_bytes": (i64, [i64, i64, i32, i32]),
     "tfr_allpairs": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, i64, i64, i32, vp, vp, vp, vp, i64, vp]),
+    "tfr_host_pack_feed": (C.c_int, [vp, i32, i64, vp, i32, i64, vp, i32, i64, i64, vp]),
     "tfr_graph_begin_capture": (C.c_int, [vp]),
     "tfr_graph_end_capture": (C.c_int, [vp, C.POINTER(vp)]),
     "tfr_graph_launch": (C.c_int, [vp, vp]),

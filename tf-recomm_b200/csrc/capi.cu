@@ -262,6 +262,49 @@ extern "C" int tfr_svd_prefetch_batch(const tfr_svd_tables* t, tfr_opt_scalars* 
                                  stream);
 }
 
+// ---- host side of the feed boundary ----------------------------------------------------------------------------
+namespace {
+template <typename Out, typename In>
+void pack_col(const char* src, int64_t stride, int64_t n, Out* dst) {
+  // a 65536-row batch is ~1.5 MB of float64 in, 0.75 MB out: split over a few host threads (memory-bound)
+  const int nt = n >= 16384 ? 4 : 1;
+#pragma omp parallel for num_threads(nt) schedule(static)
+  for (int64_t c = 0; c < nt; ++c) {
+    const int64_t k0 = n * c / nt, k1 = n * (c + 1) / nt;
+    if (stride == (int64_t)sizeof(In)) {
+      const In* p = reinterpret_cast<const In*>(src);
+      for (int64_t k = k0; k < k1; ++k) dst[k] = (Out)p[k];  // contiguous: vectorised by the host compiler
+    } else {
+      for (int64_t k = k0; k < k1; ++k) dst[k] = (Out) * reinterpret_cast<const In*>(src + k * stride);
+    }
+  }
+}
+template <typename Out>
+int pack_any(const void* src, int dtype, int64_t stride, int64_t n, Out* dst) {
+  const char* p = static_cast<const char*>(src);
+  switch (dtype) {
+    case 0: pack_col<Out, double>(p, stride, n, dst); return 0;
+    case 1: pack_col<Out, float>(p, stride, n, dst); return 0;
+    case 2: pack_col<Out, int32_t>(p, stride, n, dst); return 0;
+    case 3: pack_col<Out, int64_t>(p, stride, n, dst); return 0;
+  }
+  return -1;
+}
+}  // namespace
+
+extern "C" int tfr_host_pack_feed(const void* users_host, int32_t users_dtype, int64_t users_stride,
+                                  const void* items_host, int32_t items_dtype, int64_t items_stride,
+                                  const void* rates_host, int32_t rates_dtype, int64_t rates_stride, int64_t n,
+                                  void* staging_host) {
+  TFR_CHECK_ARG(n >= 0 && staging_host && (n == 0 || (users_host && items_host && rates_host)));
+  int32_t* ids = static_cast<int32_t*>(staging_host);
+  float* rates = reinterpret_cast<float*>(ids + 2 * n);
+  TFR_CHECK_ARG(pack_any<int32_t>(users_host, users_dtype, users_stride, n, ids) == 0);
+  TFR_CHECK_ARG(pack_any<int32_t>(items_host, items_dtype, items_stride, n, ids + n) == 0);
+  TFR_CHECK_ARG(pack_any<float>(rates_host, rates_dtype, rates_stride, n, rates) == 0);
+  return TFR_OK;
+}
+
 // ---- CUDA graphs ------------------------------------------------------------------------------------------
 extern "C" int tfr_graph_begin_capture(void* stream) {
   TFR_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeRelaxed));

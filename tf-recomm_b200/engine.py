@@ -199,53 +199,54 @@ class SvdEngine:
         return logits, infer
 
     # ---- host-fed step (the feed_dict path): pinned staging, H2D, step, D2H of the fetched predictions -------
+    _FEED_DTYPES = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.int32): 2, np.dtype(np.int64): 3}
+
+    def _feed_col(self, a):
+        """(host pointer, dtype code, byte stride) of a 1-D column for tfr_host_pack_feed; anything exotic is first
+        converted to float64 (what the reference's iterators yield, dataio.py:103)."""
+        a = np.asarray(a)
+        if a.ndim != 1 or a.dtype not in self._FEED_DTYPES:
+            a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+        return a, a.ctypes.data, self._FEED_DTYPES[a.dtype], (a.strides[0] if a.size else a.itemsize)
+
     def train_step_host(self, users, items, rates, fetch=True):
         B = len(users)
         stg = self._stage.get(B)
         if stg is None:
-            stg = dict(
-                h_ids=torch.empty(2 * B, dtype=torch.int32).pin_memory(),
-                h_rates=torch.empty(B, dtype=torch.float32).pin_memory(),
-                d_ids=torch.empty(2 * B, dtype=torch.int32, device=self.device),
-                d_rates=torch.empty(B, dtype=torch.float32, device=self.device),
-                d_out=torch.empty(2 * B, dtype=torch.float32, device=self.device),
-                h_out=torch.empty(2 * B, dtype=torch.float32).pin_memory())
+            # one pinned staging buffer [users int32 | items int32 | rates float32] -> ONE H2D copy per step
+            stg = dict(h_feed=torch.empty(3 * B, dtype=torch.int32).pin_memory(),
+                       d_feed=torch.empty(3 * B, dtype=torch.int32, device=self.device),
+                       d_out=torch.empty(2 * B, dtype=torch.float32, device=self.device),
+                       h_out=torch.empty(2 * B, dtype=torch.float32).pin_memory())
             self._stage[B] = stg
-        hi = stg["h_ids"].numpy()
-        hi[:B] = users  # value cast float64 -> int32, like TF feeding an int32 placeholder (A.7)
-        hi[B:] = items
-        stg["h_rates"].numpy()[:] = rates
-        if getattr(self, "host_step_graph", True):
-            # H2D of the batch, the step and the D2H of the fetched predictions as ONE captured graph (the staging
-            # buffers are persistent, so their addresses can be baked in): one launch + one sync per sess.run
-            g = self._graphs.get((B, "host"))
-            if g is None:
-                self.workspace(B)
+        ku, pu, du, su = self._feed_col(users)
+        ki, pi, di, si = self._feed_col(items)
+        kr, pr, dr, sr = self._feed_col(rates)
+        # value cast float64 -> int32, like TF feeding an int32 placeholder (A.7), straight into the pinned buffer
+        check(self.L.tfr_host_pack_feed(pu, du, su, pi, di, si, pr, dr, sr, B, stg["h_feed"].data_ptr()))
+        d_ids = stg["d_feed"][:2 * B]
+        d_rates = stg["d_feed"][2 * B:].view(torch.float32)
 
-                def body():
-                    stg["d_ids"].copy_(stg["h_ids"], non_blocking=True)
-                    stg["d_rates"].copy_(stg["h_rates"], non_blocking=True)
-                    self.train_step(stg["d_ids"][:B], stg["d_ids"][B:], stg["d_rates"], logits=stg["d_out"][:B],
-                                    infer=stg["d_out"][B:])
-                    stg["h_out"].copy_(stg["d_out"], non_blocking=True)
-                g = self._graphs[(B, "host")] = self._capture(body)
-            with torch.cuda.device(self.device):
+        def body():
+            stg["d_feed"].copy_(stg["h_feed"], non_blocking=True)
+            self.train_step(d_ids[:B], d_ids[B:], d_rates, logits=stg["d_out"][:B], infer=stg["d_out"][B:])
+            stg["h_out"].copy_(stg["d_out"], non_blocking=True)
+        with torch.cuda.device(self.device):
+            if getattr(self, "host_step_graph", True):
+                # H2D of the batch, the step and the D2H of the fetched predictions as ONE captured graph (the staging
+                # buffers are persistent, so their addresses can be baked in): one launch + one sync per sess.run
+                g = self._graphs.get((B, "host"))
+                if g is None:
+                    self.workspace(B)
+                    g = self._graphs[(B, "host")] = self._capture(body)
                 check(self.L.tfr_graph_launch(g, self._stream()))
-            if not fetch:
-                return None
-            torch.cuda.current_stream(self.device).synchronize()
-            out = stg["h_out"].numpy()
-            return out[:B].copy(), out[B:].copy()
-        stg["d_ids"].copy_(stg["h_ids"], non_blocking=True)
-        stg["d_rates"].copy_(stg["h_rates"], non_blocking=True)
-        self.train_step(stg["d_ids"][:B], stg["d_ids"][B:], stg["d_rates"], logits=stg["d_out"][:B],
-                        infer=stg["d_out"][B:])
+            else:
+                body()
         if not fetch:
             return None
-        stg["h_out"].copy_(stg["d_out"], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        out = stg["h_out"].numpy()
-        return out[:B].copy(), out[B:].copy()
+        out = stg["h_out"].numpy().copy()   # one copy out of the pinned buffer; the two results are views of it
+        return out[:B], out[B:]
 
     h2d_bytes = staticmethod(lambda B: 12 * B)
     d2h_bytes = staticmethod(lambda B: 8 * B)
