@@ -329,6 +329,13 @@ int tfr_host_pack_feed(const void* users_host, int32_t users_dtype, int64_t user
                        int32_t items_dtype, int64_t items_stride, const void* rates_host, int32_t rates_dtype,
                        int64_t rates_stride, int64_t n, void* staging_host /* 12 * n bytes */);
 
+/* ---- ranking consumer: replaces forward.py:47-61 get_ranking (score every item for a user, sort, keep the first 50) ---
+ * The k best entries of every row of scores [n_rows, n_cols] (row_stride floats between rows, 0 = n_cols), in rank
+ * order: out_val / out_idx [n_rows, k].  Ties go to the lowest index, NaN is never ranked, missing ranks (k > number of
+ * rankable entries) are (-inf, -1).  Scores come from tfr_svd_forward / tfr_fm_forward / tfr_allpairs. */
+int tfr_topk_rows(const float* scores, int64_t n_rows, int64_t n_cols, int64_t row_stride, int32_t k, float* out_val,
+                  int32_t* out_idx, void* stream);
+
 /* ---- CUDA-graph helpers (thin wrappers so that a ctypes host needs no CUDA bindings) ------------ */
 int tfr_graph_begin_capture(void* stream);
 int tfr_graph_end_capture(void* stream, void** graph_exec_out);

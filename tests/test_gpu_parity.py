@@ -571,3 +571,37 @@ def test_allpairs_matches_oracle(U, I, d, tc):
     # and without materialising the matrix
     out2 = eng.allpairs(want_scores=False, want_best=True, use_tensor_cores=tc)
     assert np.array_equal(out2["best_item"].cpu().numpy(), bi)
+
+
+@pytest.mark.parametrize("U,I,d,k", [(40, 1000, 20, 50), (5, 37, 15, 50), (3, 5000, 128, 7)])
+def test_get_ranking_matches_sorted_oracle_scores(U, I, d, k):
+    """forward.py:47-61: every item scored for a user, sorted by score, first k kept (ties: lowest item id)."""
+    tabs = init.init_tables(U, I, d, seed=11)
+    tabs["item_bias"][::7] = tabs["item_bias"][0]            # ties between whole groups of items
+    tabs["item_feat"][::7] = tabs["item_feat"][0]
+    eng = SvdEngine(U, I, d, 1e-3, 0.05, tables=tabs)
+    orc = oracle.SvdOracle(tabs["mu"], tabs["user_bias"], tabs["item_bias"], tabs["user_feat"], tabs["item_feat"], 1e-3, 0.05)
+    users = np.array([0, U - 1, U // 2])
+    idx, vals = eng.get_ranking(users, k=k)
+    idx, vals = idx.cpu().numpy(), vals.cpu().numpy()
+    kk = min(k, I)
+    assert idx.shape == (3, kk)
+    for r, u in enumerate(users):
+        logits, _ = eng.forward(np.full(I, u, np.int32), np.arange(I, dtype=np.int32))
+        sc = logits.cpu().numpy()
+        order = np.lexsort((np.arange(I), -sc))[:kk]         # score descending, item id ascending
+        assert np.array_equal(idx[r], order)
+        assert np.array_equal(vals[r], sc[order])
+        ref, _ = orc.forward(np.full(I, u, np.int32), np.arange(I, dtype=np.int32))
+        np.testing.assert_allclose(vals[r], ref[order], rtol=1e-5, atol=1e-6)
+
+
+def test_topk_rows_edge_cases():
+    L = _lib.load()
+    dev = torch.device("cuda")
+    sc = torch.tensor([[1.0, float("nan"), 3.0, 3.0, -1.0], [float("nan")] * 5], device=dev)
+    vals = torch.empty(2, 4, device=dev)
+    idx = torch.empty(2, 4, dtype=torch.int32, device=dev)
+    _lib.check(L.tfr_topk_rows(sc.data_ptr(), 2, 5, 5, 4, vals.data_ptr(), idx.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    assert idx.cpu().tolist() == [[2, 3, 0, 4], [-1, -1, -1, -1]]
+    assert vals[0].cpu().tolist() == [3.0, 3.0, 1.0, -1.0] and torch.isinf(vals[1]).all()

@@ -115,6 +115,7 @@ _PROTOS = {
     "tfr_allpairs_workspace_bytes": (i64, [i64, i64, i32, i32]),
     "tfr_allpairs": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, i64, i64, i32, vp, vp, vp, vp, i64, vp]),
     "tfr_host_pack_feed": (C.c_int, [vp, i32, i64, vp, i32, i64, vp, i32, i64, i64, vp]),
+    "tfr_topk_rows": (C.c_int, [vp, i64, i64, i64, i32, vp, vp, vp]),
     "tfr_graph_begin_capture": (C.c_int, [vp]),
     "tfr_graph_end_capture": (C.c_int, [vp, C.POINTER(vp)]),
     "tfr_graph_launch": (C.c_int, [vp, vp]),

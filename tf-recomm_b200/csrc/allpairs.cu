@@ -321,6 +321,66 @@ __global__ void allpairs_best_reduce_kernel(const float* __restrict__ tile_best,
   if (best_item) best_item[row] = bi;
 }
 
+// ---- ranking consumer: the k best entries of every row of a score matrix ------------------------------------------
+// forward.py:47-61 `get_ranking`: sort one user's scores over all items, keep the first 50.  One CTA per row; k rounds of
+// a block-wide arg-max over the entries that come AFTER the previous pick in the total order (score descending, index
+// ascending) -- no exclusion list, ties go to the lowest index (as in the fused top-1), NaN scores are never picked.
+__global__ void __launch_bounds__(1024) topk_rows_kernel(const float* __restrict__ scores, int64_t n_cols, int64_t row_stride,
+                                                         int k, float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
+  const float* row = scores + (size_t)blockIdx.x * row_stride;
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  __shared__ float s_last_v;
+  __shared__ int s_last_i;
+  float last_v = INFINITY;
+  int last_i = -1;
+  for (int r = 0; r < k; ++r) {
+    float bv = -INFINITY;
+    int bi = -1;
+    for (int64_t c = threadIdx.x; c < n_cols; c += blockDim.x) {
+      const float v = row[c];
+      const bool after = v < last_v || (v == last_v && (int)c > last_i);   // false for NaN
+      if (after && (v > bv || (v == bv && (bi < 0 || (int)c < bi)) || bi < 0)) { bv = v; bi = (int)c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int nw = (blockDim.x + 31) >> 5;
+      bv = threadIdx.x < nw ? s_v[threadIdx.x] : -INFINITY;
+      bi = threadIdx.x < nw ? s_i[threadIdx.x] : -1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+      }
+      if (threadIdx.x == 0) {
+        s_last_v = bv;
+        s_last_i = bi;
+        out_val[(size_t)blockIdx.x * k + r] = bi >= 0 ? bv : -INFINITY;
+        out_idx[(size_t)blockIdx.x * k + r] = bi;   // -1: fewer than k rankable entries
+      }
+    }
+    __syncthreads();
+    last_v = s_last_v;
+    last_i = s_last_i;
+    if (last_i < 0) {  // nothing left: fill the rest
+      for (int rr = r + 1 + threadIdx.x; rr < k; rr += blockDim.x) {
+        out_val[(size_t)blockIdx.x * k + rr] = -INFINITY;
+        out_idx[(size_t)blockIdx.x * k + rr] = -1;
+      }
+      break;
+    }
+    __syncthreads();
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -354,6 +414,17 @@ static int make_map(CUtensorMap* map, const float* table, int64_t rows, int dim,
 }  // namespace tfr
 
 using namespace tfr;
+
+extern "C" int tfr_topk_rows(const float* scores, int64_t n_rows, int64_t n_cols, int64_t row_stride, int32_t k,
+                             float* out_val, int32_t* out_idx, void* stream) {
+  TFR_CHECK_ARG(n_rows >= 0 && n_cols >= 0 && k > 0 && n_cols < ((int64_t)1 << 31) && n_rows < ((int64_t)1 << 31));
+  if (n_rows == 0) return TFR_OK;
+  TFR_CHECK_ARG(scores && out_val && out_idx && (row_stride == 0 || row_stride >= n_cols));
+  topk_rows_kernel<<<(unsigned)n_rows, 1024, 0, (cudaStream_t)stream>>>(scores, n_cols, row_stride ? row_stride : n_cols, k,
+                                                                      out_val, out_idx);
+  TFR_LAUNCH_CHECK();
+  return TFR_OK;
+}
 
 extern "C" int64_t tfr_allpairs_workspace_bytes(int64_t n_users, int64_t n_items, int32_t dim, int32_t use_tensor_cores) {
   if (n_users < 0 || n_items < 0 || dim <= 0) return TFR_ERR_INVALID;

@@ -181,6 +181,25 @@ class SvdEngine:
                                       bi.data_ptr() if want_best else None, ws.data_ptr(), nbytes, self._stream()))
         return dict(scores=scores, best_score=bs, best_item=bi)
 
+    # ---- ranking: forward.py:47-61 get_ranking (every item scored for one user, sorted, first 50 kept) --------------
+    def get_ranking(self, users, k=50):
+        """-> (items [n, k] int32, scores [n, k]) for a user id or a sequence of them: the k best items of each user in
+        rank order (ties: lowest item id), scored exactly (fp32 forward over all items, tfr_svd_forward's logits)."""
+        users = np.atleast_1d(np.asarray(users)).astype(np.int64)
+        n, k = len(users), int(min(k, self.I))
+        dev = self.device
+        uu = torch.from_numpy(np.repeat(users, self.I).astype(np.int32)).to(dev)
+        ii = torch.arange(self.I, dtype=torch.int32, device=dev).repeat(n)
+        scores = torch.empty(n * self.I, dtype=torch.float32, device=dev)
+        vals = torch.empty(n, k, dtype=torch.float32, device=dev)
+        idx = torch.empty(n, k, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(self.L.tfr_svd_forward(C.byref(self.tables_struct), uu.data_ptr(), ii.data_ptr(), n * self.I, self.flags,
+                                         scores.data_ptr(), None, self._stream()))
+            check(self.L.tfr_topk_rows(scores.data_ptr(), n, self.I, self.I, k, vals.data_ptr(), idx.data_ptr(),
+                                       self._stream()))
+        return idx, vals
+
     # ---- one train step on a device-resident batch: sess.run([train_op, logits, infer]), :70-72 -------------
     def train_step(self, users, items, rates, logits=None, infer=None):
         users, items, rates = self._dev_i32(users), self._dev_i32(items), self._dev_f32(rates)
