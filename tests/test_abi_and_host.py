@@ -173,3 +173,36 @@ def test_init_tables_follow_tf_initialisers():
     assert np.all(np.abs(g["user_bias"]) <= np.sqrt(3.0 / 2000) + 1e-7)
     same = init.init_tables(2000, 1000, 16, seed=3, bias_init="truncated_normal")
     assert all(np.array_equal(t[k], same[k]) for k in t)
+
+
+def test_host_pack_feed_casts_like_a_tf_feed():
+    """tfr_host_pack_feed (host-only, no GPU): the columns a reference iterator yields -- float64 VIEWS of one [B, ncols]
+    matrix, ids included (dataio.py:103,116-117) -- land in the staging buffer as int32 ids + float32 rates, by value
+    (TF feeding an int32 placeholder), for every dtype / stride the engine accepts."""
+    from tf_recomm_b200 import dataio
+    L = _lib.load()
+    rng = np.random.default_rng(0)
+    for B in (0, 1, 7, 20000):          # 20000 >= the threshold where the packing is split over host threads
+        users = rng.integers(0, 100000, B).astype(np.int32)
+        items = rng.integers(0, 5000, B).astype(np.int32)
+        rates = rng.integers(1, 6, B).astype(np.float32) + 0.5
+        it = dataio.OneEpochIterator([users, items, rates], batch_size=-1)
+        cols = next(it) if B else [np.zeros(0), np.zeros(0), np.zeros(0)]
+        if B:
+            assert cols[0].dtype == np.float64 and cols[0].strides[0] == 24      # strided float64 views
+        variants = [cols, [users, items, rates], [users.astype(np.int64), items.astype(np.int64), rates.astype(np.float64)],
+                    [users.astype(np.float32), items.astype(np.float64), rates]]
+        codes = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.int32): 2, np.dtype(np.int64): 3}
+        for u, i, r in variants:
+            out = np.full(3 * B + 1, -7, np.int32)
+            args = []
+            for a in (u, i, r):
+                a = np.asarray(a)
+                args += [a.ctypes.data, codes[a.dtype], a.strides[0] if a.size else a.itemsize]
+            assert L.tfr_host_pack_feed(*args, B, out.ctypes.data) == 0
+            assert np.array_equal(out[:B], users) and np.array_equal(out[B:2 * B], items)
+            assert np.array_equal(out[2 * B:3 * B].view(np.float32), rates)
+            assert out[3 * B] == -7                                              # nothing written past 12 * B bytes
+    bad = np.zeros(4)
+    assert L.tfr_host_pack_feed(bad.ctypes.data, 9, 8, bad.ctypes.data, 0, 8, bad.ctypes.data, 0, 8, 4,
+                                np.zeros(12, np.int32).ctypes.data) < 0           # unknown dtype code -> error, no crash
