@@ -17,34 +17,6 @@
 
 namespace tfr {
 
-template <int VEC, int L>
-__device__ __forceinline__ float row_dot(const float* __restrict__ pu, const float* __restrict__ qi, int dim,
-                                         int lane, bool abs_item) {
-  float acc = 0.0f;
-  if (VEC == 4) {
-    const float4* pu4 = reinterpret_cast<const float4*>(pu);
-    const float4* qi4 = reinterpret_cast<const float4*>(qi);
-    const int n4 = dim >> 2;
-    for (int k = lane; k < n4; k += L) {
-      const float4 a = ld_gather_f4(pu4 + k);
-      float4 b = ld_gather_f4(qi4 + k);
-      if (abs_item) { b.x = fabsf(b.x); b.y = fabsf(b.y); b.z = fabsf(b.z); b.w = fabsf(b.w); }
-      acc = add_rn(acc, mul_rn(a.x, b.x));
-      acc = add_rn(acc, mul_rn(a.y, b.y));
-      acc = add_rn(acc, mul_rn(a.z, b.z));
-      acc = add_rn(acc, mul_rn(a.w, b.w));
-    }
-  } else {
-    for (int k = lane; k < dim; k += L) {
-      const float a = ld_gather_f1(pu + k);
-      float b = ld_gather_f1(qi + k);
-      if (abs_item) b = fabsf(b);
-      acc = add_rn(acc, mul_rn(a, b));
-    }
-  }
-  return group_sum<L>(acc);
-}
-
 __device__ __forceinline__ float head(int flags, float x) {
   return (flags & TFR_LOSS_SIGMOID_CE) ? rintf(sigmoid_tf(x)) : x;
 }
