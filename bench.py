@@ -353,7 +353,11 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "baseline_config": w["config"], "users": w["U"], "items": w["I"], "dim": w["d"],
                    "batch": w["B"], "ratings": w["N"], "model": "README: squared error + L2 + Adam (TF IndexedSlices semantics)",
-                   "lr": LR, "reg": REG, "l2_policy": "per-step working set %.0f MB > 126 MB L2: no flush needed"
+                   "lr": LR, "reg": REG,
+                   "scaling_note": "--gpus N >= 2 measures BASELINE configs[4] (100M x 10M row-sharded: 170 GB of state "
+                                   "that no single GPU holds), a different workload from this one: compare the multi-GPU "
+                                   "lines with each other (baseline n_gpus = 2), not with this line",
+                   "l2_policy": "per-step working set %.0f MB > 126 MB L2: no flush needed"
                    % (r["bytes_step"] / 1e6) if r["bytes_step"] > 126e6 else
                    "working set %.1f MB is L2-resident by construction (launch-bound config)" % (r["bytes_step"] / 1e6),
                    "timing": "CUDA events around K replays of the captured step graph (each replay also assembles and "
