@@ -55,6 +55,13 @@ const char* tfr_last_error(void);
 int tfr_abi_version(void);
 /* Number of SMs of the current device (148 on B200), or negative status. */
 int tfr_device_sm_count(void);
+/* Tuning knobs -- the ONLY process-wide state of the library (everything else is caller-owned).  A knob's value is what
+ * tfr_tune_set gave it, else the environment variable TFR_<NAME> at first use, else its default.  Names (csrc/capi.cu):
+ * SMEM_CARVEOUT, SEG_TILE, SEG_MAX_UNITS, PASS_RING (1 = interleaved tables take the TMA-bulk ring pass, 0 = the
+ * LDG/STG pass), RING_STAGES, RING_STAGE_KB, RING_THREADS, RING_L2_HINT, STREAM_THREADS, STREAM_CTAS_PER_SM, ...
+ * Knobs change launch geometry only, never results. */
+int tfr_tune_set(const char* name, int32_t value);
+int tfr_tune_get(const char* name, int32_t* value);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer scalars kept in DEVICE memory so that a captured graph can be replayed every step.
@@ -263,11 +270,6 @@ int tfr_sgd_apply(float* var, int32_t width, const int32_t* sorted_ids, int64_t 
 int tfr_svd_finish_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
                         const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, int32_t n_partials,
                         void* stream);
-
-/* Layout experiment (tools/pass_bench.py): the decay-only pass on an interleaved table T[rows][3][width]
- * (var row | m row | v row): one read and one write stream instead of three and three. */
-int tfr_experiment_interleaved_pass(float* T, int64_t rows, int32_t width, const tfr_opt_scalars* opt, int32_t copy_only,
-                                    void* stream);
 
 /* ---- row-sharded tables: the owner's half of the id -> row exchange ------------------------------
  * For every batch position b: if ids[b] mod n_ranks == rank, copy the local row ids[b] / n_ranks (and its bias)

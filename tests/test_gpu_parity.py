@@ -605,3 +605,37 @@ def test_topk_rows_edge_cases():
     _lib.check(L.tfr_topk_rows(sc.data_ptr(), 2, 5, 5, 4, vals.data_ptr(), idx.data_ptr(), torch.cuda.current_stream().cuda_stream))
     assert idx.cpu().tolist() == [[2, 3, 0, 4], [-1, -1, -1, -1]]
     assert vals[0].cpu().tolist() == [3.0, 3.0, 1.0, -1.0] and torch.isinf(vals[1]).all()
+
+
+@pytest.mark.parametrize("shape", [(301, 157, 128), (5000, 3001, 128), (1234, 777, 20), (40, 33, 64), (3000, 17, 256)])
+@pytest.mark.parametrize("ring_cfg", [dict(RING_STAGES=5, RING_STAGE_KB=24, RING_THREADS=544),
+                                      dict(RING_STAGES=2, RING_STAGE_KB=8, RING_THREADS=96),
+                                      dict(RING_STAGES=7, RING_STAGE_KB=12, RING_THREADS=288, RING_L2_HINT=2)])
+def test_ring_pass_bit_identical(shape, ring_cfg):
+    """The TMA-bulk ring pass (adam_ring.cu) and the LDG/STG pass (adam.cu) are the same function of their inputs:
+    whole train steps (Adam, interleaved tables) with either pass leave bit-identical tables, slots and scalars --
+    partial last stages, rows % 4 != 0 bias tails, more units per thread than prefetch registers included."""
+    U, I, d = shape
+    rng = np.random.default_rng(U)
+    B = 700
+    batches = [make_batch(rng, U, I, B) for _ in range(3)]
+    out = []
+    try:
+        for ring in (0, 1):
+            _lib.tune_set("PASS_RING", ring)
+            for k, v in ring_cfg.items():
+                _lib.tune_set(k, v)
+            eng, _ = both(U, I, d, 1e-3, 0.05)
+            for b in batches:
+                eng.train_step(*b)
+            torch.cuda.synchronize()
+            out.append((eng.get_tables(), eng.opt_scalars()))
+    finally:
+        _lib.tune_set("PASS_RING", 1)
+        for k, v in dict(RING_STAGES=5, RING_STAGE_KB=24, RING_THREADS=544, RING_L2_HINT=0).items():
+            _lib.tune_set(k, v)
+    (ta, sa), (tb, sb) = out
+    for n in ta:
+        assert np.array_equal(ta[n].view(np.int32), tb[n].view(np.int32)), n
+    for f in ("global_step", "beta1_power", "beta2_power", "lr_t", "g_mu", "se_sum"):
+        assert getattr(sa, f) == getattr(sb, f), f

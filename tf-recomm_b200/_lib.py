@@ -81,6 +81,8 @@ _PROTOS = {
     "tfr_last_error": (C.c_char_p, []),
     "tfr_abi_version": (C.c_int, []),
     "tfr_device_sm_count": (C.c_int, []),
+    "tfr_tune_set": (C.c_int, [C.c_char_p, i32]),
+    "tfr_tune_get": (C.c_int, [C.c_char_p, C.POINTER(i32)]),
     "tfr_opt_init": (C.c_int, [vp, f32, f32, f32, f32, f32, i32, i32, vp]),
     "tfr_opt_set_se_ring": (C.c_int, [vp, vp, i64, vp]),
     "tfr_opt_set_timeline": (C.c_int, [vp, vp, vp]),
@@ -107,7 +109,6 @@ _PROTOS = {
     "tfr_adam_slice_multi": (C.c_int, [C.POINTER(SliceUpdate), i32, i32, i64, vp, i32, i32, vp]),
     "tfr_sgd_apply": (C.c_int, [vp, i32, vp, i64, vp, vp]),
     "tfr_svd_finish_step": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, C.POINTER(StepWs), i32, vp]),
-    "tfr_experiment_interleaved_pass": (C.c_int, [vp, i64, i32, vp, i32, vp]),
     "tfr_shard_gather_rows": (C.c_int, [vp, vp, i64, i32, i64, vp, i64, i32, i32, vp, vp, vp, vp]),
     "tfr_fm_forward": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
     "tfr_fm_segment_grads": (C.c_int, [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i64, C.POINTER(StepWs), vp]),
@@ -149,6 +150,17 @@ def check(rc):
     if rc < 0:
         raise TfrError("libtfrecomm: %s (status %d)" % (load().tfr_last_error().decode(), rc))
     return rc
+
+
+def tune_set(name, value):
+    """Process-wide tuning knob (tfr_tune_set): launch geometry only, never results."""
+    check(load().tfr_tune_set(name.encode(), int(value)))
+
+
+def tune_get(name):
+    v = i32()
+    check(load().tfr_tune_get(name.encode(), C.byref(v)))
+    return v.value
 
 
 def exported_symbols():

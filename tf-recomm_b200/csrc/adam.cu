@@ -12,7 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "adam_math.cuh"
 
 namespace tfr {
 
@@ -35,26 +35,6 @@ __device__ __forceinline__ void st_hint_f4(float4* p, const float4& v, int h) {
   else asm volatile("st.global.wt.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-struct AdamK {
-  float b1, b2, lr_t, eps, omb1, omb2;
-};
-__device__ __forceinline__ AdamK load_k(const tfr_opt_scalars* opt) {
-  AdamK k;
-  k.b1 = opt->beta1; k.b2 = opt->beta2; k.lr_t = opt->lr_t; k.eps = opt->eps;
-  k.omb1 = opt->one_minus_beta1; k.omb2 = opt->one_minus_beta2;
-  return k;
-}
-__device__ __forceinline__ void adam_decay(float& var, float& m, float& v, const AdamK& k) {
-  m = mul_rn(m, k.b1);
-  v = mul_rn(v, k.b2);
-  var = sub_rn(var, div_rn(mul_rn(k.lr_t, m), add_rn(sqrt_rn(v), k.eps)));
-}
-__device__ __forceinline__ void adam_grad(float& var, float& m, float& v, float g, const AdamK& k) {
-  m = add_rn(mul_rn(m, k.b1), mul_rn(g, k.omb1));
-  v = add_rn(mul_rn(v, k.b2), mul_rn(mul_rn(g, g), k.omb2));
-  var = sub_rn(var, div_rn(mul_rn(k.lr_t, m), add_rn(sqrt_rn(v), k.eps)));
-}
-
 // ---- the whole-table pass: every row of every table, in address order, ONE launch ----------------------
 // Each parameter is read and written exactly once per step (24 B/param).  The concatenated tables are cut
 // into units of 4 floats; a persistent grid strides over them, UNROLL units per thread and trip (6*UNROLL
@@ -73,16 +53,6 @@ struct StreamTab {
                      // row are interleaved (m = var + width, v = var + 2*width) -- then ONE stream is read and written
   uint32_t unit_end; // exclusive end of this table's units in the concatenated unit space
 };
-// end-of-step work folded into the pass (the last CTA to finish does it): dense Adam on bias_global from the
-// forward's per-CTA partials + the step scalars (what finish_step_kernel does as a launch of its own)
-struct FinishArgs {
-  tfr_opt_scalars* opt;  // writable alias of the kernel's (read-only) scalars: written by ONE warp after every CTA
-                         // has arrived, i.e. after every read of the step's scalars
-  float *mu, *m_mu, *v_mu;
-  const float* partials;
-  const double* se_partials;
-  int n_partials;  // 0 = no end-of-step work in this launch
-};
 struct StreamArgs {
   StreamTab t[4];
   int n_tabs;
@@ -95,53 +65,6 @@ struct StreamArgs {
   int ld_hint, st_hint;
   int copy_only;  // experiment (TFR_STREAM_COPY_ONLY=1): same loads and stores, no arithmetic -- the memory ceiling
 };
-
-// one warp: fold the per-CTA partials in a fixed order, update bias_global (TF: training_ops.cc ApplyAdam, A.5),
-// advance beta powers / lr_t / counters (TF: adam.py::_finish), record the step's float64 squared-error sum
-__device__ __noinline__ void finish_step_scalars(float* mu, float* m_mu, float* v_mu, tfr_opt_scalars* opt,
-                                                    const float* partials, const double* se_partials, int n_partials) {
-  float a = 0.0f;
-  double se = 0.0;
-  const int ln = threadIdx.x & 31;
-  for (int j = ln; j < n_partials; j += 32) { a = add_rn(a, partials[j]); se += se_partials[j]; }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a = add_rn(a, __shfl_xor_sync(0xffffffffu, a, o));
-    se += __shfl_xor_sync(0xffffffffu, se, o);
-  }
-  if (ln == 0) {
-    const float g = a;  // d cost / d bias_global = sum_b e_b  (A.3)
-    opt->g_mu = g;
-    opt->se_sum = se;
-    if (opt->se_ring && opt->se_ring_len > 0) opt->se_ring[opt->global_step % opt->se_ring_len] = se;
-    const bool sgd = opt->flags & TFR_OPT_SGD;
-    if (opt->var_mask & TFR_VAR_MU) {
-      if (sgd) {
-        *mu = sub_rn(*mu, mul_rn(opt->lr, g));
-      } else {  // TF: training_ops.cc ApplyAdam (A.5)
-        float alpha = sqrt_rn(sub_rn(1.0f, opt->beta2_power));
-        alpha = mul_rn(opt->lr, alpha);
-        alpha = div_rn(alpha, sub_rn(1.0f, opt->beta1_power));
-        float mm = *m_mu, vv = *v_mu;
-        mm = add_rn(mm, mul_rn(sub_rn(g, mm), opt->one_minus_beta1));
-        vv = add_rn(vv, mul_rn(sub_rn(mul_rn(g, g), vv), opt->one_minus_beta2));
-        *m_mu = mm;
-        *v_mu = vv;
-        *mu = sub_rn(*mu, div_rn(mul_rn(mm, alpha), add_rn(sqrt_rn(vv), opt->eps)));
-      }
-    }
-    if (!sgd) {  // TF: adam.py::_finish
-      opt->beta1_power = mul_rn(opt->beta1_power, opt->beta1);
-      opt->beta2_power = mul_rn(opt->beta2_power, opt->beta2);
-      // lr_t of the NEXT step (TF: _apply_sparse_shared recomputes it from the advanced powers), so that a step
-      // needs no kernel in front of the forward
-      float tt = sqrt_rn(sub_rn(1.0f, opt->beta2_power));
-      opt->lr_t = div_rn(mul_rn(opt->lr, tt), sub_rn(1.0f, opt->beta1_power));
-    }
-    opt->global_step += 1;
-    opt->batch_cursor += 1;
-  }
-}
 
 template <int UNROLL>
 __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_constant__ StreamArgs a,
@@ -261,46 +184,6 @@ __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_
       finish_step_scalars(a.fin.mu, a.fin.m_mu, a.fin.v_mu, a.fin.opt, a.fin.partials, a.fin.se_partials,
                           a.fin.n_partials);
       if (threadIdx.x == 0) a.fin.opt->ticket = 0;
-    }
-  }
-}
-
-// ---- layout experiment: the same update on an INTERLEAVED table T[rows][3][width] (var row | m row | v row) -----------
-// One read stream and one write stream instead of three and three.  tools/pass_bench.py --interleaved times it.
-template <int UNROLL>
-__global__ void __launch_bounds__(512, 2) adam_interleaved_kernel(float* __restrict__ T, uint32_t rows, uint32_t upr,
-                                                               const tfr_opt_scalars* __restrict__ opt, int copy_only) {
-  const AdamK k = load_k(opt);
-  const uint32_t n_units = rows * upr;  // units of var (= of m, of v)
-  const uint32_t stride = gridDim.x * blockDim.x;
-  float4* base = reinterpret_cast<float4*>(T);
-  for (uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < n_units; q0 += stride * UNROLL) {
-    float4 x[UNROLL], y[UNROLL], z[UNROLL];
-    size_t at[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const uint32_t q = q0 + u * stride;
-      if (q < n_units) {
-        const uint32_t row = q / upr, c = q - row * upr;
-        at[u] = (size_t)row * 3u * upr + c;
-        x[u] = ld_hint_f4(base + at[u], 2);
-        y[u] = ld_hint_f4(base + at[u] + upr, 2);
-        z[u] = ld_hint_f4(base + at[u] + 2u * upr, 2);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const uint32_t q = q0 + u * stride;
-      if (q >= n_units) continue;
-      if (!copy_only) {
-        adam_decay(x[u].x, y[u].x, z[u].x, k);
-        adam_decay(x[u].y, y[u].y, z[u].y, k);
-        adam_decay(x[u].z, y[u].z, z[u].z, k);
-        adam_decay(x[u].w, y[u].w, z[u].w, k);
-      }
-      st_stream_f4(base + at[u], x[u]);
-      st_stream_f4(base + at[u] + upr, y[u]);
-      st_stream_f4(base + at[u] + 2u * upr, z[u]);
     }
   }
 }
@@ -455,25 +338,16 @@ static int launch_stream_chunks(const StreamTab* chunks, int n_chunks, const tfr
   }
   a.n_tabs = n_chunks;
   a.total_units = (uint32_t)units;
-  static int copy_only = -1;
-  if (copy_only < 0) copy_only = getenv("TFR_STREAM_COPY_ONLY") ? atoi(getenv("TFR_STREAM_COPY_ONLY")) : 0;
-  a.copy_only = copy_only;
-  static int ldh = -1, sth = -1;
-  if (ldh < 0) { ldh = getenv("TFR_STREAM_LD") ? atoi(getenv("TFR_STREAM_LD")) : 2; sth = getenv("TFR_STREAM_ST") ? atoi(getenv("TFR_STREAM_ST")) : 0; }
-  a.ld_hint = ldh; a.st_hint = sth;
+  a.copy_only = tune(TUNE_STREAM_COPY_ONLY);
+  a.ld_hint = tune(TUNE_STREAM_LD);
+  a.st_hint = tune(TUNE_STREAM_ST);
   // persistent grid: 2 CTAs x 448 threads x 64 registers per SM, 2 units per thread and trip.  448, not 512: two
   // CTAs of 512 threads take the whole register file, and the id sort of the NEXT batch (8K registers per CTA,
   // forked under this pass) could then only start when the pass drains -- which puts it on the critical path.
   // (3 x 256 also leaves room but measures 7 % slower: TFR_STREAM_* to experiment.)
-  static int cfg_ctas = -1, cfg_unroll = 0, cfg_threads = 512;
-  if (cfg_ctas < 0) {
-    const char* e1 = getenv("TFR_STREAM_CTAS_PER_SM");
-    const char* e2 = getenv("TFR_STREAM_UNROLL");
-    const char* e3 = getenv("TFR_STREAM_THREADS");
-    cfg_ctas = e1 ? atoi(e1) : 2;
-    cfg_unroll = e2 ? atoi(e2) : 2;
-    cfg_threads = e3 ? atoi(e3) : 448;
-  }
+  const int cfg_ctas = tune(TUNE_STREAM_CTAS_PER_SM), cfg_unroll = tune(TUNE_STREAM_UNROLL);
+  int cfg_threads = tune(TUNE_STREAM_THREADS);
+  if (cfg_threads < 32 || cfg_threads > 512) cfg_threads = 448;
   int64_t grid = ((int64_t)units + cfg_threads * cfg_unroll - 1) / (cfg_threads * cfg_unroll);
   const int64_t cap = (int64_t)sm_count() * cfg_ctas;
   if (cfg_ctas > 0 && grid > cap) grid = cap;
@@ -513,6 +387,10 @@ static int launch_stream_chunks(const StreamTab* chunks, int n_chunks, const tfr
 }
 
 namespace tfr {
+// adam_ring.cu: the TMA-bulk ring pass for interleaved feature tables (+ plain bias tables)
+bool ring_pass_eligible(const tfr_adam_table* tabs, int n);
+int ring_pass_launch(const tfr_adam_table* tabs, int n, const tfr_opt_scalars* opt, int tl_slot, cudaStream_t st,
+                     const FinishArgs* fin);
 // fin != null: the pass's last launch also ends the step (see FinishArgs); returns 1 if it did, 0 if no launch
 // was issued (nothing to stream), negative on error.
 int adam_stream_multi_impl(const tfr_adam_table* tables, int32_t n_tables, tfr_opt_scalars* opt, int32_t tl_slot,
@@ -528,6 +406,14 @@ extern "C" int tfr_adam_stream_multi(const tfr_adam_table* tables, int32_t n_tab
 int tfr::adam_stream_multi_impl(const tfr_adam_table* tables, int32_t n_tables, tfr_opt_scalars* opt, int32_t tl_slot,
                                 void* stream, const FinishArgs* fin) {
   TFR_CHECK_ARG(tables && n_tables >= 1 && n_tables <= 4 && opt && tl_slot >= 0 && tl_slot < TFR_TL_SLOTS);
+  for (int i = 0; i < n_tables; ++i) {
+    TFR_CHECK_ARG(tables[i].rows >= 0 && tables[i].width > 0);
+    TFR_CHECK_ARG(tables[i].rows == 0 || (tables[i].var && tables[i].m && tables[i].v && (!tables[i].slot || tables[i].gsum)));
+  }
+  if (ring_pass_eligible(tables, n_tables)) {
+    const int rc = ring_pass_launch(tables, n_tables, opt, tl_slot, (cudaStream_t)stream, fin);
+    return rc < 0 ? rc : 1;
+  }
   // The kernel indexes floats with 32 bits: a table of >= 2^32 floats (the 50M x 128 user shard of configs[4] at
   // G = 2) is cut into row ranges, and launches are split so that one launch covers < 2^32 units.
   const uint64_t kMaxFloats = ((uint64_t)1 << 32) - 8;
@@ -575,16 +461,6 @@ int tfr::adam_stream_multi_impl(const tfr_adam_table* tables, int32_t n_tables, 
     return rc < 0 ? rc : 1;
   }
   return 0;
-}
-
-extern "C" int tfr_experiment_interleaved_pass(float* T, int64_t rows, int32_t width, const tfr_opt_scalars* opt,
-                                               int32_t copy_only, void* stream) {
-  TFR_CHECK_ARG(T && opt && rows > 0 && width > 0 && width % 4 == 0 && rows * (int64_t)(width / 4) < ((int64_t)1 << 32));
-  const int threads = getenv("TFR_STREAM_THREADS") ? atoi(getenv("TFR_STREAM_THREADS")) : 448;
-  adam_interleaved_kernel<2><<<2 * sm_count(), threads, 0, (cudaStream_t)stream>>>(T, (uint32_t)rows, (uint32_t)(width / 4),
-                                                                                opt, copy_only);
-  TFR_LAUNCH_CHECK();
-  return TFR_OK;
 }
 
 extern "C" int tfr_adam_slice_multi(const tfr_slice_update* sides, int32_t n_sides, int32_t width, int64_t n,

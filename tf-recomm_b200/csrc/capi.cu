@@ -4,8 +4,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
-#include <set>
 
 #include "common.cuh"
 
@@ -30,6 +30,31 @@ int sm_count() {
   return n;
 }
 
+namespace {
+struct TuneEntry { const char* name; int dflt; };
+const TuneEntry kTune[TUNE_COUNT] = {
+    {"SMEM_CARVEOUT", 62},   // 141 KB of shared memory: four CTAs of the segment-sum kernel (32 KB each) per SM
+    {"TILES_CARVEOUT", -1}, {"SEG_MAX_UNITS", 0}, {"SEG_TILE", 0}, {"STREAM_COPY_ONLY", 0}, {"STREAM_LD", 2},
+    {"STREAM_ST", 0}, {"STREAM_CTAS_PER_SM", 2}, {"STREAM_UNROLL", 2}, {"STREAM_THREADS", 448}, {"PASS_RING", 1},
+    {"RING_STAGES", 5}, {"RING_STAGE_KB", 24}, {"RING_THREADS", 544}, {"RING_L2_HINT", 0}, {"RING_CTAS_PER_SM", 1},
+};
+std::mutex g_tune_mu;
+int g_tune_val[TUNE_COUNT];
+bool g_tune_known[TUNE_COUNT];
+}  // namespace
+
+int tune(TuneKey k) {
+  std::lock_guard<std::mutex> g(g_tune_mu);
+  if (!g_tune_known[k]) {
+    char env[64];
+    snprintf(env, sizeof(env), "TFR_%s", kTune[k].name);
+    const char* e = getenv(env);
+    g_tune_val[k] = e ? atoi(e) : kTune[k].dflt;
+    g_tune_known[k] = true;
+  }
+  return g_tune_val[k];
+}
+
 int fwd_err_n_partials(int dim, int64_t B);
 int seg_tile(int64_t B, int dim);
 int svd_segment_grads_impl(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
@@ -39,17 +64,14 @@ int adam_pass_and_finish(const tfr_adam_table* tabs, int nt, const tfr_svd_table
 
 void prep_kernel(const void* fn) {
   static std::mutex mu;
-  static std::set<const void*> done;
+  static std::map<const void*, int> applied;  // the carve-out a kernel was last given
+  const int carve = tune(TUNE_SMEM_CARVEOUT);
   std::lock_guard<std::mutex> g(mu);
-  if (done.count(fn)) return;
-  static int carve = -1;
-  if (carve < 0) {
-    const char* e = getenv("TFR_SMEM_CARVEOUT");
-    carve = e ? atoi(e) : 62;  // 141 KB of shared memory: four CTAs of the segment-sum kernel (32 KB each) per SM
-  }
+  auto it = applied.find(fn);
+  if (it != applied.end() && it->second == carve) return;
   if (carve > 0) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   cudaGetLastError();
-  done.insert(fn);
+  applied[fn] = carve;
 }
 
 }  // namespace tfr
@@ -58,6 +80,30 @@ using namespace tfr;
 
 extern "C" const char* tfr_last_error(void) { return g_err; }
 extern "C" int tfr_abi_version(void) { return TFR_ABI_VERSION; }
+
+extern "C" int tfr_tune_set(const char* name, int32_t value) {
+  TFR_CHECK_ARG(name);
+  for (int k = 0; k < TUNE_COUNT; ++k)
+    if (!strcmp(name, kTune[k].name)) {
+      std::lock_guard<std::mutex> g(g_tune_mu);
+      g_tune_val[k] = value;
+      g_tune_known[k] = true;
+      return TFR_OK;
+    }
+  set_error("unknown tuning knob %s", name);
+  return TFR_ERR_INVALID;
+}
+
+extern "C" int tfr_tune_get(const char* name, int32_t* value) {
+  TFR_CHECK_ARG(name && value);
+  for (int k = 0; k < TUNE_COUNT; ++k)
+    if (!strcmp(name, kTune[k].name)) {
+      *value = tune((TuneKey)k);
+      return TFR_OK;
+    }
+  set_error("unknown tuning knob %s", name);
+  return TFR_ERR_INVALID;
+}
 
 extern "C" int tfr_device_sm_count(void) {
   int dev = 0, n = 0;

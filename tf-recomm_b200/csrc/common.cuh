@@ -10,6 +10,23 @@ namespace tfr {
 
 void set_error(const char* fmt, ...);
 int sm_count();
+
+// Tuning knobs: the ONE piece of process-wide state of the library (include/tfrecomm.h: tfr_tune_set / tfr_tune_get).
+// A knob's value is, in this order: what tfr_tune_set gave it, the environment variable TFR_<NAME> read at first use,
+// its default.  Every launch reads its knobs through tune(): nothing is cached at the call sites.
+enum TuneKey {
+  TUNE_SMEM_CARVEOUT,     // preferred shared-memory carve-out (%) given to every kernel of the step (see prep_kernel)
+  TUNE_TILES_CARVEOUT,    // < 0: same as SMEM_CARVEOUT
+  TUNE_SEG_MAX_UNITS,     // segment sums: force 1 / 2 / 4 units per lane (0 = heuristic)
+  TUNE_SEG_TILE,          // segment sums: force tiles of 8 / 16 / 32 entries (0 = heuristic)
+  TUNE_STREAM_COPY_ONLY,  // LDG pass without arithmetic (memory ceiling experiment)
+  TUNE_STREAM_LD, TUNE_STREAM_ST,  // cache hints of the LDG pass (0 = .cs, 1 = default, 2 = .cg, 3 = .lu / .wt)
+  TUNE_STREAM_CTAS_PER_SM, TUNE_STREAM_UNROLL, TUNE_STREAM_THREADS,
+  TUNE_PASS_RING,         // 1: interleaved tables take the TMA-bulk ring pass (adam_ring.cu), 0: the LDG pass
+  TUNE_RING_STAGES, TUNE_RING_STAGE_KB, TUNE_RING_THREADS, TUNE_RING_L2_HINT, TUNE_RING_CTAS_PER_SM,
+  TUNE_COUNT
+};
+int tune(TuneKey k);
 // Gives every kernel of the step the SAME shared-memory carve-out.  An SM cannot host CTAs of two kernels
 // whose carve-outs differ, so without this the persistent streaming pass (no shared memory -> "max L1")
 // keeps the forward / sort / segment-sum kernels (which use shared memory) off every SM until it drains.

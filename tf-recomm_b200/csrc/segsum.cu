@@ -633,12 +633,8 @@ struct SegGeom {
   int vec, lanes, units;
 };
 static SegGeom seg_geom(int dim) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("TFR_SEG_MAX_UNITS");  // experiments: force 1, 2 or 4 units per lane
-    forced = e ? atoi(e) : 0;
-    if (forced != 1 && forced != 2 && forced != 4) forced = 0;
-  }
+  int forced = tune(TUNE_SEG_MAX_UNITS);  // experiments: force 1, 2 or 4 units per lane
+  if (forced != 1 && forced != 2 && forced != 4) forced = 0;
   SegGeom g;
   g.vec = (dim % 4 == 0) ? 4 : 1;
   const int n_units = dim / g.vec;
@@ -657,13 +653,8 @@ static SegGeom seg_geom(int dim) {
 // one tile's latency times the number of waves.  Pick the largest tile of 32 / 16 / 8 entries that still gives every SM
 // a dozen warps; smaller tiles mean more runs crossing tiles, i.e. more fix-up work.
 int seg_tile(int64_t B, int dim) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("TFR_SEG_TILE");
-    forced = e ? atoi(e) : 0;
-    if (forced != 8 && forced != 16 && forced != 32) forced = 0;
-  }
-  if (forced) return forced;
+  const int forced = tune(TUNE_SEG_TILE);
+  if (forced == 8 || forced == 16 || forced == 32) return forced;
   const SegGeom g = seg_geom(dim);
   const int64_t groups_per_warp = 32 / g.lanes;
   const int64_t want = (int64_t)sm_count() * 12;
@@ -693,12 +684,10 @@ static int prep_tiles(const void* fn, size_t smem) {
   auto it = done.find(fn);
   if (it != done.end() && it->second >= smem) return TFR_OK;
   TFR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  static int carve = -2;
   // the same carve-out as every other kernel of the step (common.cuh: prep_kernel), so that no SM has to be
-  // reconfigured between the pass, the tiles and the fix-up; TFR_TILES_CARVEOUT to experiment (100 = max shared)
-  if (carve == -2)
-    carve = getenv("TFR_TILES_CARVEOUT") ? atoi(getenv("TFR_TILES_CARVEOUT"))
-                                         : (getenv("TFR_SMEM_CARVEOUT") ? atoi(getenv("TFR_SMEM_CARVEOUT")) : 62);
+  // reconfigured between the pass, the tiles and the fix-up; TILES_CARVEOUT to experiment (100 = max shared)
+  int carve = tune(TUNE_TILES_CARVEOUT);
+  if (carve < 0) carve = tune(TUNE_SMEM_CARVEOUT);
   TFR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   done[fn] = smem;
   return TFR_OK;
