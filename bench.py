@@ -268,18 +268,25 @@ def run_workload(name, args, torch, with_e2e=True, with_roofline=True, sample_cl
             rows = rng.integers(0, n_train, B)
             batches.append((cols[0][rows].astype(np.float64), cols[1][rows].astype(np.float64),
                             cols[2][rows].astype(np.float64)))   # float64 columns: what ShuffleIterator yields
+        # the driver's loop (svd_train_val.py): step t returns its predictions (host), batch t+1 is handed over at once --
+        # its packing, H2D copy and id sort run under step t's table pass.  Every step's H2D (12 B / rating) and D2H
+        # (8 B / rating) are inside the timed region.
         for b in batches[:3]:
             eng.train_step_host(*b)
         torch.cuda.synchronize()
+        eng.prefetch_host(*batches[3])
         t0 = time.perf_counter()
-        for b in batches[3:]:
-            eng.train_step_host(*b)
+        for j in range(3, len(batches)):
+            eng.train_step_host(*batches[j])
+            if j + 1 < len(batches):
+                eng.prefetch_host(*batches[j + 1])
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         n = len(batches) - 3
         res["e2e"] = {"value": B * n / dt, "unit": "ratings/s", "h2d_bytes_per_step": eng.h2d_bytes(B),
                       "d2h_bytes_per_step": eng.d2h_bytes(B), "ms_per_step": dt / n * 1e3, "steps": n,
-                      "path": "SvdEngine.train_step_host (what Session.run([train_op, logits, infer], feed_dict) calls)"}
+                      "path": "SvdEngine.train_step_host + prefetch_host of the next batch (what Session.run([train_op, logits, "
+                              "infer], feed_dict) / Session.prefetch call; the loop of svd_train_val.py)"}
     if with_roofline and w["d"] % 4 == 0:
         res["roofline"] = kernel_roofline(eng, w, cols, min(args.steps, 20), torch, peak, peak_src)
     del eng

@@ -77,6 +77,9 @@ typedef struct {
   int32_t flags, var_mask;
   int64_t global_step;   /* svd_train_val.py:48 tf.train.get_or_create_global_step()        */
   int64_t batch_cursor;  /* next batch index into a device-resident index stream (see below) */
+  int64_t prefetch_cursor; /* next batch the ASSEMBLE-AHEAD path draws: advanced only by tfr_svd_prefetch_batch's own
+                              kernels (side stream), never by the step -- the step's last CTA advances batch_cursor
+                              while the side stream may be running, so the two must not share a counter */
   double se_sum;         /* sum over the last step's batch of (rate - infer)^2, float64 like
                             svd_train_val.py:104 (np.power(train_rates - train_infer, 2))   */
   float g_mu;            /* last step's d cost / d bias_global (sum_b e_b)                   */
@@ -139,8 +142,11 @@ int tfr_svd_forward(const tfr_svd_tables* t, const int32_t* users, const int32_t
  * cols_* are the training columns resident in HBM; row_index holds the pre-drawn MT19937
  * `np.random.randint(0, N, B)` stream for many steps (generated on the host so that it is the
  * reference's stream).  Batch k = rows row_index[k*B .. k*B+B).  batch_index >= 0 selects that batch;
- * batch_index = -1-k selects batch (opt->batch_cursor + k): -1 = this step's batch (graph replay), -2 = the
- * NEXT step's batch, assembled ahead under the current step's table pass. */
+ * -1 = the batch at opt->batch_cursor (this step's batch; call it on the step's own stream);
+ * -2 = the batch at opt->prefetch_cursor (assemble-ahead on a side stream; tfr_svd_prefetch_batch then advances
+ * that cursor with a kernel of its own, so nothing the concurrent step writes is read);
+ * -3 (tfr_svd_prefetch_batch only) = the batch at batch_cursor, and prefetch_cursor := batch_cursor + 1: primes the
+ * assemble-ahead path, on the step's own stream. */
 int tfr_svd_batch_assemble(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* col_user,
                            const int32_t* col_item, const float* col_rate, const int64_t* row_index,
                            int64_t batch_index, int64_t B, int32_t* users, int32_t* items, float* rates,
@@ -175,6 +181,8 @@ int tfr_unique_first_occurrence(const int32_t* sorted_ids, const int32_t* sorted
  * beta powers and batch_cursor.  Launches: [id sort] -> forward fused into the segment sums -> fix-up of runs that
  * cross tiles -> ONE Adam pass whose last CTA ends the step. */
 int64_t tfr_svd_step_workspace_bytes(int64_t B, int32_t dim);
+/* Sets batch_cursor and prefetch_cursor (both to k): the next step / the next assemble-ahead draw batch k. */
+int tfr_opt_set_cursor(tfr_opt_scalars* opt_dev, int64_t k, void* stream);
 /* The id-only half of a step, for the NEXT batch, to be run on a side stream under the current step's table pass:
  * tfr_svd_batch_assemble(batch_index) into users/items/rates + tfr_dedup_sort_pairs into `workspace`'s sorted-pair
  * buffers.  tfr_svd_train_step_presorted then runs the rest (forward -> segment sums -> Adam pass -> finish) on
@@ -192,11 +200,16 @@ int tfr_svd_train_step_presorted(const tfr_svd_tables* t, tfr_opt_scalars* opt, 
                                  int64_t workspace_bytes, void* stream);
 /* flags / var_mask must equal what tfr_opt_init was given (the host copy selects the launches, the
  * device copy drives the kernels).  side_streams (optional; n_side = 0..1): [0] runs the id sort next to the
- * forward.  Fork/join is by events, so the whole step is still capturable as one graph from `stream`. */
+ * forward.  Fork/join is by the two caller-owned events fork_join_events[0..1] (cudaEvent_t, created on the step's
+ * device, e.g. by tfr_event_create; required when n_side > 0 -- the library keeps no events of its own), so the whole
+ * step is still capturable as one graph from `stream`. */
 int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
                        const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
                        int32_t flags, int32_t var_mask, void* workspace, int64_t workspace_bytes, void* stream,
-                       void* const* side_streams, int32_t n_side);
+                       void* const* side_streams, int32_t n_side, void* const* fork_join_events);
+/* cudaEvent_t (timing disabled) on the current device, for callers without CUDA bindings of their own. */
+int tfr_event_create(void** event_out);
+int tfr_event_destroy(void* event);
 
 /* Pieces of the step, exported for parity tests and for callers that schedule them themselves. */
 typedef struct { /* carved out of the step workspace by tfr_svd_step_carve */
@@ -326,7 +339,13 @@ int tfr_allpairs(const float* user_feat, const float* item_feat, const float* us
 /* ---- host side of the feed_dict boundary: the columns a reference iterator yields (dataio.py:114-117: float64 views
  * of one [B, ncols] matrix, ids included) packed into a pinned staging buffer in the device's types -- int32 ids
  * (value cast, like TF feeding an int32 placeholder, A.7) followed by float32 rates: [users B | items B | rates B].
- * HOST pointers; dtype codes: 0 = float64, 1 = float32, 2 = int32, 3 = int64; strides in BYTES.  No device work. */
+ * HOST pointers; dtype codes: 0 = float64, 1 = float32, 2 = int32, 3 = int64; strides in BYTES.  No device work.
+ * user_num / item_num > 0: ids outside [0, num) are an error (TFR_ERR_INVALID, like TF's embedding_lookup raising
+ * InvalidArgumentError on the CPU) -- nothing out of range ever reaches a gather; <= 0: unchecked. */
+int tfr_host_pack_feed_checked(const void* users_host, int32_t users_dtype, int64_t users_stride,
+                               const void* items_host, int32_t items_dtype, int64_t items_stride,
+                               const void* rates_host, int32_t rates_dtype, int64_t rates_stride, int64_t n,
+                               void* staging_host /* 12 * n bytes */, int64_t user_num, int64_t item_num);
 int tfr_host_pack_feed(const void* users_host, int32_t users_dtype, int64_t users_stride, const void* items_host,
                        int32_t items_dtype, int64_t items_stride, const void* rates_host, int32_t rates_dtype,
                        int64_t rates_stride, int64_t n, void* staging_host /* 12 * n bytes */);

@@ -70,6 +70,8 @@ def lib():
         L.orc_unique_first_occurrence.restype = C.c_int64
         L.orc_segment_sum.argtypes = [_f32p, _i32p, C.c_int64, C.c_int32, C.c_int64, _f32p]
         L.orc_segment_sum.restype = None
+        L.orc_set_segment_order.argtypes = [C.c_int]
+        L.orc_set_segment_order.restype = None
         L.orc_adam_lr_t.argtypes = [C.c_float, C.c_float, C.c_float]
         L.orc_adam_lr_t.restype = C.c_float
         L.orc_adam_sparse.argtypes = [_f32p, _f32p, _f32p, C.c_int64, C.c_int32, _i32p, C.c_int64, _f32p,
@@ -90,6 +92,12 @@ def lib():
         L.orc_allpairs.restype = None
         _lib = L
     return _lib
+
+
+def set_segment_order(order):
+    """0 = batch order (TF's CPU unsorted_segment_sum, the default), 1 = reverse batch order (another legitimate fp32
+    evaluation of the same sums).  Process-wide; tests restore 0."""
+    lib().orc_set_segment_order(int(order))
 
 
 def _p(a, t=_f32p):

@@ -214,10 +214,18 @@ ORC_API int64_t orc_unique_first_occurrence(const int32_t *ids, int64_t B, int32
 }
 
 /* tf.unsorted_segment_sum CPU kernel (A.3): zero-init, then out[idx[b]] += values[b] for b = 0..B-1 IN ORDER */
+/* Summation order of the segment sums.  0 (default) = batch order, what TF's CPU kernel does (A.3).  1 = reverse batch  */
+/* order: an equally legitimate fp32 evaluation of the same sum (TF's GPU unsorted_segment_sum adds with atomics, in no   */
+/* specified order).  Used only by tests/test_oracle.py to MEASURE how far two legitimate orders of this very oracle      */
+/* drift apart -- the yardstick for the fp32 parity bar of tests/test_gpu_parity.py.                */
+static int g_segment_order = 0;
+ORC_API void orc_set_segment_order(int order) { g_segment_order = order; }
+
 ORC_API void orc_segment_sum(const float *values, const int32_t *idx, int64_t B, int32_t width,
                              int64_t n_uniq, float *out) {
   memset(out, 0, (size_t)n_uniq * width * sizeof(float));
-  for (int64_t b = 0; b < B; ++b) {
+  for (int64_t bb = 0; bb < B; ++bb) {
+    const int64_t b = g_segment_order == 1 ? B - 1 - bb : bb;
     float *o = out + (size_t)idx[b] * width;
     const float *v = values + (size_t)b * width;
     for (int k = 0; k < width; ++k) o[k] = o[k] + v[k];

@@ -78,6 +78,16 @@ def svd(train, test, args, log=print):
         start = time.time()
         total_steps = args.epochs * nb_batches
         i = 0
+
+        def feed_of(b):
+            return {user_batch: b[0], item_batch: b[1], rate_batch: b[2], wins_batch: b[3], fails_batch: b[4]}
+        # session mode: this driver owns the iterator, so batch i+1 is drawn (same RandomState order as the reference's
+        # loop: one draw per step) and handed to sess.prefetch as soon as step i has returned its predictions -- its
+        # packing, H2D copy and id sort then run under step i's table pass
+        ahead = None
+        if not (args.mode == "stream" and not discrete) and total_steps > 0:
+            ahead = next(iter_train)
+            sess.prefetch(feed_of(ahead))
         while i < total_steps:
             if args.mode == "stream" and not discrete:
                 # steps i .. next report: the first report comes after one step, then every nb_batches
@@ -93,11 +103,11 @@ def svd(train, test, args, log=print):
                 if report_at % nb_batches != 0:
                     continue  # the tail after the last full epoch is trained but not reported (:106)
             else:
-                train_users, train_items, train_rates, train_wins, train_fails = next(iter_train)
-                _, train_logits, train_infer = sess.run(
-                    [train_op, logits, infer], feed_dict={user_batch: train_users, item_batch: train_items,
-                                                          rate_batch: train_rates, wins_batch: train_wins,
-                                                          fails_batch: train_fails})
+                train_users, train_items, train_rates, train_wins, train_fails = ahead
+                _, train_logits, train_infer = sess.run([train_op, logits, infer], feed_dict=feed_of(ahead))
+                if i + 1 < total_steps:
+                    ahead = next(iter_train)
+                    sess.prefetch(feed_of(ahead))
                 if discrete:
                     nll_batch = sess.run(cost, feed_dict={rate_batch: train_rates, logits: train_logits})
                     proba_batch = ops.sigmoid(train_logits)

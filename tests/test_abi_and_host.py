@@ -206,3 +206,36 @@ def test_host_pack_feed_casts_like_a_tf_feed():
     bad = np.zeros(4)
     assert L.tfr_host_pack_feed(bad.ctypes.data, 9, 8, bad.ctypes.data, 0, 8, bad.ctypes.data, 0, 8, 4,
                                 np.zeros(12, np.int32).ctypes.data) < 0           # unknown dtype code -> error, no crash
+
+
+def test_host_pack_feed_checked_rejects_out_of_range_ids():
+    """tfr_host_pack_feed_checked: ids outside [0, num) are TFR_ERR_INVALID whatever the source dtype -- judged on the
+    source value, so an id that does not fit int32 cannot alias a valid row after the cast."""
+    import ctypes as C
+    L = _lib.load()
+    n = 20000
+    rng = np.random.default_rng(0)
+    rates = rng.random(n)
+    out = np.zeros(3 * n, np.int32)
+    for dt, code in ((np.float64, 0), (np.float32, 1), (np.int32, 2), (np.int64, 3)):
+        users = rng.integers(0, 100, n).astype(dt)
+        items = rng.integers(0, 50, n).astype(dt)
+
+        def call(u, i):
+            return L.tfr_host_pack_feed_checked(u.ctypes.data, code, u.itemsize, i.ctypes.data, code, i.itemsize,
+                                                rates.ctypes.data, 0, 8, n, out.ctypes.data, 100, 50)
+        assert call(users, items) == 0
+        assert np.array_equal(out[:n], users.astype(np.int32)) and np.array_equal(out[n:2 * n], items.astype(np.int32))
+        for pos, val in ((0, 100), (n - 1, -1), (n // 2, 1e6)):
+            u2 = users.copy(); u2[pos] = val
+            assert call(u2, items) == -1 and b"out of range" in L.tfr_last_error()
+            i2 = items.copy(); i2[pos] = 50 if val == 100 else val
+            assert call(users, i2) == -1
+        if dt in (np.int64, np.float64):
+            u2 = users.copy(); u2[3] = 2 ** 32 + 7   # would alias row 7 after a cast to int32
+            assert call(u2, items) == -1
+    # unchecked entry point: same packing, no range test
+    users = np.array([5, 1000000, -3], np.int64); items = np.zeros(3, np.int64); r3 = np.zeros(3)
+    o3 = np.zeros(9, np.int32)
+    assert L.tfr_host_pack_feed(users.ctypes.data, 3, 8, items.ctypes.data, 3, 8, r3.ctypes.data, 0, 8, 3, o3.ctypes.data) == 0
+    assert list(o3[:3]) == [5, 1000000, -3]

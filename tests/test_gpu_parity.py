@@ -19,6 +19,25 @@ RTOL = 1e-5   # north_star: per-step parameters within 1e-5 relative (fp32)
 ATOL = 2e-7   # absolute floor for entries near zero (tables are O(1e-2), updates O(lr))
 
 
+EXEMPT = 1e-3   # fraction of entries allowed outside the element-wise bound (see assert_fp32_close)
+PARITY_STATS = []   # every assert_fp32_close call: what, size, relative L2, entries outside, max abs error
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dump_parity_stats():
+    """Measured parity statistics of this run -> gpurun_out/parity_stats.json (summarised in DESIGN.md section 4)."""
+    yield
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_stats.json"), "w") as f:
+            json.dump(PARITY_STATS, f)
+    except OSError:
+        pass
+
+
 def zipf_ids(rng, n, size, a=1.0):
     p = 1.0 / np.arange(1, n + 1) ** a
     p /= p.sum()
@@ -50,11 +69,13 @@ def assert_fp32_close(got, ref, what, max_abs=None, rtol=RTOL):
     ref = np.asarray(ref, np.float64).reshape(-1)
     d = np.abs(got - ref)
     nref = np.linalg.norm(ref)
-    assert np.linalg.norm(got - ref) <= rtol * max(nref, 1e-30) + 1e-30, "%s: relative L2 error %.3g" % (
-        what, np.linalg.norm(got - ref) / max(nref, 1e-30))
     rms = nref / np.sqrt(max(ref.size, 1))
     bad = d > rtol * np.abs(ref) + rtol * rms + 1e-30
-    assert bad.mean() <= 1e-3, "%s: %d of %d entries outside 1e-5" % (what, bad.sum(), ref.size)
+    PARITY_STATS.append(dict(what=what, n=int(ref.size), rel_l2=float(np.linalg.norm(got - ref) / max(nref, 1e-30)),
+                             outside=int(bad.sum()), max_abs=float(d.max()) if d.size else 0.0, rtol=rtol))
+    assert np.linalg.norm(got - ref) <= rtol * max(nref, 1e-30) + 1e-30, "%s: relative L2 error %.3g" % (
+        what, np.linalg.norm(got - ref) / max(nref, 1e-30))
+    assert bad.mean() <= EXEMPT, "%s: %d of %d entries outside 1e-5" % (what, bad.sum(), ref.size)
     if max_abs is not None:
         assert d.max() <= max_abs, "%s: max abs error %.3g > %.3g" % (what, d.max(), max_abs)
 
@@ -395,6 +416,51 @@ def test_fm_forward_golden_and_oracle(golden_dir):
             np.testing.assert_allclose(y.cpu().numpy(), z["y"], rtol=1e-5, atol=1e-6)
 
 
+# ---- BASELINE.json full size, the benchmarked path itself, stepped against the oracle --------------------------------
+def test_full_size_config4_oracle_stepped_through_the_bench_path():
+    """BASELINE configs[3] (ML-25M shape 162541 x 62423, d = 128, B = 65536) -- the configuration bench.py's `value`
+    is measured on -- stepped by the oracle for 10 steps against (a) run_stream_steps(use_graph=True): one captured
+    8-step pipelined graph + two single-step graphs, the exact path behind `value`, and (b) train_step_host with the
+    next batch prefetched, the path behind `e2e`.  Same synthetic columns and MT19937 index stream as bench.py; the
+    initial tables are injected into both.  (a) and (b) must be bit-identical to each other."""
+    import bench
+    w = bench.WORKLOADS["ml25m_d128_b65536"]
+    U, I, d, B, steps = w["U"], w["I"], w["d"], w["B"], 10
+    cols = bench.make_columns(w)
+    n_train = len(cols[0])
+    np.random.seed(13575)
+    idx = np.concatenate([np.random.randint(0, n_train, (B,)) for _ in range(steps)])
+    tabs = init.init_tables(U, I, d, seed=13575)
+    orc = oracle.SvdOracle(tabs["mu"], tabs["user_bias"], tabs["item_bias"], tabs["user_feat"], tabs["item_feat"],
+                           bench.LR, bench.REG)
+    eng_g = SvdEngine(U, I, d, bench.LR, bench.REG, tables=tabs)
+    eng_h = SvdEngine(U, I, d, bench.LR, bench.REG, tables=tabs)
+    eng_g.set_train_data(*cols)
+    eng_g.set_index_stream(idx, B)
+    eng_g.set_se_ring(steps)
+    assert eng_g.graph_steps == 8
+    bufs = eng_g.run_stream_steps(steps, use_graph=True)
+    batches = [tuple(c[idx[s * B:(s + 1) * B]].astype(np.float64) for c in cols) for s in range(steps)]
+    eng_h.prefetch_host(*batches[0])
+    se_ref = []
+    for s in range(steps):
+        _, infer_h = eng_h.train_step_host(*batches[s])
+        if s + 1 < steps:
+            eng_h.prefetch_host(*batches[s + 1])
+        rows = idx[s * B:(s + 1) * B]
+        ref_logits, ref_infer = orc.train_step(cols[0][rows], cols[1][rows], cols[2][rows])
+        np.testing.assert_allclose(infer_h, ref_infer, rtol=RTOL, atol=2e-6, err_msg="step %d" % s)
+        se_ref.append(np.sum((cols[2][rows].astype(np.float64) - ref_infer.astype(np.float64)) ** 2))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(bufs["infer"].cpu().numpy(), ref_infer, rtol=RTOL, atol=2e-6)   # the last step's fetch
+    np.testing.assert_allclose(eng_g.se_ring.cpu().numpy(), np.array(se_ref), rtol=1e-6)
+    assert eng_g.global_step == steps and eng_h.global_step == steps
+    tg, th = eng_g.get_tables(), eng_h.get_tables()
+    for n in tg:
+        assert np.array_equal(tg[n], th[n]), n          # graph-replayed and host-fed: the same kernels, bit for bit
+    assert_state_close(eng_g, orc, "ml25m full size, 10 steps")
+
+
 # ---- BASELINE.json full sizes: size-independent properties -----------------------------------------------
 def test_full_size_config4_properties():
     """ML-25M shape (162541 x 62423, d=128, B=65536): sortedness + permutation of the dedup, idempotence,
@@ -608,9 +674,10 @@ def test_topk_rows_edge_cases():
 
 
 @pytest.mark.parametrize("shape", [(301, 157, 128), (5000, 3001, 128), (1234, 777, 20), (40, 33, 64), (3000, 17, 256)])
-@pytest.mark.parametrize("ring_cfg", [dict(RING_STAGES=5, RING_STAGE_KB=24, RING_THREADS=544),
-                                      dict(RING_STAGES=2, RING_STAGE_KB=8, RING_THREADS=96),
-                                      dict(RING_STAGES=7, RING_STAGE_KB=12, RING_THREADS=288, RING_L2_HINT=2)])
+@pytest.mark.parametrize("ring_cfg", [dict(RING_STAGES=4, RING_STAGE_KB=24, RING_THREADS=320, RING_CTAS_PER_SM=2),
+                                      dict(RING_STAGES=2, RING_STAGE_KB=8, RING_THREADS=96, RING_CTAS_PER_SM=1),
+                                      dict(RING_STAGES=7, RING_STAGE_KB=12, RING_THREADS=576, RING_L2_HINT=3,
+                                           RING_CTAS_PER_SM=1)])
 def test_ring_pass_bit_identical(shape, ring_cfg):
     """The TMA-bulk ring pass (adam_ring.cu) and the LDG/STG pass (adam.cu) are the same function of their inputs:
     whole train steps (Adam, interleaved tables) with either pass leave bit-identical tables, slots and scalars --
@@ -631,11 +698,72 @@ def test_ring_pass_bit_identical(shape, ring_cfg):
             torch.cuda.synchronize()
             out.append((eng.get_tables(), eng.opt_scalars()))
     finally:
-        _lib.tune_set("PASS_RING", 1)
-        for k, v in dict(RING_STAGES=5, RING_STAGE_KB=24, RING_THREADS=544, RING_L2_HINT=0).items():
+        _lib.tune_set("PASS_RING", 0)
+        for k, v in dict(RING_STAGES=4, RING_STAGE_KB=24, RING_THREADS=320, RING_L2_HINT=2).items():
             _lib.tune_set(k, v)
     (ta, sa), (tb, sb) = out
     for n in ta:
         assert np.array_equal(ta[n].view(np.int32), tb[n].view(np.int32)), n
     for f in ("global_step", "beta1_power", "beta2_power", "lr_t", "g_mu", "se_sum"):
         assert getattr(sa, f) == getattr(sb, f), f
+
+
+def test_host_fed_unfetched_and_prefetched_match_fetched():
+    """sess.run(train_op) without fetching predictions does not synchronise: the pinned staging buffers must still
+    never be repacked while a copy out of them is queued (two sets, event-ordered).  Unfetched, fetched and
+    prefetched-ahead step loops leave bit-identical tables."""
+    U, I, d, B, steps = 3000, 2000, 64, 4096, 12
+    rng = np.random.default_rng(11)
+    batches = [tuple(c.astype(np.float64) for c in make_batch(rng, U, I, B)) for _ in range(steps)]
+    eng_f, _ = both(U, I, d, 1e-3, 0.05)
+    eng_u, _ = both(U, I, d, 1e-3, 0.05)
+    eng_p, _ = both(U, I, d, 1e-3, 0.05)
+    preds_f, preds_p = [], []
+    for b in batches:
+        preds_f.append(eng_f.train_step_host(*b))
+        eng_u.train_step_host(*b, fetch=False)
+    eng_p.prefetch_host(*batches[0])
+    for k, b in enumerate(batches):
+        preds_p.append(eng_p.train_step_host(*b))
+        if k + 1 < steps:
+            eng_p.prefetch_host(*batches[k + 1])
+    torch.cuda.synchronize()
+    tf_, tu, tp = eng_f.get_tables(), eng_u.get_tables(), eng_p.get_tables()
+    for n in tf_:
+        assert np.array_equal(tf_[n], tu[n]), n
+        assert np.array_equal(tf_[n], tp[n]), n
+    for a, b in zip(preds_f, preds_p):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # a prefetched batch that is not the one stepped next is dropped, not trained on
+    eng_p.prefetch_host(*batches[0])
+    eng_p.train_step_host(*batches[1])
+    eng_f.train_step_host(*batches[1])
+    torch.cuda.synchronize()
+    assert np.array_equal(eng_p.get_tables()["user_feat"], eng_f.get_tables()["user_feat"])
+
+
+def test_out_of_range_ids_raise():
+    """ids outside the tables are an error where they enter (TF's lookup raises InvalidArgumentError on the CPU)."""
+    U, I, d, B = 50, 40, 8, 64
+    eng, _ = both(U, I, d, 1e-3, 0.05)
+    rng = np.random.default_rng(0)
+    users, items, rates = make_batch(rng, U, I, B)
+    before = eng.get_tables()
+    for bad_u, bad_i in ((U, None), (-1, None), (None, I), (None, -3), (2 ** 31 + 5, None)):
+        u2, i2 = users.astype(np.float64).copy(), items.astype(np.float64).copy()
+        if bad_u is not None:
+            u2[7] = bad_u
+        if bad_i is not None:
+            i2[9] = bad_i
+        with pytest.raises(_lib.TfrError):
+            eng.train_step_host(u2, i2, rates.astype(np.float64))
+        with pytest.raises(_lib.TfrError):
+            eng.train_step(u2.astype(np.int64), i2.astype(np.int64), rates)
+        with pytest.raises(_lib.TfrError):
+            eng.forward(u2.astype(np.int64), i2.astype(np.int64))
+        with pytest.raises(_lib.TfrError):
+            eng.set_train_data(u2.astype(np.int64), i2.astype(np.int64), rates)
+    after = eng.get_tables()
+    for n in before:
+        assert np.array_equal(before[n], after[n]), n    # nothing was launched
+    assert eng.global_step == 0

@@ -32,7 +32,7 @@ class OptScalars(C.Structure):
                 ("beta1_power", f32), ("beta2_power", f32), ("lr_t", f32),
                 ("one_minus_beta1", f32), ("one_minus_beta2", f32),
                 ("flags", i32), ("var_mask", i32),
-                ("global_step", i64), ("batch_cursor", i64), ("se_sum", C.c_double),
+                ("global_step", i64), ("batch_cursor", i64), ("prefetch_cursor", i64), ("se_sum", C.c_double),
                 ("g_mu", f32), ("ticket", C.c_uint32), ("se_ring", vp), ("se_ring_len", i64), ("timeline", vp)]
 
 
@@ -94,7 +94,9 @@ _PROTOS = {
     "tfr_unique_first_occurrence": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, vp]),
     "tfr_svd_step_workspace_bytes": (i64, [i64, i32]),
     "tfr_svd_train_step": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, i64, vp, vp, i32, i32, vp, i64, vp,
-                                     C.POINTER(vp), i32]),
+                                     C.POINTER(vp), i32, C.POINTER(vp)]),
+    "tfr_event_create": (C.c_int, [C.POINTER(vp)]),
+    "tfr_event_destroy": (C.c_int, [vp]),
     "tfr_svd_prefetch_batch": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, vp]),
     "tfr_svd_train_step_presorted": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, i64, vp, vp, i32, i32, i32, vp, i64,
                                                vp]),
@@ -116,6 +118,8 @@ _PROTOS = {
     "tfr_allpairs_workspace_bytes": (i64, [i64, i64, i32, i32]),
     "tfr_allpairs": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, i64, i64, i32, vp, vp, vp, vp, i64, vp]),
     "tfr_host_pack_feed": (C.c_int, [vp, i32, i64, vp, i32, i64, vp, i32, i64, i64, vp]),
+    "tfr_host_pack_feed_checked": (C.c_int, [vp, i32, i64, vp, i32, i64, vp, i32, i64, i64, vp, i64, i64]),
+    "tfr_opt_set_cursor": (C.c_int, [vp, i64, vp]),
     "tfr_topk_rows": (C.c_int, [vp, i64, i64, i64, i32, vp, vp, vp]),
     "tfr_graph_begin_capture": (C.c_int, [vp]),
     "tfr_graph_end_capture": (C.c_int, [vp, C.POINTER(vp)]),

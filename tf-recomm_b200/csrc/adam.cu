@@ -69,6 +69,8 @@ struct StreamArgs {
 template <int UNROLL>
 __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_constant__ StreamArgs a,
                                                                 const tfr_opt_scalars* __restrict__ opt, int tl_slot) {
+  pdl_wait();                // the fix-up's summed gradients and slot maps are complete
+  pdl_launch_dependents();   // the next step's segment sums may become resident as this grid drains
   TlScope tl_scope(opt, tl_slot);
   const AdamK k = load_k(opt);
   const uint32_t stamp = (uint32_t)opt->global_step;
@@ -308,7 +310,7 @@ __global__ void opt_init_kernel(tfr_opt_scalars* opt, float lr, float reg, float
   float tt = sqrt_rn(sub_rn(1.0f, beta2));
   opt->lr_t = div_rn(mul_rn(lr, tt), sub_rn(1.0f, beta1));
   opt->flags = flags; opt->var_mask = var_mask;
-  opt->global_step = 0; opt->batch_cursor = 0;
+  opt->global_step = 0; opt->batch_cursor = 0; opt->prefetch_cursor = 0;
   opt->se_sum = 0.0; opt->g_mu = 0.0f; opt->ticket = 0u;
   opt->se_ring = nullptr; opt->se_ring_len = 0; opt->timeline = nullptr;
 }
@@ -375,14 +377,14 @@ static int launch_stream_chunks(const StreamTab* chunks, int n_chunks, const tfr
     a.partition = 1;
     grid = at;
   }
+  const bool pdl = tune(TUNE_PDL) != 0;
   if (cfg_unroll >= 4) {
     TFR_PREP(adam_stream_multi_kernel<4>);
-    adam_stream_multi_kernel<4><<<(unsigned)grid, cfg_threads, 0, st>>>(a, opt, tl_slot);
+    TFR_CUDA(launch_kernel(adam_stream_multi_kernel<4>, dim3((unsigned)grid), dim3(cfg_threads), 0, st, pdl, a, opt, tl_slot));
   } else {
     TFR_PREP(adam_stream_multi_kernel<2>);
-    adam_stream_multi_kernel<2><<<(unsigned)grid, cfg_threads, 0, st>>>(a, opt, tl_slot);
+    TFR_CUDA(launch_kernel(adam_stream_multi_kernel<2>, dim3((unsigned)grid), dim3(cfg_threads), 0, st, pdl, a, opt, tl_slot));
   }
-  TFR_LAUNCH_CHECK();
   return TFR_OK;
 }
 

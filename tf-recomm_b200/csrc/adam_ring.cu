@@ -45,8 +45,13 @@ struct RingArgs {
   RingBias b[2];
   int n_tabs, n_bias;
   int n_ring;            // stages in the ring
-  uint32_t stage_bytes;  // bytes of one ring slot (>= every table's stage)
-  int l2_hint;           // 0 = none, 1 = evict_first on the bulk loads, 2 = on loads and stores
+  uint32_t stage_bytes;  // bytes of one ring slot: [rows' var | m | v ... ][slot-map entries of the rows]
+  uint32_t slot_off;     // offset of the slot-map entries inside a ring slot
+  int l2_hint;           // L2 evict_first policy: bit 0 = on the bulk loads, bit 1 = on the bulk stores
+  int slot_mode;         // 1 = slot-map entries ride along with the stage (default); experiments: 0 = read from global
+                         // memory, 2 = as 1 without the look-ahead gradient fetch, 3 = no lookups at all (WRONG
+                         // results: the memory ceiling of the pass)
+  int copy_only;         // experiment: no arithmetic
   FinishArgs fin;
 };
 
@@ -59,6 +64,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -117,19 +133,26 @@ __device__ __forceinline__ StageRef stage_ref(const RingArgs& a, int64_t g) {
   return r;
 }
 
-__global__ void __launch_bounds__(RING_MAX_THREADS, 1) adam_ring_kernel(const __grid_constant__ RingArgs a,
+// CAP / MINB: launch bounds only (register budget): <384, 2> = two CTAs of 8 consumer warps + the two DMA warps per SM,
+// <576, 1> one CTA of up to 18 warps, <1024, 1> anything wider
+template <int CAP, int MINB>
+__global__ void __launch_bounds__(CAP, MINB) adam_ring_kernel(const __grid_constant__ RingArgs a,
                                                                        const tfr_opt_scalars* __restrict__ opt,
                                                                        int tl_slot) {
+  pdl_wait();                // the fix-up's summed gradients and slot maps are complete
+  pdl_launch_dependents();   // the next step's segment sums may become resident as this grid drains
   TlScope tl_scope(opt, tl_slot);
   extern __shared__ __align__(128) unsigned char ring_smem[];
   uint64_t* const full = reinterpret_cast<uint64_t*>(ring_smem + (size_t)a.n_ring * a.stage_bytes);
   uint64_t* const done = full + a.n_ring;
-  const int n_cons = (int)blockDim.x - 32;  // the last warp moves the bytes
+  uint64_t* const empty = done + a.n_ring;
+  const int n_cons = (int)blockDim.x - 64;  // the last two warps move the bytes: one thread loads, one stores
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int s = 0; s < a.n_ring; ++s) {
       mbar_init(full + s, 1);
       mbar_init(done + s, (uint32_t)(n_cons >> 5));
+      mbar_init(empty + s, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -138,32 +161,40 @@ __global__ void __launch_bounds__(RING_MAX_THREADS, 1) adam_ring_kernel(const __
   const int64_t n_it = total > (int64_t)blockIdx.x ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (tid >= n_cons) {
-    // ---- the DMA thread: loads run n_ring - 1 stages ahead; a stage is refilled once the bulk store of its
-    // previous contents has finished READING shared memory (wait_group.read, one store group behind) ----
+    auto gaddr = [&](const StageRef& r) {
+      return reinterpret_cast<unsigned char*>(a.t[r.tb].base) + (size_t)r.row0 * (size_t)(12 * a.t[r.tb].width);
+    };
+    const uint64_t pol = a.l2_hint ? l2_evict_first_policy() : 0;
     if (tid == n_cons) {
-      const bool hl = a.l2_hint >= 1, hs = a.l2_hint >= 2;
-      const uint64_t pol = a.l2_hint ? l2_evict_first_policy() : 0;
-      auto gaddr = [&](const StageRef& r) {
-        return reinterpret_cast<unsigned char*>(a.t[r.tb].base) + (size_t)r.row0 * (size_t)(12 * a.t[r.tb].width);
-      };
-      auto load = [&](int64_t i) {
+      // ---- the LOADER: fills ring slot i % n_ring as soon as the storer has drained its previous contents ----
+      const bool hl = a.l2_hint & 1;
+      for (int64_t i = 0; i < n_it; ++i) {
+        const int s = (int)(i % a.n_ring);
+        if (i >= a.n_ring) mbar_wait(empty + s, (uint32_t)(((i / a.n_ring) - 1) & 1));
         const StageRef r = stage_ref(a, (int64_t)blockIdx.x + i * gridDim.x);
         const uint32_t bytes = r.rows * (uint32_t)(12 * a.t[r.tb].width);
-        const int s = (int)(i % a.n_ring);
-        mbar_expect_tx(full + s, bytes);
-        bulk_load(ring_smem + (size_t)s * a.stage_bytes, gaddr(r), bytes, full + s, hl, pol);
-      };
-      const int64_t pro = n_it < a.n_ring ? n_it : a.n_ring;
-      for (int64_t i = 0; i < pro; ++i) load(i);
+        // the rows' slot-map entries ride along (an even number of them: 16-byte granularity; an odd last row's
+        // entry is read from global memory by its consumers)
+        const uint32_t sbytes = (a.slot_mode >= 1 && a.t[r.tb].slot) ? (r.rows & ~1u) * 8u : 0u;
+        unsigned char* const dst = ring_smem + (size_t)s * a.stage_bytes;
+        mbar_expect_tx(full + s, bytes + sbytes);
+        bulk_load(dst, gaddr(r), bytes, full + s, hl, pol);
+        if (sbytes) bulk_load(dst + a.slot_off, a.t[r.tb].slot + r.row0, sbytes, full + s, false, pol);
+      }
+    } else if (tid == n_cons + 32) {
+      // ---- the STORER: writes a stage back once every consumer warp is done with it; the ring slot is handed
+      // back to the loader when the bulk store has finished READING shared memory (one store group behind, so
+      // that a store is always in flight) ----
+      const bool hs = a.l2_hint & 2;
       for (int64_t i = 0; i < n_it; ++i) {
         const int s = (int)(i % a.n_ring);
         mbar_wait(done + s, (uint32_t)((i / a.n_ring) & 1));
         const StageRef r = stage_ref(a, (int64_t)blockIdx.x + i * gridDim.x);
         bulk_store(gaddr(r), ring_smem + (size_t)s * a.stage_bytes, r.rows * (uint32_t)(12 * a.t[r.tb].width), hs, pol);
         bulk_commit();
-        if (i >= 1 && i - 1 + a.n_ring < n_it) {
-          bulk_wait_read<1>();  // the store of iteration i-1 has left shared memory
-          load(i - 1 + a.n_ring);
+        if (i >= 1) {
+          bulk_wait_read<1>();
+          mbar_arrive(empty + (int)((i - 1) % a.n_ring));
         }
       }
       bulk_wait_all();
@@ -210,50 +241,66 @@ __global__ void __launch_bounds__(RING_MAX_THREADS, 1) adam_ring_kernel(const __
       }
     }
     // ---- the ring's consumers: unit u of a stage (row u / upr, column u % upr) belongs to thread u % n_cons ----
-    // slot-map entry and summed gradient of the NEXT stage's units are fetched while this stage is computed
-    int64_t sl_next[RING_MAXU];
-    auto fetch_slots = [&](int64_t i, int64_t (&sl)[RING_MAXU]) {
+    // A row's slot-map entry arrives in shared memory with the stage.  The summed gradient of a touched row is
+    // fetched one stage AHEAD when that stage has already landed (the loads run n_ring - 1 stages ahead, so it
+    // usually has): the L2 round trip then overlaps this stage's arithmetic instead of preceding the next one's.
+    float4 g_pf[RING_MAXU];
+    bool has_pf[RING_MAXU];
+    bool pf_valid = false;
 #pragma unroll
-      for (int j = 0; j < RING_MAXU; ++j) sl[j] = -1;
-      if (i >= n_it) return;
+    for (int j = 0; j < RING_MAXU; ++j) { has_pf[j] = false; g_pf[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    // slot-map entry of row `row` of the stage in ring slot `st_base`
+    auto slot_of = [&](const RingTable& t, const StageRef& r, const unsigned char* st_base, uint32_t row) -> int64_t {
+      if (!t.slot || a.slot_mode == 3) return -1;
+      if (a.slot_mode >= 1 && row < (r.rows & ~1u)) return reinterpret_cast<const int64_t*>(st_base + a.slot_off)[row];
+      return t.slot[r.row0 + row];
+    };
+    auto lookup = [&](int64_t i, bool (&has)[RING_MAXU], float4 (&g)[RING_MAXU]) {
       const StageRef r = stage_ref(a, (int64_t)blockIdx.x + i * gridDim.x);
       const RingTable& t = a.t[r.tb];
-      if (!t.slot) return;
       const uint32_t upr = (uint32_t)t.width >> 2, units = r.rows * upr;
+      const unsigned char* st_base = ring_smem + (size_t)(i % a.n_ring) * a.stage_bytes;
 #pragma unroll
       for (int j = 0; j < RING_MAXU; ++j) {
+        has[j] = false;
         const uint32_t u = (uint32_t)tid + (uint32_t)j * (uint32_t)n_cons;
-        if (u < units) sl[j] = t.slot[r.row0 + u / upr];
+        if (u < units) {
+          const uint32_t row = u / upr;
+          const int64_t sl = slot_of(t, r, st_base, row);
+          if ((uint32_t)(sl >> 32) == stamp && t.slot) {
+            has[j] = true;
+            g[j] = *reinterpret_cast<const float4*>(t.gsum + (size_t)(uint32_t)sl * t.width + ((u - row * upr) << 2));
+          }
+        }
       }
     };
-    fetch_slots(0, sl_next);
     for (int64_t i = 0; i < n_it; ++i) {
       const StageRef r = stage_ref(a, (int64_t)blockIdx.x + i * gridDim.x);
       const RingTable& t = a.t[r.tb];
       const uint32_t upr = (uint32_t)t.width >> 2, units = r.rows * upr;
-      int64_t sl[RING_MAXU];
+      const int s = (int)(i % a.n_ring);
+      unsigned char* const st_base = ring_smem + (size_t)s * a.stage_bytes;
+      float4* const st = reinterpret_cast<float4*>(st_base);
+      mbar_wait(full + s, (uint32_t)((i / a.n_ring) & 1));
       float4 g[RING_MAXU];
       bool has[RING_MAXU];
+      if (pf_valid) {
 #pragma unroll
-      for (int j = 0; j < RING_MAXU; ++j) {
-        sl[j] = sl_next[j];
-        has[j] = false;
-        g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const uint32_t u = (uint32_t)tid + (uint32_t)j * (uint32_t)n_cons;
-        if (u < units && (uint32_t)(sl[j] >> 32) == stamp && t.slot) {
-          has[j] = true;
-          g[j] = *reinterpret_cast<const float4*>(t.gsum + (size_t)(uint32_t)sl[j] * t.width + ((u % upr) << 2));
-        }
+        for (int j = 0; j < RING_MAXU; ++j) { has[j] = has_pf[j]; g[j] = g_pf[j]; }
+      } else {
+        lookup(i, has, g);
       }
-      fetch_slots(i + 1, sl_next);
-      const int s = (int)(i % a.n_ring);
-      float4* const st = reinterpret_cast<float4*>(ring_smem + (size_t)s * a.stage_bytes);
-      mbar_wait(full + s, (uint32_t)((i / a.n_ring) & 1));
+      pf_valid = false;
+      if (a.slot_mode <= 1 && i + 1 < n_it && mbar_test(full + (int)((i + 1) % a.n_ring), (uint32_t)(((i + 1) / a.n_ring) & 1))) {
+        lookup(i + 1, has_pf, g_pf);
+        pf_valid = true;
+      }
       auto update = [&](uint32_t u, bool hs, const float4& gg) {
         const uint32_t row = u / upr, col = u - row * upr;
         float4* const p = st + (size_t)row * 3u * upr + col;
         float4 x = p[0], y = p[upr], z = p[2u * upr];
-        if (hs) {
+        if (a.copy_only) {
+        } else if (hs) {
           adam_grad(x.x, y.x, z.x, gg.x, k);
           adam_grad(x.y, y.y, z.y, gg.y, k);
           adam_grad(x.z, y.z, z.z, gg.z, k);
@@ -275,11 +322,11 @@ __global__ void __launch_bounds__(RING_MAX_THREADS, 1) adam_ring_kernel(const __
       for (uint32_t u = (uint32_t)tid + (uint32_t)RING_MAXU * (uint32_t)n_cons; u < units; u += (uint32_t)n_cons) {
         bool hs = false;
         float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t.slot) {
-          const uint32_t row = u / upr;
-          const int64_t s2 = t.slot[r.row0 + row];
-          hs = (uint32_t)(s2 >> 32) == stamp;
-          if (hs) gg = *reinterpret_cast<const float4*>(t.gsum + (size_t)(uint32_t)s2 * t.width + ((u - row * upr) << 2));
+        const uint32_t row = u / upr;
+        const int64_t s2 = slot_of(t, r, st_base, row);
+        if ((uint32_t)(s2 >> 32) == stamp && t.slot) {
+          hs = true;
+          gg = *reinterpret_cast<const float4*>(t.gsum + (size_t)(uint32_t)s2 * t.width + ((u - row * upr) << 2));
         }
         update(u, hs, gg);
       }
@@ -305,16 +352,18 @@ __global__ void __launch_bounds__(RING_MAX_THREADS, 1) adam_ring_kernel(const __
 }
 
 struct RingConfig {
-  int enabled, n_ring, stage_kb, threads, l2_hint, ctas_per_sm;
+  int enabled, n_ring, stage_kb, threads, l2_hint, ctas_per_sm, slot_mode, copy_only;
 };
 static RingConfig ring_config() {
   RingConfig c;
   c.enabled = tune(TUNE_PASS_RING);
   c.n_ring = tune(TUNE_RING_STAGES);
   c.stage_kb = tune(TUNE_RING_STAGE_KB);
-  c.threads = tune(TUNE_RING_THREADS);   // 16 consumer warps + the DMA warp
+  c.threads = tune(TUNE_RING_THREADS);   // consumer warps + the loader warp + the storer warp
   c.l2_hint = tune(TUNE_RING_L2_HINT);
   c.ctas_per_sm = tune(TUNE_RING_CTAS_PER_SM);
+  c.slot_mode = tune(TUNE_RING_SLOT_MODE);
+  c.copy_only = tune(TUNE_STREAM_COPY_ONLY);
   return c;
 }
 
@@ -330,7 +379,8 @@ bool ring_pass_eligible(const tfr_adam_table* tabs, int n) {
     if (t.width % 4 != 0 || t.stride != 3 * (int64_t)t.width || t.m != t.var + t.width || t.v != t.var + 2 * t.width ||
         ((uintptr_t)t.var & 15u) || (t.gsum && ((uintptr_t)t.gsum & 15u)))
       return false;
-    if (12 * (int64_t)t.width > 48 * 1024) return false;
+    if (2 * 12 * (int64_t)t.width > 48 * 1024) return false;  // a stage is at least two rows
+    if (t.slot && ((uintptr_t)t.slot & 15u)) return false;
     if (++nf > 2) return false;
   }
   return nf > 0;
@@ -343,6 +393,7 @@ int ring_pass_launch(const tfr_adam_table* tabs, int n, const tfr_opt_scalars* o
   memset(&a, 0, sizeof(a));
   if (fin) a.fin = *fin;
   uint32_t stage_bytes = 0;
+  int max_stage_rows = 0;
   int64_t total = 0;
   for (int i = 0; i < n; ++i) {
     const tfr_adam_table& t = tabs[i];
@@ -355,37 +406,52 @@ int ring_pass_launch(const tfr_adam_table* tabs, int n, const tfr_opt_scalars* o
     r.base = t.var; r.slot = t.slot; r.gsum = t.gsum; r.rows = t.rows; r.width = t.width;
     const int row_bytes = 12 * t.width;
     int sr = (c.stage_kb * 1024) / row_bytes;
-    if (sr < 1) sr = 1;
+    sr &= ~1;  // even: the slot-map entries of a stage are copied in 16-byte units
+    if (sr < 2) sr = 2;
     r.stage_rows = sr;
+    if (sr > max_stage_rows) max_stage_rows = sr;
     r.n_stages = (t.rows + sr - 1) / sr;
     total += r.n_stages;
     if ((uint32_t)(sr * row_bytes) > stage_bytes) stage_bytes = (uint32_t)(sr * row_bytes);
   }
   stage_bytes = (stage_bytes + 127u) & ~127u;
+  a.slot_off = stage_bytes;
+  stage_bytes += ((uint32_t)max_stage_rows * 8u + 127u) & ~127u;
   a.stage_bytes = stage_bytes;
   a.n_ring = c.n_ring < 2 ? 2 : c.n_ring;
   a.l2_hint = c.l2_hint;
-  const size_t smem = (size_t)a.n_ring * stage_bytes + 2 * (size_t)a.n_ring * sizeof(uint64_t);
-  static std::mutex mu;
-  static size_t prepared = 0;
-  {
-    std::lock_guard<std::mutex> g(mu);
-    if (smem > prepared) {
-      TFR_CUDA(cudaFuncSetAttribute(adam_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      prepared = smem;
-    }
+  a.slot_mode = c.slot_mode;
+  a.copy_only = c.copy_only;
+  const size_t smem = (size_t)a.n_ring * stage_bytes + 3 * (size_t)a.n_ring * sizeof(uint64_t);
+  if (smem > 227 * 1024) {
+    set_error("ring pass: %zu bytes of shared memory (RING_STAGES x RING_STAGE_KB too large)", smem);
+    return TFR_ERR_INVALID;
   }
-  TFR_PREP(adam_ring_kernel);
   int64_t grid = (int64_t)sm_count() * (c.ctas_per_sm < 1 ? 1 : c.ctas_per_sm);
   if (grid > total) grid = total;
   if (grid < 1) grid = 1;
   int threads = c.threads;
-  if (threads < 64) threads = 64;
+  if (threads < 96) threads = 96;
   if (threads > RING_MAX_THREADS) threads = RING_MAX_THREADS;
   threads = threads / 32 * 32;
-  adam_ring_kernel<<<(unsigned)grid, threads, smem, st>>>(a, opt, tl_slot);
-  TFR_LAUNCH_CHECK();
-  return TFR_OK;
+  static std::mutex mu;
+  static std::map<const void*, size_t> prepared;
+  auto go = [&](auto kernel) -> int {
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    {
+      std::lock_guard<std::mutex> g(mu);
+      if (smem > prepared[fn]) {
+        TFR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prepared[fn] = smem;
+      }
+    }
+    prep_kernel_carveout(fn, smem * (size_t)(c.ctas_per_sm < 1 ? 1 : c.ctas_per_sm));
+    TFR_CUDA(launch_kernel(kernel, dim3((unsigned)grid), dim3(threads), smem, st, tune(TUNE_PDL) != 0, a, opt, tl_slot));
+    return TFR_OK;
+  };
+  if (threads <= 320 && c.ctas_per_sm >= 2) return go(adam_ring_kernel<384, 2>);
+  if (threads <= 576) return go(adam_ring_kernel<576, 1>);
+  return go(adam_ring_kernel<1024, 1>);
 }
 
 }  // namespace tfr

@@ -20,23 +20,32 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int sm_count() {
-  static int cached = 0;
-  if (cached > 0) return cached;
+int sm_count() {  // of the CURRENT device (cached per device: a process may drive several)
+  static int cached[64] = {0};
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-  cached = n;
+  if (dev >= 0 && dev < 64) cached[dev] = n;
   return n;
 }
 
 namespace {
 struct TuneEntry { const char* name; int dflt; };
 const TuneEntry kTune[TUNE_COUNT] = {
-    {"SMEM_CARVEOUT", 62},   // 141 KB of shared memory: four CTAs of the segment-sum kernel (32 KB each) per SM
+    {"SMEM_CARVEOUT", 62},   // 141 KB of shared memory on every kernel of the step: four CTAs of the segment-sum kernel
+                             // (32 KB each) per SM, and enough L1 for the LDG pass (100 %: pass 125 -> 149 us)
     {"TILES_CARVEOUT", -1}, {"SEG_MAX_UNITS", 0}, {"SEG_TILE", 0}, {"STREAM_COPY_ONLY", 0}, {"STREAM_LD", 2},
-    {"STREAM_ST", 0}, {"STREAM_CTAS_PER_SM", 2}, {"STREAM_UNROLL", 2}, {"STREAM_THREADS", 448}, {"PASS_RING", 1},
-    {"RING_STAGES", 5}, {"RING_STAGE_KB", 24}, {"RING_THREADS", 544}, {"RING_L2_HINT", 0}, {"RING_CTAS_PER_SM", 1},
+    {"STREAM_ST", 0}, {"STREAM_CTAS_PER_SM", 2}, {"STREAM_UNROLL", 2}, {"STREAM_THREADS", 448},
+    // the TMA-bulk ring pass is OFF by default: alone it matches the LDG pass (135 vs 137 us at the ML-25M shape), in
+    // situ -- the next batch's id sort competing for issue slots with its 16 consumer warps per SM -- it loses (150-157
+    // vs 125 us); profiles/r02_pass_ring_vs_ldg.md
+    {"PASS_RING", 0},
+    {"RING_STAGES", 4}, {"RING_STAGE_KB", 24}, {"RING_THREADS", 320}, {"RING_L2_HINT", 2}, {"RING_CTAS_PER_SM", 2},
+    {"RING_SLOT_MODE", 1},
+    // programmatic dependent launch along tiles -> fix-up -> pass: no gain at the ML-25M shape (178.2 vs 177.5 us per
+    // step) and a loss at the ML-1M shape (the early-resident dependents delay the side stream's id sort: 53 vs 37 us)
+    {"PDL", 0},
 };
 std::mutex g_tune_mu;
 int g_tune_val[TUNE_COUNT];
@@ -56,16 +65,24 @@ int tune(TuneKey k) {
 }
 
 int fwd_err_n_partials(int dim, int64_t B);
+int advance_prefetch_cursor(tfr_opt_scalars* opt, cudaStream_t st, bool prime);
 int seg_tile(int64_t B, int dim);
 int svd_segment_grads_impl(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const int32_t* users,
                            const int32_t* items, int64_t B, const tfr_svd_step_ws* ws, int flags_host, void* stream);
 int adam_pass_and_finish(const tfr_adam_table* tabs, int nt, const tfr_svd_tables* t, tfr_opt_scalars* opt,
                          const tfr_svd_step_ws* ws, int n_partials, int tl_slot, void* stream);
 
-void prep_kernel(const void* fn) {
+void prep_kernel(const void* fn) { prep_kernel_carveout(fn, 0); }
+
+void prep_kernel_carveout(const void* fn, size_t smem_per_sm) {
   static std::mutex mu;
   static std::map<const void*, int> applied;  // the carve-out a kernel was last given
-  const int carve = tune(TUNE_SMEM_CARVEOUT);
+  int carve = tune(TUNE_SMEM_CARVEOUT);
+  if (carve > 0 && smem_per_sm > 0) {
+    const size_t need = smem_per_sm + 4096;  // + the per-CTA reserve
+    const int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > carve) carve = pct > 100 ? 100 : pct;
+  }
   std::lock_guard<std::mutex> g(mu);
   auto it = applied.find(fn);
   if (it != applied.end() && it->second == carve) return;
@@ -147,8 +164,9 @@ static int64_t carve(char* base, int64_t B, int32_t dim, tfr_svd_step_ws* o) {
   tfr_svd_step_ws w;
   memset(&w, 0, sizeof(w));
   w.err = (float*)take(B * 4);
-  w.partials = (float*)take(TFR_MAX_PARTIALS * 4);
-  w.se_partials = (double*)take(TFR_MAX_PARTIALS * 8);
+  // + 1: [TFR_MAX_PARTIALS] receives the partials folded by the fix-up's last CTA (off the table pass's tail)
+  w.partials = (float*)take((TFR_MAX_PARTIALS + 1) * 4);
+  w.se_partials = (double*)take((TFR_MAX_PARTIALS + 1) * 8);
   w.su_ids = (int32_t*)take(B * 4);
   w.su_pos = (int32_t*)take(B * 4);
   w.si_ids = (int32_t*)take(B * 4);
@@ -201,14 +219,14 @@ extern "C" int tfr_svd_step_carve(void* workspace, int64_t workspace_bytes, int6
 //   S0: segment sums (need err + sorted pairs) -> fix-up  (write gsum and the row -> slot maps)
 //   S0: Adam: ONE in-order pass over every row of every table  |  SGD: slice rows only (ops.py:145)
 //   S0: finish
-static cudaEvent_t g_ev[2] = {nullptr, nullptr};
-
 static int run_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users, const int32_t* items,
                     const float* rates, int64_t B, float* logits, float* infer, int32_t flags, int32_t var_mask,
                     void* workspace, int64_t workspace_bytes, void* stream, void* const* side_streams, int32_t n_side,
-                    bool presorted, int phases = 3) {
+                    void* const* fj_events, bool presorted, int phases = 3) {
   TFR_CHECK_ARG(t && opt && users && items && rates && B > 0 && t->dim > 0);
-  TFR_CHECK_ARG(n_side >= 0 && n_side <= 1 && (n_side == 0 || side_streams));
+  TFR_CHECK_ARG(n_side >= 0 && n_side <= 1 && (n_side == 0 || (side_streams && fj_events && fj_events[0] && fj_events[1])));
+  cudaEvent_t ev_fork = n_side > 0 ? (cudaEvent_t)fj_events[0] : nullptr;
+  cudaEvent_t ev_join = n_side > 0 ? (cudaEvent_t)fj_events[1] : nullptr;
   // flags / var_mask repeat what the caller gave tfr_opt_init: the device copy drives the kernels, the
   // host copy selects which launches are issued (var_list: untrained tables get no launch at all).
   const bool sgd = flags & TFR_OPT_SGD;
@@ -223,13 +241,14 @@ static int run_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t
   // Single-table mode: the forward is fused into the segment sums.  Row-sharded mode (g_* set): every rank needs
   // every occurrence's error, the local tiles only visit the occurrences of local rows -> separate forward.
   const bool fused = t->g_user_feat == nullptr;
-  const int n_partials = fused ? tfr_svd_fused_n_partials(dim, B) : fwd_err_n_partials(dim, B);
+  // fused: the fix-up's last CTA has already folded the forward's per-CTA partial sums into [TFR_MAX_PARTIALS]
+  tfr_svd_step_ws ws_fin = ws;
+  int n_partials = fused ? 1 : fwd_err_n_partials(dim, B);
+  if (fused) { ws_fin.partials = ws.partials + TFR_MAX_PARTIALS; ws_fin.se_partials = ws.se_partials + TFR_MAX_PARTIALS; }
   if (!(phases & 1)) goto phase2;
   if (sorts != s0) {
-    if (!g_ev[0])
-      for (int i = 0; i < 2; ++i) TFR_CUDA(cudaEventCreateWithFlags(&g_ev[i], cudaEventDisableTiming));
-    TFR_CUDA(cudaEventRecord(g_ev[0], s0));
-    TFR_CUDA(cudaStreamWaitEvent(sorts, g_ev[0], 0));
+    TFR_CUDA(cudaEventRecord(ev_fork, s0));
+    TFR_CUDA(cudaStreamWaitEvent(sorts, ev_fork, 0));
   }
   // + 1: in row-sharded mode the value user_num / item_num itself occurs (the "not mine" mark)
   if (!presorted && (rc = tfr_dedup_sort_pairs_tl(users, (int64_t)t->user_num + 1, ws.su_ids, ws.su_pos, items,
@@ -238,8 +257,8 @@ static int run_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t
     return rc;
   if (!fused && (rc = tfr_svd_fwd_err(t, opt, users, items, rates, B, logits, infer, &ws, s0))) return rc;
   if (sorts != s0) {
-    TFR_CUDA(cudaEventRecord(g_ev[1], sorts));
-    TFR_CUDA(cudaStreamWaitEvent(s0, g_ev[1], 0));
+    TFR_CUDA(cudaEventRecord(ev_join, sorts));
+    TFR_CUDA(cudaStreamWaitEvent(s0, ev_join, 0));
   }
   if (fused) {
     if ((rc = tfr_svd_fwd_segment_grads(t, opt, users, items, rates, B, logits, infer, flags, &ws, s0))) return rc;
@@ -257,7 +276,7 @@ phase2:
     if (var_mask & TFR_VAR_IB) tabs[nt++] = tfr_adam_table{t->item_bias, t->m_ib, t->v_ib, t->item_num, 1, t->item_slot, ws.gsum_ib, 0};
     if (var_mask & TFR_VAR_IF) tabs[nt++] = tfr_adam_table{t->item_feat, t->m_if, t->v_if, t->item_num, dim, t->item_slot, ws.gsum_if, t->feat_stride};
     if (var_mask & TFR_VAR_UF) tabs[nt++] = tfr_adam_table{t->user_feat, t->m_uf, t->v_uf, t->user_num, dim, t->user_slot, ws.gsum_uf, t->feat_stride};
-    return adam_pass_and_finish(tabs, nt, t, opt, &ws, n_partials, TFR_TL_STREAM_UF, s0);
+    return adam_pass_and_finish(tabs, nt, t, opt, &ws_fin, n_partials, TFR_TL_STREAM_UF, s0);
   }
   {
     tfr_slice_update sides[2];
@@ -272,15 +291,16 @@ phase2:
                                      ws.si_ids, ws.gsum_if, ws.gsum_ib, t->feat_stride};
     if (ns && (rc = tfr_adam_slice_multi(sides, ns, dim, B, opt, 1, TFR_TL_TOUCHED_U, s0))) return rc;
   }
-  return tfr_svd_finish_step(t, opt, users, items, B, &ws, n_partials, s0);
+  return tfr_svd_finish_step(t, opt, users, items, B, &ws_fin, n_partials, s0);
 }
 
 extern "C" int tfr_svd_train_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
                                   const int32_t* items, const float* rates, int64_t B, float* logits, float* infer,
                                   int32_t flags, int32_t var_mask, void* workspace, int64_t workspace_bytes,
-                                  void* stream, void* const* side_streams, int32_t n_side) {
+                                  void* stream, void* const* side_streams, int32_t n_side,
+                                  void* const* fork_join_events) {
   return run_step(t, opt, users, items, rates, B, logits, infer, flags, var_mask, workspace, workspace_bytes, stream,
-                  side_streams, n_side, false);
+                  side_streams, n_side, fork_join_events, false);
 }
 
 extern "C" int tfr_svd_train_step_presorted(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* users,
@@ -289,20 +309,22 @@ extern "C" int tfr_svd_train_step_presorted(const tfr_svd_tables* t, tfr_opt_sca
                                             void* workspace, int64_t workspace_bytes, void* stream) {
   TFR_CHECK_ARG(phases >= 1 && phases <= 3);
   return run_step(t, opt, users, items, rates, B, logits, infer, flags, var_mask, workspace, workspace_bytes, stream,
-                  nullptr, 0, true, phases);
+                  nullptr, 0, nullptr, true, phases);
 }
 
 extern "C" int tfr_svd_prefetch_batch(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* col_user,
                                       const int32_t* col_item, const float* col_rate, const int64_t* row_index,
                                       int64_t batch_index, int64_t B, int32_t* users, int32_t* items, float* rates,
                                       void* workspace, int64_t workspace_bytes, void* stream) {
-  TFR_CHECK_ARG(t && B > 0 && t->dim > 0);
+  TFR_CHECK_ARG(t && B > 0 && t->dim > 0 && batch_index >= -3);
   tfr_svd_step_ws ws;
   int rc = tfr_svd_step_carve(workspace, workspace_bytes, B, t->dim, &ws);
   if (rc) return rc;
-  if ((rc = tfr_svd_batch_assemble(t, opt, col_user, col_item, col_rate, row_index, batch_index, B, users, items,
-                                   rates, stream)))
+  if ((rc = tfr_svd_batch_assemble(t, opt, col_user, col_item, col_rate, row_index, batch_index == -3 ? -1 : batch_index,
+                                   B, users, items, rates, stream)))
     return rc;
+  // stream-ordered after the assemble kernel has read it: the next assemble-ahead draws the following batch
+  if (batch_index <= -2 && (rc = advance_prefetch_cursor(opt, (cudaStream_t)stream, batch_index == -3))) return rc;
   return tfr_dedup_sort_pairs_tl(users, (int64_t)t->user_num + 1, ws.su_ids, ws.su_pos, items,
                                  (int64_t)t->item_num + 1, ws.si_ids, ws.si_pos, B, ws.sort_ws, ws.sort_ws_bytes, opt,
                                  stream);
@@ -310,44 +332,86 @@ extern "C" int tfr_svd_prefetch_batch(const tfr_svd_tables* t, tfr_opt_scalars* 
 
 // ---- host side of the feed boundary ----------------------------------------------------------------------------
 namespace {
+// returns the number of values outside [0, bound) (bound <= 0: unchecked), judged on the SOURCE value so that an id
+// that does not fit int32 cannot alias a valid one after the cast
 template <typename Out, typename In>
-void pack_col(const char* src, int64_t stride, int64_t n, Out* dst) {
+int64_t pack_col(const char* src, int64_t stride, int64_t n, Out* dst, int64_t bound) {
   // a 65536-row batch is ~1.5 MB of float64 in, 0.75 MB out: split over a few host threads (memory-bound)
   const int nt = n >= 16384 ? 4 : 1;
-#pragma omp parallel for num_threads(nt) schedule(static)
+  int64_t bad = 0;
+#pragma omp parallel for num_threads(nt) schedule(static) reduction(+ : bad)
   for (int64_t c = 0; c < nt; ++c) {
     const int64_t k0 = n * c / nt, k1 = n * (c + 1) / nt;
+    const In lo = (In)0, hi = (In)bound;
     if (stride == (int64_t)sizeof(In)) {
       const In* p = reinterpret_cast<const In*>(src);
-      for (int64_t k = k0; k < k1; ++k) dst[k] = (Out)p[k];  // contiguous: vectorised by the host compiler
+      if (bound > 0) {
+        for (int64_t k = k0; k < k1; ++k) { const In x = p[k]; bad += !(x >= lo && x < hi); dst[k] = (Out)x; }
+      } else {
+        for (int64_t k = k0; k < k1; ++k) dst[k] = (Out)p[k];  // contiguous: vectorised by the host compiler
+      }
     } else {
-      for (int64_t k = k0; k < k1; ++k) dst[k] = (Out) * reinterpret_cast<const In*>(src + k * stride);
+      for (int64_t k = k0; k < k1; ++k) {
+        const In x = *reinterpret_cast<const In*>(src + k * stride);
+        if (bound > 0) bad += !(x >= lo && x < hi);
+        dst[k] = (Out)x;
+      }
     }
   }
+  return bad;
 }
 template <typename Out>
-int pack_any(const void* src, int dtype, int64_t stride, int64_t n, Out* dst) {
+int64_t pack_any(const void* src, int dtype, int64_t stride, int64_t n, Out* dst, int64_t bound = 0) {
   const char* p = static_cast<const char*>(src);
   switch (dtype) {
-    case 0: pack_col<Out, double>(p, stride, n, dst); return 0;
-    case 1: pack_col<Out, float>(p, stride, n, dst); return 0;
-    case 2: pack_col<Out, int32_t>(p, stride, n, dst); return 0;
-    case 3: pack_col<Out, int64_t>(p, stride, n, dst); return 0;
+    case 0: return pack_col<Out, double>(p, stride, n, dst, bound);
+    case 1: return pack_col<Out, float>(p, stride, n, dst, bound);
+    case 2: return pack_col<Out, int32_t>(p, stride, n, dst, bound);
+    case 3: return pack_col<Out, int64_t>(p, stride, n, dst, bound);
   }
   return -1;
 }
 }  // namespace
 
+extern "C" int tfr_host_pack_feed_checked(const void* users_host, int32_t users_dtype, int64_t users_stride,
+                                          const void* items_host, int32_t items_dtype, int64_t items_stride,
+                                          const void* rates_host, int32_t rates_dtype, int64_t rates_stride, int64_t n,
+                                          void* staging_host, int64_t user_num, int64_t item_num) {
+  TFR_CHECK_ARG(n >= 0 && staging_host && (n == 0 || (users_host && items_host && rates_host)));
+  TFR_CHECK_ARG(users_dtype >= 0 && users_dtype <= 3 && items_dtype >= 0 && items_dtype <= 3 && rates_dtype >= 0 &&
+                rates_dtype <= 3);
+  TFR_CHECK_ARG(user_num < ((int64_t)1 << 31) && item_num < ((int64_t)1 << 31));
+  int32_t* ids = static_cast<int32_t*>(staging_host);
+  float* rates = reinterpret_cast<float*>(ids + 2 * n);
+  const int64_t bad_u = pack_any<int32_t>(users_host, users_dtype, users_stride, n, ids, user_num);
+  const int64_t bad_i = pack_any<int32_t>(items_host, items_dtype, items_stride, n, ids + n, item_num);
+  pack_any<float>(rates_host, rates_dtype, rates_stride, n, rates);
+  if (bad_u || bad_i) {
+    set_error("indices out of range: %lld user ids outside [0, %lld), %lld item ids outside [0, %lld)", (long long)bad_u,
+              (long long)user_num, (long long)bad_i, (long long)item_num);
+    return TFR_ERR_INVALID;
+  }
+  return TFR_OK;
+}
+
 extern "C" int tfr_host_pack_feed(const void* users_host, int32_t users_dtype, int64_t users_stride,
                                   const void* items_host, int32_t items_dtype, int64_t items_stride,
                                   const void* rates_host, int32_t rates_dtype, int64_t rates_stride, int64_t n,
                                   void* staging_host) {
-  TFR_CHECK_ARG(n >= 0 && staging_host && (n == 0 || (users_host && items_host && rates_host)));
-  int32_t* ids = static_cast<int32_t*>(staging_host);
-  float* rates = reinterpret_cast<float*>(ids + 2 * n);
-  TFR_CHECK_ARG(pack_any<int32_t>(users_host, users_dtype, users_stride, n, ids) == 0);
-  TFR_CHECK_ARG(pack_any<int32_t>(items_host, items_dtype, items_stride, n, ids + n) == 0);
-  TFR_CHECK_ARG(pack_any<float>(rates_host, rates_dtype, rates_stride, n, rates) == 0);
+  return tfr_host_pack_feed_checked(users_host, users_dtype, users_stride, items_host, items_dtype, items_stride,
+                                    rates_host, rates_dtype, rates_stride, n, staging_host, 0, 0);
+}
+
+extern "C" int tfr_event_create(void** event_out) {
+  TFR_CHECK_ARG(event_out);
+  cudaEvent_t ev = nullptr;
+  TFR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  *event_out = (void*)ev;
+  return TFR_OK;
+}
+
+extern "C" int tfr_event_destroy(void* event) {
+  if (event) TFR_CUDA(cudaEventDestroy((cudaEvent_t)event));
   return TFR_OK;
 }
 

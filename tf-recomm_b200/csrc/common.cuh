@@ -24,6 +24,8 @@ enum TuneKey {
   TUNE_STREAM_CTAS_PER_SM, TUNE_STREAM_UNROLL, TUNE_STREAM_THREADS,
   TUNE_PASS_RING,         // 1: interleaved tables take the TMA-bulk ring pass (adam_ring.cu), 0: the LDG pass
   TUNE_RING_STAGES, TUNE_RING_STAGE_KB, TUNE_RING_THREADS, TUNE_RING_L2_HINT, TUNE_RING_CTAS_PER_SM,
+  TUNE_RING_SLOT_MODE,
+  TUNE_PDL,               // 1: programmatic dependent launch along the step's critical path (see pdl_wait)
   TUNE_COUNT
 };
 int tune(TuneKey k);
@@ -31,6 +33,10 @@ int tune(TuneKey k);
 // whose carve-outs differ, so without this the persistent streaming pass (no shared memory -> "max L1")
 // keeps the forward / sort / segment-sum kernels (which use shared memory) off every SM until it drains.
 void prep_kernel(const void* fn);
+// same, for a kernel whose resident CTAs need `smem_per_sm` bytes of shared memory per SM: the common carve-out if
+// that is enough, else the smallest percentage that is (a preferred carve-out is a ceiling for occupancy: the driver
+// only guarantees that ONE CTA fits)
+void prep_kernel_carveout(const void* fn, size_t smem_per_sm);
 #define TFR_PREP(kernel) tfr::prep_kernel(reinterpret_cast<const void*>(kernel))
 
 #define TFR_CHECK_ARG(cond)                                                        \
@@ -51,6 +57,36 @@ void prep_kernel(const void* fn);
   } while (0)
 
 #define TFR_LAUNCH_CHECK() TFR_CUDA(cudaGetLastError())
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------
+// The kernels of the step's critical path (segment sums -> fix-up -> table pass -> next step's segment sums) are
+// launched with programmaticStreamSerializationAllowed: a kernel's CTAs become resident while its predecessor drains
+// and block at pdl_wait() until the predecessor grid has completed and flushed -- the launch latency between two
+// kernels disappears from the critical path.  Every kernel calls pdl_wait() BEFORE pdl_launch_dependents(), so a
+// kernel can only start once its predecessor's predecessor is complete (dependencies stay transitive).  Both are
+// no-ops in a kernel that was launched the plain way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 // ---- explicit-rounding fp32 arithmetic: every TensorFlow op is its own rounding, never an FMA ----
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }

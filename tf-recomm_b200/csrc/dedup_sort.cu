@@ -15,8 +15,9 @@
 
 namespace tfr {
 
-// Grid-wide barrier of a grid whose CTAs all become resident (<= 128 CTAs of 512 threads on 148 SMs, and no
-// kernel that can run beside this one waits on it).  A plain launch + this barrier instead of a cooperative
+// Grid-wide barrier of a grid whose CTAs all become resident (the grid is sized against the device's resident
+// capacity at launch, sort_resident_capacity: <= 128 CTAs of 256 threads on 148 SMs; and no kernel that can run beside
+// this one waits on it).  A plain launch + this barrier instead of a cooperative
 // launch: the driver gang-schedules cooperative grids only onto an otherwise idle GPU, which kept the next
 // batch's sort from running under the current step's table pass (measured with tools/timeline.py).
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
@@ -221,10 +222,28 @@ static int bits_for(int64_t max_id) {
 
 using namespace tfr;
 
-static int sort_bpp(int64_t n) {
+// How many CTAs of the sort can be resident on the current device at once (cached per device).  The kernel's grid
+// barrier needs EVERY CTA of the grid to become resident: the grid is sized against this, so a device with fewer SMs
+// (or a build that uses more shared memory) shrinks the grid instead of hanging.  CTAs that have to wait for a
+// neighbour kernel (the table pass) to leave room are fine: nothing that runs beside the sort waits on it.
+static int sort_resident_capacity() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (cached[dev] > 0) return cached[dev];
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dedup_sort_kernel, SORT_THREADS, 0) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  // one CTA per SM at most: beside a persistent neighbour only that much room is certain
+  cached[dev] = per_sm > 0 ? sms : 0;
+  return cached[dev];
+}
+
+static int sort_bpp(int64_t n, int capacity) {
   int64_t bpp = (n + 1023) / 1024;
   if (bpp < 1) bpp = 1;
   if (bpp > SORT_MAX_BPP) bpp = SORT_MAX_BPP;
+  if (bpp > capacity / 2) bpp = capacity / 2;
   return (int)bpp;
 }
 
@@ -266,7 +285,12 @@ extern "C" int tfr_dedup_sort_pairs_tl(const int32_t* ids_a, int64_t max_id_a, i
   if (ids_b && bits_for(max_id_b) > bits) bits = bits_for(max_id_b);
   int n_passes = (bits + RADIX_BITS_MAX - 1) / RADIX_BITS_MAX;
   int digit_bits = (bits + n_passes - 1) / n_passes;
-  int bpp = sort_bpp(n);
+  const int capacity = sort_resident_capacity();
+  if (capacity < 2) {
+    set_error("id sort: the device cannot hold the sort's grid (occupancy query failed or < 2 resident CTAs)");
+    return TFR_ERR_CUDA;
+  }
+  int bpp = sort_bpp(n, capacity);
   // the whole 256-byte header: the grid barrier and the fix-up work-list counters the segment sums keep at +64
   TFR_CUDA(cudaMemsetAsync(barrier, 0, 256, (cudaStream_t)stream));
   TFR_PREP(dedup_sort_kernel);

@@ -182,6 +182,8 @@ __global__ void __launch_bounds__(SEG_THREADS) segsum_tiles_kernel(SegSide su, S
                                                                    const tfr_opt_scalars* __restrict__ opt,
                                                                    const float* __restrict__ err, int64_t B, int dim,
                                                                    int n_tiles, int tile) {
+  pdl_wait();                // the previous step's table pass (tables, step scalars) is complete
+  pdl_launch_dependents();   // the fix-up's CTAs may become resident as this grid drains
   TlScope tl_scope(opt, TFR_TL_TILES);
   constexpr int P = seg_sub(UNITS, L);
   constexpr int SH = ilog2(L) - ilog2(P);  // lane l ends up with the dot of entry l >> SH of the sub-batch
@@ -477,7 +479,10 @@ constexpr int FIX_LONG_CAP = 32;   // long chains a CTA can park (more: the warp
 template <int VEC>
 __global__ void __launch_bounds__(FIX_THREADS, 3) segsum_fixup_kernel(SegSide su, SegSide si, const tfr_opt_scalars* __restrict__ opt,
                                                                    uint32_t* counters, int64_t B, int dim, int n_tiles,
-                                                                   int tile, int cw) {
+                                                                   int tile, int cw, float* fold_err, double* fold_se,
+                                                                   int fold_n) {
+  pdl_wait();                // the tiles kernel's partial rows and work lists are complete
+  pdl_launch_dependents();   // the table pass's CTAs may become resident as this grid drains
   TlScope tl_scope(opt, TFR_TL_FIXUP, true);
   extern __shared__ float s_part[];  // [G][dim] (+ [G] bias partials)
   __shared__ int s_long[FIX_LONG_CAP][2];
@@ -489,6 +494,20 @@ __global__ void __launch_bounds__(FIX_THREADS, 3) segsum_fixup_kernel(SegSide su
   const uint32_t n_fix = min(*s.fix_count, (uint32_t)n_tiles);
   if (threadIdx.x == 0) s_nlong = 0;
   __syncthreads();
+  // One warp folds the fused forward's per-CTA partial sums (complete: the tiles kernel wrote them) into
+  // [TFR_MAX_PARTIALS] -- in the order and with the adds of finish_step_scalars -- BESIDE the chains, so that the
+  // step's end (the table pass's last CTA) reads one value instead of hundreds behind its tail.
+  if (fold_n > 0 && blockIdx.y == 0 && blockIdx.x == gridDim.x - 1 && warp == FIX_THREADS / 32 - 1) {
+    float a = 0.0f;
+    double se = 0.0;
+    for (int j = lane; j < fold_n; j += 32) { a = add_rn(a, fold_err[j]); se += fold_se[j]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a = add_rn(a, __shfl_xor_sync(0xffffffffu, a, o));
+      se += __shfl_xor_sync(0xffffffffu, se, o);
+    }
+    if (lane == 0) { fold_err[TFR_MAX_PARTIALS] = a; fold_se[TFR_MAX_PARTIALS] = se; }
+  }
 
   // t1 = first tile after t0 that is not TILE_MID; head = sorted index of the run's first entry (ids are sorted:
   // the run is the suffix of tile t0)
@@ -713,13 +732,14 @@ static int launch_segsum(const SegSide& su, const SegSide& si, int n_sides, cons
   dim3 fix_grid((unsigned)min((n_tiles + fix_warps - 1) / fix_warps, 3 * sm_count() / n_sides), (unsigned)n_sides);
   dim3 grid((unsigned)segsum_grid_x(dim, B), (unsigned)n_sides);
   const FwdArgs none{};
+  const bool pdl = tune(TUNE_PDL) != 0;
   const size_t smem = seg_smem_bytes(dim, g.lanes, units, g.vec);
   const bool generic = generic_flags || su.xval != nullptr;
 #define TFR_SEG_LAUNCH(V, LL, UU, FU, GE)                                                                          \
   {                                                                                                                \
     if (int rc = prep_tiles((const void*)segsum_tiles_kernel<V, LL, UU, FU, GE>, smem)) return rc;                 \
-    segsum_tiles_kernel<V, LL, UU, FU, GE><<<grid, SEG_THREADS, smem, st>>>(su, si, fw ? *fw : none, opt, err, B, dim, \
-                                                                            n_tiles, tile);                        \
+    TFR_CUDA(launch_kernel(segsum_tiles_kernel<V, LL, UU, FU, GE>, grid, dim3(SEG_THREADS), smem, st, pdl, su, si,   \
+                           fw ? *fw : none, opt, err, B, dim, n_tiles, tile));                                     \
   }
 #define TFR_SEG_CASE(V, LL, UU)                                                                                   \
   if (g.vec == V && g.lanes == LL && units == UU) {                                                               \
@@ -729,8 +749,9 @@ static int launch_segsum(const SegSide& su, const SegSide& si, int n_sides, cons
     else if (generic) TFR_SEG_LAUNCH(V, LL, UU, false, true)                                                       \
     else TFR_SEG_LAUNCH(V, LL, UU, false, false)                                                                   \
     TFR_LAUNCH_CHECK();                                                                                            \
-    segsum_fixup_kernel<V><<<fix_grid, FIX_THREADS, fix_smem, st>>>(su, si, opt, counters, B, dim, n_tiles, tile, cw);    \
-    TFR_LAUNCH_CHECK();                                                                                            \
+    TFR_CUDA(launch_kernel(segsum_fixup_kernel<V>, fix_grid, dim3(FIX_THREADS), fix_smem, st, pdl, su, si, opt, counters, \
+                           B, dim, n_tiles, tile, cw, fw ? fw->partials : nullptr, fw ? fw->se_partials : nullptr,  \
+                           fw ? (int)grid.x : 0));                                                                  \
     return TFR_OK;                                                                                                 \
   }
   // default geometry (<= 4 units per lane): L = 1 for rows of up to 4 units, then UNITS = 4

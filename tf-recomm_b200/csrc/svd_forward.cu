@@ -168,9 +168,9 @@ __global__ void __launch_bounds__(256) batch_assemble_kernel(tfr_svd_tables t, t
                                                              int64_t B, int32_t* __restrict__ users,
                                                              int32_t* __restrict__ items, float* __restrict__ rates) {
   TlScope tl_scope(opt, TFR_TL_ASSEMBLE);
-  // batch_index >= 0: that batch; batch_index = -1-k: batch (opt->batch_cursor + k), k = 0 for "this step's",
-  // k = 1 when the NEXT step's batch is assembled ahead, under the current step's table pass
-  const int64_t batch = batch_index >= 0 ? batch_index : opt->batch_cursor + (-1 - batch_index);
+  // batch_index >= 0: that batch; -1: the batch at batch_cursor (this step's, on the step's stream); -2: the batch at
+  // prefetch_cursor (assembled ahead on a side stream: a counter the concurrent step never writes)
+  const int64_t batch = batch_index >= 0 ? batch_index : (batch_index == -1 ? opt->batch_cursor : opt->prefetch_cursor);
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) {
     const int64_t row = row_index[batch * B + b];
@@ -178,6 +178,18 @@ __global__ void __launch_bounds__(256) batch_assemble_kernel(tfr_svd_tables t, t
     items[b] = col_item[row];
     rates[b] = col_rate[row];
   }
+}
+
+__global__ void advance_prefetch_cursor_kernel(tfr_opt_scalars* opt) { opt->prefetch_cursor += 1; }
+__global__ void set_cursor_kernel(tfr_opt_scalars* opt, int64_t k) { opt->batch_cursor = k; opt->prefetch_cursor = k; }
+
+__global__ void prime_prefetch_cursor_kernel(tfr_opt_scalars* opt) { opt->prefetch_cursor = opt->batch_cursor + 1; }
+
+int advance_prefetch_cursor(tfr_opt_scalars* opt, cudaStream_t st, bool prime) {
+  if (prime) prime_prefetch_cursor_kernel<<<1, 1, 0, st>>>(opt);
+  else advance_prefetch_cursor_kernel<<<1, 1, 0, st>>>(opt);
+  TFR_LAUNCH_CHECK();
+  return TFR_OK;
 }
 
 template <bool TRAIN>
@@ -241,9 +253,17 @@ extern "C" int tfr_svd_batch_assemble(const tfr_svd_tables* t, tfr_opt_scalars* 
                                       int64_t batch_index, int64_t B, int32_t* users, int32_t* items, float* rates,
                                       void* stream) {
   TFR_CHECK_ARG(t && opt && B > 0 && users && items && rates && col_user && col_item && col_rate && row_index);
+  TFR_CHECK_ARG(batch_index >= -2);
   TFR_PREP(batch_assemble_kernel);
   batch_assemble_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       *t, opt, col_user, col_item, col_rate, row_index, batch_index, B, users, items, rates);
+  TFR_LAUNCH_CHECK();
+  return TFR_OK;
+}
+
+extern "C" int tfr_opt_set_cursor(tfr_opt_scalars* opt_dev, int64_t k, void* stream) {
+  TFR_CHECK_ARG(opt_dev && k >= 0);
+  set_cursor_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(opt_dev, k);
   TFR_LAUNCH_CHECK();
   return TFR_OK;
 }

@@ -89,12 +89,20 @@ class SvdEngine:
             # side stream for the id sort (runs next to the forward): see tfr_svd_train_step
             self.side_streams = [torch.cuda.Stream(device=dev)]
             self._side_arr = (C.c_void_p * 1)(*[s_.cuda_stream for s_ in self.side_streams])
+            # fork / join events of the step's side-stream fork: owned by this engine, on this engine's device
+            self._fj_events = (C.c_void_p * 2)()
+            for k_ in range(2):
+                ev = C.c_void_p()
+                check(self.L.tfr_event_create(C.byref(ev)))
+                self._fj_events[k_] = ev.value
             self._fill_struct()
             check(self.L.tfr_opt_init(self.opt.data_ptr(), lr, reg, beta1, beta2, eps, self.flags, self.var_mask,
                                       self._stream()))
         self._ws = {}
         self._stage = {}
         self._graphs = {}
+        self._host_state = {}
+        self._copy_stream = torch.cuda.Stream(device=self.device)
         self.data = None
         self.se_ring = None
         self.overlap = True
@@ -138,6 +146,22 @@ class SvdEngine:
         check(self.L.tfr_svd_step_carve(ws.data_ptr(), ws.numel(), B, self.d, C.byref(out)))
         return out
 
+    def _check_ids(self, users, items):
+        """ids outside the tables are an error where they enter (TF's CPU embedding_lookup raises
+        InvalidArgumentError): nothing out of range ever reaches a gather."""
+        for name, a, n in (("user", users, self.U), ("item", items, self.I)):
+            if isinstance(a, torch.Tensor):
+                if a.numel() == 0:
+                    continue
+                lo, hi = (int(x) for x in torch.aminmax(a))
+            else:
+                a = np.asarray(a)
+                if a.size == 0:
+                    continue
+                lo, hi = a.min(), a.max()
+            if lo < 0 or hi >= n:
+                raise TfrError("indices out of range: %s ids span [%s, %s], table has %d rows" % (name, lo, hi, n))
+
     def _dev_i32(self, a):
         if isinstance(a, torch.Tensor):
             return a.to(device=self.device, dtype=torch.int32).contiguous()
@@ -151,6 +175,7 @@ class SvdEngine:
 
     # ---- forward only: sess.run([logits, infer]) at svd_train_val.py:121-122 --------------------------------
     def forward(self, users, items):
+        self._check_ids(users, items)
         users, items = self._dev_i32(users), self._dev_i32(items)
         B = users.numel()
         logits = torch.empty(B, dtype=torch.float32, device=self.device)
@@ -201,7 +226,9 @@ class SvdEngine:
         return idx, vals
 
     # ---- one train step on a device-resident batch: sess.run([train_op, logits, infer]), :70-72 -------------
-    def train_step(self, users, items, rates, logits=None, infer=None):
+    def train_step(self, users, items, rates, logits=None, infer=None, check_ids=True):
+        if check_ids:
+            self._check_ids(users, items)
         users, items, rates = self._dev_i32(users), self._dev_i32(items), self._dev_f32(rates)
         B = users.numel()
         if logits is None:
@@ -214,7 +241,7 @@ class SvdEngine:
             check(self.L.tfr_svd_train_step(C.byref(self.tables_struct), self.opt.data_ptr(), users.data_ptr(),
                                             items.data_ptr(), rates.data_ptr(), B, logits.data_ptr(),
                                             infer.data_ptr(), self.flags, self.var_mask, ws.data_ptr(), ws.numel(),
-                                            st, self._side_arr, self._n_side()))
+                                            st, self._side_arr, self._n_side(), self._fj_events))
         return logits, infer
 
     # ---- host-fed step (the feed_dict path): pinned staging, H2D, step, D2H of the fetched predictions -------
@@ -228,43 +255,101 @@ class SvdEngine:
             a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
         return a, a.ctypes.data, self._FEED_DTYPES[a.dtype], (a.strides[0] if a.size else a.itemsize)
 
-    def train_step_host(self, users, items, rates, fetch=True):
+    # The feed path is a two-set pipeline.  prefetch_host(batch) packs the columns into one pinned staging buffer (value
+    # cast + range check in C), copies it to the device and sorts its ids on the SIDE stream -- all of which needs no
+    # table data, so it runs under the previous step's table pass.  train_step_host(batch) then issues forward +
+    # segment sums, copies the predictions (they come from the PRE-update tables) back on a copy stream
+    # while the Adam pass runs, and returns as soon as the predictions are on the host.  A driver that owns its
+    # iterator (svd_train_val.py) hands over batch t+1 right after step t returns; a plain sess.run(feed_dict) without
+    # a prefetch does the same work in line.  Every reuse of a staging buffer is ordered by an event: the pinned
+    # buffer is never repacked while a copy from it is queued (also with fetch=False, which does not synchronise).
+    def _host_set(self, B, k):
+        key = ("host", B, k)
+        st = self._stage.get(key)
+        if st is None:
+            ws = self.workspace((B, "h", k))
+            carved = StepWs()
+            check(self.L.tfr_svd_step_carve(ws.data_ptr(), ws.numel(), B, self.d, C.byref(carved)))
+            st = dict(h_feed=torch.empty(3 * B, dtype=torch.int32).pin_memory(),
+                      d_feed=torch.empty(3 * B, dtype=torch.int32, device=self.device),
+                      d_out=torch.empty(2 * B, dtype=torch.float32, device=self.device),
+                      h_out=torch.empty(2 * B, dtype=torch.float32).pin_memory(),
+                      ws=ws, carved=carved, used=False, copied=False,
+                      ev_h2d=torch.cuda.Event(), ev_sorted=torch.cuda.Event(), ev_pred=torch.cuda.Event(),
+                      ev_d2h=torch.cuda.Event(), ev_done=torch.cuda.Event())
+            self._stage[key] = st
+        return st
+
+    def prefetch_host(self, users, items, rates):
+        """Hands over the NEXT batch early: pack -> H2D -> id sort on the side stream, under whatever the main stream
+        is doing (normally the previous step's table pass).  The following train_step_host must get these very
+        arrays; a different batch simply drops the prefetched one."""
         B = len(users)
-        stg = self._stage.get(B)
-        if stg is None:
-            # one pinned staging buffer [users int32 | items int32 | rates float32] -> ONE H2D copy per step
-            stg = dict(h_feed=torch.empty(3 * B, dtype=torch.int32).pin_memory(),
-                       d_feed=torch.empty(3 * B, dtype=torch.int32, device=self.device),
-                       d_out=torch.empty(2 * B, dtype=torch.float32, device=self.device),
-                       h_out=torch.empty(2 * B, dtype=torch.float32).pin_memory())
-            self._stage[B] = stg
+        hs = self._host_state.setdefault(B, dict(next=0, pending=None))
+        k = hs["pending"][0] if hs["pending"] is not None else hs["next"]
+        st = self._host_set(B, k)
         ku, pu, du, su = self._feed_col(users)
         ki, pi, di, si = self._feed_col(items)
         kr, pr, dr, sr = self._feed_col(rates)
-        # value cast float64 -> int32, like TF feeding an int32 placeholder (A.7), straight into the pinned buffer
-        check(self.L.tfr_host_pack_feed(pu, du, su, pi, di, si, pr, dr, sr, B, stg["h_feed"].data_ptr()))
-        d_ids = stg["d_feed"][:2 * B]
-        d_rates = stg["d_feed"][2 * B:].view(torch.float32)
-
-        def body():
-            stg["d_feed"].copy_(stg["h_feed"], non_blocking=True)
-            self.train_step(d_ids[:B], d_ids[B:], d_rates, logits=stg["d_out"][:B], infer=stg["d_out"][B:])
-            stg["h_out"].copy_(stg["d_out"], non_blocking=True)
+        if st["used"]:
+            st["ev_h2d"].synchronize()   # the previous copy out of this pinned buffer has completed
+        # value cast float64 -> int32, like TF feeding an int32 placeholder (A.7), straight into the pinned buffer;
+        # ids outside the tables are an error here, before anything is launched (TF's lookup raises as well)
+        check(self.L.tfr_host_pack_feed_checked(pu, du, su, pi, di, si, pr, dr, sr, B, st["h_feed"].data_ptr(),
+                                                self.U, self.I))
+        side = self.side_streams[0]
         with torch.cuda.device(self.device):
-            if getattr(self, "host_step_graph", True):
-                # H2D of the batch, the step and the D2H of the fetched predictions as ONE captured graph (the staging
-                # buffers are persistent, so their addresses can be baked in): one launch + one sync per sess.run
-                g = self._graphs.get((B, "host"))
-                if g is None:
-                    self.workspace(B)
-                    g = self._graphs[(B, "host")] = self._capture(body)
-                check(self.L.tfr_graph_launch(g, self._stream()))
-            else:
-                body()
+            if st["used"]:
+                side.wait_event(st["ev_done"])   # the step that last used this set's device buffers has finished
+            with torch.cuda.stream(side):
+                st["d_feed"].copy_(st["h_feed"], non_blocking=True)
+                st["ev_h2d"].record(side)
+                w = st["carved"]
+                d = st["d_feed"]
+                check(self.L.tfr_dedup_sort_pairs_tl(d.data_ptr(), self.U + 1, w.su_ids, w.su_pos, d.data_ptr() + 4 * B,
+                                                     self.I + 1, w.si_ids, w.si_pos, B, w.sort_ws, w.sort_ws_bytes,
+                                                     self.opt.data_ptr(), side.cuda_stream))
+                st["ev_sorted"].record(side)
+        st["used"] = True
+        hs["pending"] = (k, users, items, rates)
+
+    def train_step_host(self, users, items, rates, fetch=True):
+        B = len(users)
+        hs = self._host_state.setdefault(B, dict(next=0, pending=None))
+        pend = hs["pending"]
+        if pend is None or pend[1] is not users or pend[2] is not items or pend[3] is not rates:
+            self.prefetch_host(users, items, rates)
+            pend = hs["pending"]
+        k = pend[0]
+        hs["pending"], hs["next"] = None, 1 - k
+        st = self._host_set(B, k)
+        d = st["d_feed"]
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(st["ev_sorted"])
+            if st["copied"]:
+                main.wait_event(st["ev_d2h"])   # d_out is about to be overwritten: its last copy out must be done
+
+            def phase(p):
+                check(self.L.tfr_svd_train_step_presorted(C.byref(self.tables_struct), self.opt.data_ptr(), d.data_ptr(),
+                                                          d.data_ptr() + 4 * B, d.data_ptr() + 8 * B, B,
+                                                          st["d_out"].data_ptr(), st["d_out"].data_ptr() + 4 * B,
+                                                          self.flags, self.var_mask, p, st["ws"].data_ptr(),
+                                                          st["ws"].numel(), main.cuda_stream))
+            phase(1)
+            if fetch:
+                st["ev_pred"].record(main)
+                self._copy_stream.wait_event(st["ev_pred"])
+                with torch.cuda.stream(self._copy_stream):
+                    st["h_out"].copy_(st["d_out"], non_blocking=True)
+                    st["ev_d2h"].record(self._copy_stream)
+                st["copied"] = True
+            phase(2)
+            st["ev_done"].record(main)
         if not fetch:
             return None
-        torch.cuda.current_stream(self.device).synchronize()
-        out = stg["h_out"].numpy().copy()   # one copy out of the pinned buffer; the two results are views of it
+        st["ev_d2h"].synchronize()
+        out = st["h_out"].numpy().copy()   # one copy out of the pinned buffer; the two results are views of it
         return out[:B], out[B:]
 
     h2d_bytes = staticmethod(lambda B: 12 * B)
@@ -272,7 +357,32 @@ class SvdEngine:
 
     # ---- device-resident training data + pre-drawn index stream (dataio.ShuffleIterator on the device) ------
     def set_train_data(self, col_user, col_item, col_rate):
+        self._check_ids(col_user, col_item)   # once, where the columns enter: the assembled batches are then in range
+        # captured stream graphs bake the column addresses in: drop them (and whatever was assembled ahead)
+        self._destroy_graphs()
+        self._primed = None
         self.data = dict(user=self._dev_i32(col_user), item=self._dev_i32(col_item), rate=self._dev_f32(col_rate))
+
+    def _destroy_graphs(self):
+        for g in self._graphs.values():
+            self.L.tfr_graph_destroy(g)
+        self._graphs.clear()
+
+    def close(self):
+        """Releases the captured graphs (device memory goes with the tensors)."""
+        if getattr(self, "_graphs", None):
+            torch.cuda.synchronize(self.device)
+            self._destroy_graphs()
+        for k_ in range(2):
+            if getattr(self, "_fj_events", None) is not None and self._fj_events[k_]:
+                self.L.tfr_event_destroy(self._fj_events[k_])
+                self._fj_events[k_] = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def set_index_stream(self, row_index, B):
         """row_index: the reference's np.random.randint(0, N, B) draws for consecutive steps, concatenated."""
@@ -286,7 +396,7 @@ class SvdEngine:
         cap = getattr(self, "_row_index_buf", None)
         if cap is None or cap.numel() < ri.numel() + B:
             self._row_index_buf = torch.zeros(ri.numel() + B, dtype=torch.int64, device=self.device)
-            self._graphs.clear()
+            self._destroy_graphs()
         self._row_index_buf[:ri.numel()].copy_(ri)
         self._row_index_buf[ri.numel():].zero_()
         self._primed = None
@@ -296,8 +406,8 @@ class SvdEngine:
 
     def set_batch_cursor(self, k):
         self._primed = None
-        off = OptScalars.batch_cursor.offset
-        self.opt[off:off + 8].copy_(torch.tensor([k], dtype=torch.int64).view(torch.uint8))
+        with torch.cuda.device(self.device):
+            check(self.L.tfr_opt_set_cursor(self.opt.data_ptr(), int(k), self._stream()))
 
     def set_se_ring(self, n):
         self.se_ring = torch.zeros(n, dtype=torch.float64, device=self.device)
@@ -335,14 +445,19 @@ class SvdEngine:
         check(self.L.tfr_svd_train_step(C.byref(self.tables_struct), self.opt.data_ptr(), bufs["users"].data_ptr(),
                                         bufs["items"].data_ptr(), bufs["rates"].data_ptr(), B,
                                         bufs["logits"].data_ptr(), bufs["infer"].data_ptr(), self.flags,
-                                        self.var_mask, ws.data_ptr(), ws.numel(), st, self._side_arr, self._n_side()))
+                                        self.var_mask, ws.data_ptr(), ws.numel(), st, self._side_arr, self._n_side(),
+                                        self._fj_events))
 
-    def _prefetch(self, B, slot, k_ahead, stream_handle):
-        """Batch (cursor + k_ahead): assemble + id sort into buffer set `slot` (tfr_svd_prefetch_batch)."""
+    def _prefetch(self, B, slot, prime, stream_handle):
+        """Assemble + id sort of a batch into buffer set `slot` (tfr_svd_prefetch_batch).  prime: the batch at
+        batch_cursor, on the step's own stream, and prefetch_cursor := batch_cursor + 1; otherwise the batch at
+        prefetch_cursor (a counter only the side stream advances: the concurrent step's last CTA advances
+        batch_cursor, which must therefore not be read here)."""
         bufs, ws = self.stream_buffers(B, slot), self.workspace((B, slot))
         check(self.L.tfr_svd_prefetch_batch(C.byref(self.tables_struct), self.opt.data_ptr(),
                                             self.data["user"].data_ptr(), self.data["item"].data_ptr(),
-                                            self.data["rate"].data_ptr(), self.row_index.data_ptr(), -1 - k_ahead, B,
+                                            self.data["rate"].data_ptr(), self.row_index.data_ptr(),
+                                            -3 if prime else -2, B,
                                             bufs["users"].data_ptr(), bufs["items"].data_ptr(),
                                             bufs["rates"].data_ptr(), ws.data_ptr(), ws.numel(), stream_handle))
 
@@ -368,11 +483,11 @@ class SvdEngine:
             small = bool(self.prefetch_at_start)
         if small:
             side.wait_stream(main)
-            self._prefetch(B, 1 - slot, 1, side.cuda_stream)
+            self._prefetch(B, 1 - slot, False, side.cuda_stream)
         phase(1)                      # forward + segment sums
         if not small:
             side.wait_stream(main)
-            self._prefetch(B, 1 - slot, 1, side.cuda_stream)
+            self._prefetch(B, 1 - slot, False, side.cuda_stream)
         hook = getattr(self, "timing_hook", None)   # bench.py: event-record nodes around the table pass, in situ
         if hook:
             hook("pass_begin", slot, main)
@@ -465,7 +580,7 @@ class SvdEngine:
         if slot is None:  # nothing assembled ahead for the batch at the cursor: prime set 0
             slot = 0
             if launch:
-                self._prefetch(B, 0, 0, self._stream())
+                self._prefetch(B, 0, True, self._stream())
         # graphs of `self.graph_steps` consecutive steps: one launch per graph_steps steps instead of one per step --
         # the gap between two graph launches is paid once per graph.  The remainder runs as single-step graphs.
         K = max(2, int(getattr(self, "graph_steps", 8)) // 2 * 2)

@@ -158,6 +158,17 @@ class Session(object):
             raise _lib.TfrError("fetch needs %s in feed_dict" % what)
         return feed[ph]
 
+    def prefetch(self, feed_dict):
+        """Not in TensorFlow's API: hands the NEXT train step's feed_dict over early, so that its host packing, H2D
+        copy and id sort run under the current step's table pass (SvdEngine.prefetch_host).  The following
+        run([train_op, ...], feed_dict) must be fed the same arrays; anything else just drops the prefetched batch."""
+        m = current_model()
+        if m.engine is None:
+            raise _lib.TfrError("variables are not initialised: run the initializer op first")
+        m.engine.prefetch_host(self._fed(feed_dict, m.user_batch, "user_batch"),
+                               self._fed(feed_dict, m.item_batch, "item_batch"),
+                               self._fed(feed_dict, m.rate_batch, "rate_batch"))
+
     def run(self, fetches, feed_dict=None):
         feed = feed_dict or {}
         single = not isinstance(fetches, (list, tuple))

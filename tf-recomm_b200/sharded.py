@@ -85,7 +85,7 @@ class ShardedSvdEngine:
         check(self.L.tfr_svd_train_step(C.byref(bufs["tables"]), e.opt.data_ptr(), bufs["key_u"].data_ptr(),
                                         bufs["key_i"].data_ptr(), rates.data_ptr(), B, bufs["logits"].data_ptr(),
                                         bufs["infer"].data_ptr(), e.flags, e.var_mask, ws.data_ptr(), ws.numel(), st,
-                                        e._side_arr, e._n_side()))
+                                        e._side_arr, e._n_side(), e._fj_events))
         return bufs["logits"], bufs["infer"]
 
     def train_step(self, users, items, rates):

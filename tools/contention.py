@@ -41,7 +41,7 @@ def main():
     side = torch.cuda.Stream(device=dev)
     opt = eng.opt.data_ptr()
     # the batch at the cursor, assembled + sorted into set 0
-    eng._prefetch(B, 0, 0, main_s.cuda_stream)
+    eng._prefetch(B, 0, True, main_s.cuda_stream)
     bufs, ws = eng.stream_buffers(B, 0), eng.workspace((B, 0))
 
     def chain():

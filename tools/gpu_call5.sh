@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2c5_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2c5_pytest.log
+cp gpurun_out/parity_stats.json gpurun_out/r2c5_parity_stats.json 2>/dev/null
+timeout 300 python tools/timeline.py ml25m_d128_b65536 > gpurun_out/r2c5_timeline.log 2>&1
+timeout 300 python tools/timeline.py ml1m_d15_b10000 >> gpurun_out/r2c5_timeline.log 2>&1
+timeout 300 python tools/e2e_breakdown.py ml25m_d128_b65536 > gpurun_out/r2c5_e2e.log 2>&1
+timeout 300 python tools/e2e_breakdown.py ml1m_d15_b10000 >> gpurun_out/r2c5_e2e.log 2>&1
+timeout 600 python bench.py --steps 200 --warmup 5 --cpu-steps 2 > gpurun_out/r2c5_bench.json 2> gpurun_out/r2c5_bench.err
+tail -5 gpurun_out/r2c5_pytest.log; cat gpurun_out/r2c5_timeline.log gpurun_out/r2c5_e2e.log; cat gpurun_out/r2c5_bench.json
