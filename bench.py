@@ -195,6 +195,10 @@ def kernel_roofline(eng, w, cols, steps, torch, peak, peak_src):
     torch.cuda.synchronize()
     eng.timing_hook = hook
     try:
+        # the steps are issued eagerly (one host call per kernel): park the device behind a spin kernel first so that
+        # the host has queued every step before the first one runs -- the events then see device time only, never a
+        # launch the host had not issued yet
+        torch.cuda._sleep(int(3e7))
         eng.run_stream_steps(max(steps, 4), use_graph=False)
     finally:
         eng.timing_hook = None
@@ -204,16 +208,19 @@ def kernel_roofline(eng, w, cols, steps, torch, peak, peak_src):
     bytes_launch = 24.0 * (U + I) * (d + 1)
     achieved = bytes_launch / (tot_ms / n / 1e3) / 1e9
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_pass_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_pass_traffic.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r01_pass_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("workload") == w.get("name", "ml25m_d128_b65536"):
-            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "committed capture, not measured in this run: " + tj["source"]
     return {"bound": "hbm", "kernel": "adam_stream_multi_kernel (TF-Adam pass over every row of all tables, one launch)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
             "bytes_per_launch": bytes_launch, "launch_ms": tot_ms / n, "launches_timed": n,
             "how": "CUDA events on the launching stream right before / after the launch, inside complete pipelined "
-                   "steps (in situ: the next batch's assemble + id sort run beside it on the side stream)",
+                   "steps (in situ: the next batch's assemble + id sort run beside it on the side stream); all steps "
+                   "are queued behind a spin kernel first, so the interval holds no host launch latency",
             "algorithmic_bytes": "24 B/param x (users+items) x (dim+1)", "traffic": traffic, "traffic_source": traffic_src}
 
 
@@ -268,8 +275,8 @@ def run_workload(name, args, torch, with_e2e=True, with_roofline=True, sample_cl
             rows = rng.integers(0, n_train, B)
             batches.append((cols[0][rows].astype(np.float64), cols[1][rows].astype(np.float64),
                             cols[2][rows].astype(np.float64)))   # float64 columns: what ShuffleIterator yields
-        # the driver's loop (svd_train_val.py): step t returns its predictions (host), batch t+1 is handed over at once --
-        # its packing, H2D copy and id sort run under step t's table pass.  Every step's H2D (12 B / rating) and D2H
+        # the driver's loop (svd_train_val.py): batch t+1 is handed over, then step t is asked for and returns its
+        # predictions (host) -- the packing, H2D copy and id sort of t+1 run under step t.  Every step's H2D (12 B / rating) and D2H
         # (8 B / rating) are inside the timed region.
         for b in batches[:3]:
             eng.train_step_host(*b)
@@ -277,9 +284,9 @@ def run_workload(name, args, torch, with_e2e=True, with_roofline=True, sample_cl
         eng.prefetch_host(*batches[3])
         t0 = time.perf_counter()
         for j in range(3, len(batches)):
-            eng.train_step_host(*batches[j])
             if j + 1 < len(batches):
-                eng.prefetch_host(*batches[j + 1])
+                eng.prefetch_host(*batches[j + 1])   # handed over before step j is asked for: overlaps it on the device
+            eng.train_step_host(*batches[j])
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         n = len(batches) - 3
@@ -388,10 +395,33 @@ def main():
                         "vs_baseline": ra["value"] / PUBLISHED_RATINGS_PER_S["ml1m_d15_b10000"],
                         "e2e": ra.get("e2e"), "note": "launch/L2-bound: 5.2 MB/step, HBM fraction not meaningful"}
         try:
+            line["also_allpairs"] = run_allpairs_workload(torch)
+        except Exception as exc:
+            line["also_allpairs"] = {"workload": "allpairs_162541x62423_d128", "error": repr(exc)}
+        try:
             line["also_fm"] = run_fm_workload(torch)
         except Exception as exc:  # the headline line must not be lost to the secondary workload
             line["also_fm"] = {"workload": "fm_ktm_d20_b10000", "error": repr(exc)}
     emit(line)
+
+
+def run_allpairs_workload(torch):
+    """BASELINE configs[3]'s second half: all-pairs scoring of the ML-25M shape (als3.py:112, 2.6 TFLOP; the 40.6 GB score
+    matrix is never written -- every consumer lives in the tcgen05 GEMM's epilogue).  ms, TFLOP/s and the fraction of
+    the tf32 tensor peak (half the measured bf16 cuBLAS peak: tf32 MMAs run at half the bf16 rate) per consumer."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import allpairs_bench
+    w = WORKLOADS["ml25m_d128_b65536"]
+    res = allpairs_bench.run(w["U"], w["I"], w["d"], simt=False, reps=4)
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    bf16 = json.load(open(p)).get("bf16_tflops") if os.path.exists(p) else 1590.0
+    tf32_peak = bf16 / 2.0
+    for v in res.values():
+        v["frac_of_tf32_peak"] = v["tflops"] / tf32_peak
+    return {"workload": "allpairs_162541x62423_d128", "baseline_config": "configs[3] (all-pairs GEMM eval scoring)",
+            "flop": 2.0 * w["U"] * w["I"] * w["d"], "dtype": "tf32 operands, fp32 accumulate (float64 rescore for rankings)",
+            "tf32_peak_tflops": tf32_peak, "tf32_peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (burst)",
+            "consumers": res}
 
 
 def run_fm_workload(torch, epochs=12, warm_epochs=2):

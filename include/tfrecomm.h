@@ -336,6 +336,27 @@ int tfr_allpairs(const float* user_feat, const float* item_feat, const float* us
                  float* scores, float* best_score, int32_t* best_item, void* workspace, int64_t workspace_bytes,
                  void* stream);
 
+/* ---- all-pairs CONSUMERS in the GEMM epilogue (tcgen05 path: dim % 32 == 0, dim <= 128): the score matrix is never written.
+ *  k > 0: per-user ranking over ALL items -- forward.py:47-61 get_ranking (score every item for a user, sort, keep the
+ *    first 50) for every user at once.  The tensor cores (tf32 operands) keep each row's n_cand >= k best candidates
+ *    (n_cand <= 128; 64 for k = 50 is plenty); the candidates are then rescored in float64 -- the reference's own
+ *    precision, als3.py:112 is numpy float64 -- ranked (score descending, lowest item index on ties) and CERTIFIED: the
+ *    first k are the exact top-k of the whole row if the k-th exact score exceeds the worst candidate's tensor-core score
+ *    by more than the tf32 error bound 2^-9 * ||u|| * max||v||.  Rows that cannot be certified (near-ties) are redone over
+ *    all items in float64 on CUDA cores.  Result: topk_val (float64) / topk_idx [n_users, k], identical to ranking the
+ *    float64 score matrix; *n_uncertified = how many rows took the exact path.  Missing ranks (k > n_items): (-inf, -1).
+ *  obs_indptr != null: the squared error on the OBSERVED pairs, als3.py:110-120,139-143 (predict = M[user_ids, work_ids],
+ *    compute_rmse): pairs as CSR by user (obs_indptr int64 [n_users + 1], obs_item ascending inside a user, obs_rate);
+ *    row_se[u] = sum over u's pairs of (score - rating)^2 in float64, scores as the tensor cores produce them (tf32
+ *    operands: relative error <= 2^-9 on the dot product; tfr_svd_forward on the pairs is the exact alternative).
+ * Both consumers can be requested in one sweep.  workspace: tfr_allpairs_topk_workspace_bytes (k > 0 only). */
+int64_t tfr_allpairs_topk_workspace_bytes(int64_t n_users, int64_t n_items, int32_t k, int32_t n_cand);
+int tfr_allpairs_consume(const float* user_feat, const float* item_feat, const float* user_bias, const float* item_bias,
+                         const float* mu, int64_t n_users, int64_t n_items, int32_t dim, int64_t user_stride,
+                         int64_t item_stride, int32_t k, int32_t n_cand, double* topk_val, int32_t* topk_idx,
+                         int32_t* n_uncertified, const int64_t* obs_indptr, const int32_t* obs_item, const float* obs_rate,
+                         double* row_se, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- host side of the feed_dict boundary: the columns a reference iterator yields (dataio.py:114-117: float64 views
  * of one [B, ncols] matrix, ids included) packed into a pinned staging buffer in the device's types -- int32 ids
  * (value cast, like TF feeding an int32 placeholder, A.7) followed by float32 rates: [users B | items B | rates B].
@@ -349,6 +370,65 @@ int tfr_host_pack_feed_checked(const void* users_host, int32_t users_dtype, int6
 int tfr_host_pack_feed(const void* users_host, int32_t users_dtype, int64_t users_stride, const void* items_host,
                        int32_t items_dtype, int64_t items_stride, const void* rates_host, int32_t rates_dtype,
                        int64_t rates_stride, int64_t n, void* staging_host /* 12 * n bytes */);
+
+/* ---- the feed_dict step, host side AND device side in two calls (what Session.prefetch / Session.run issue) -------------
+ * One staging set of the feed path; all memory and the five events (cudaEvent_t, tfr_event_create) are the caller's.
+ * Two or three sets are used round-robin.  Every reuse is ordered by the set's events: the pinned buffer is never repacked
+ * while a copy out of it is queued, the device buffers never overwritten while a step still reads them. */
+typedef struct {
+  void* h_feed;      /* pinned host, 12 * B bytes: [users int32 | items int32 | rates float32]                 */
+  void* d_feed;      /* device, same layout                                                                    */
+  float* d_out;      /* device, 2 * B floats: [logits | infer]                                                 */
+  float* h_out;      /* pinned host, 2 * B floats                                                              */
+  void* workspace;   /* tfr_svd_step_workspace_bytes(B, dim)                                                   */
+  int64_t workspace_bytes;
+  void *ev_h2d, *ev_sorted, *ev_pred, *ev_d2h, *ev_done;
+  int32_t used;      /* set by the library: the set has been through a prefetch / a step before               */
+  int32_t copied;    /* set by the library: a copy out of d_out has been issued                               */
+} tfr_feed_set;
+/* pack (tfr_host_pack_feed_checked: value cast + range check) -> H2D copy -> id sort, the last two on side_stream: needs no
+ * table data, so it runs under whatever the step stream is doing (normally the previous step's table pass).  Blocks
+ * the HOST only on ev_h2d of the set's previous use (the pinned buffer must be free to repack). */
+int tfr_svd_feed_prefetch(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set, const void* users_host,
+                          int32_t users_dtype, int64_t users_stride, const void* items_host, int32_t items_dtype,
+                          int64_t items_stride, const void* rates_host, int32_t rates_dtype, int64_t rates_stride,
+                          int64_t B, void* side_stream);
+/* forward + segment sums -> [copy of the predictions to h_out on copy_stream, beside the table pass] -> Adam pass / SGD.
+ * fetch: 0 = nothing, 1 = infer only (B floats into h_out[B..2B); the README head has logits == infer), 2 = logits and
+ * infer.  Asynchronous: the caller waits on set->ev_d2h (tfr_event_synchronize) before reading h_out. */
+int tfr_svd_feed_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set, int64_t B, int32_t flags,
+                      int32_t var_mask, int32_t fetch, void* stream, void* copy_stream);
+int tfr_event_synchronize(void* event);
+
+/* ---- DISCRETE-branch metrics on the device: replaces the host code of svd_train_val.py:94-98,138-143 -------------------
+ * out4 (device, 4 doubles) = [ sum_b sigmoid_cross_entropy(labels_b, logits_b)   (cost_nll, ops.py:125-126),
+ *                              #{b : round(sigmoid(logits_b)) == labels_b}         (:96,140),
+ *                              roc_auc_score(labels, sigmoid(logits))              (:97,141; NaN if one class only),
+ *                              #{b : labels_b > 0.5} ]
+ * AUC by the rank statistic with tied scores averaged (what sklearn's trapezoids give): the fp32 probabilities are sorted
+ * with the step's stable radix sort, runs of equal scores found by flags + prefix sums.  Deterministic. */
+int64_t tfr_binary_metrics_workspace_bytes(int64_t n);
+int tfr_binary_metrics(const float* logits, const float* labels, int64_t n, void* workspace, int64_t workspace_bytes,
+                       double* out4, void* stream);
+
+/* ---- KTM design matrix on the device: replaces fm.py:61-93 df_to_sparse (scipy coo / hstack / tocsr on the host) ---------
+ * One block per active agent, hstacked in the order given: agents_host[g] in 0..7 = users, items, skills, attempts, wins,
+ * fails, item_wins, item_fails; col0_host[g] = first column of block g.  users / items: one-hot; skills: qmatrix[item];
+ * wins / fails: the per-skill counters of the event (skill_wins / skill_fails CSR rows, explicit zeros kept);
+ * attempts = skill_wins + skill_fails as scipy adds them (union pattern, zero sums dropped); item_wins / item_fails: the
+ * item one-hot scaled by the event's wins / fails column.  Two steps: indptr (count + scan; indptr[n] = nnz), then fill.
+ * Device pointers except agents_host / col0_host. */
+int64_t tfr_ktm_workspace_bytes(int64_t n);
+int tfr_ktm_csr_indptr(const int32_t* user, const int32_t* item, const float* wins_col, const float* fails_col,
+                       const int64_t* q_indptr, const int32_t* q_indices, const float* q_data, const int64_t* sw_indptr,
+                       const int32_t* sw_indices, const float* sw_data, const int64_t* sf_indptr, const int32_t* sf_indices,
+                       const float* sf_data, int64_t n, const int32_t* agents_host, const int32_t* col0_host,
+                       int32_t n_agents, int64_t* indptr, void* workspace, int64_t workspace_bytes, void* stream);
+int tfr_ktm_csr_fill(const int32_t* user, const int32_t* item, const float* wins_col, const float* fails_col,
+                     const int64_t* q_indptr, const int32_t* q_indices, const float* q_data, const int64_t* sw_indptr,
+                     const int32_t* sw_indices, const float* sw_data, const int64_t* sf_indptr, const int32_t* sf_indices,
+                     const float* sf_data, int64_t n, const int32_t* agents_host, const int32_t* col0_host,
+                     int32_t n_agents, const int64_t* indptr, int32_t* indices, float* data, void* stream);
 
 /* ---- ranking consumer: replaces forward.py:47-61 get_ranking (score every item for a user, sort, keep the first 50) ---
  * The k best entries of every row of scores [n_rows, n_cols] (row_stride floats between rows, 0 = n_cols), in rank

@@ -25,7 +25,7 @@ from collections import deque
 import numpy as np
 
 import tf_recomm_b200  # noqa: F401
-from tf_recomm_b200 import config, dataio, ops, synthetic
+from tf_recomm_b200 import config, dataio, ops, summary, synthetic
 
 
 def roc_auc(y_true, score):
@@ -44,6 +44,7 @@ def svd(train, test, args, log=print):
     BATCH_SIZE = args.batch
     nb_batches = len(train["user"]) // BATCH_SIZE
     discrete = args.variant == "fork"
+    host_metrics = bool(getattr(args, "host_metrics", False))
     cols = ["user", "item", "outcome", "wins", "fails"]
     iter_train = dataio.ShuffleIterator([train[c] for c in cols], batch_size=BATCH_SIZE)
     iter_test = dataio.OneEpochIterator([test[c] for c in cols], batch_size=-1)
@@ -67,6 +68,7 @@ def svd(train, test, args, log=print):
     with ops.Session() as sess:
         sess.run(init_op)
         engine = ops.session.current_model().engine
+        writer = summary.FileWriter(args.logdir) if getattr(args, "logdir", None) else None   # :57
         log("{} {} {} {}".format("epoch", "train_error", "val_error", "elapsed_time"))
         train_se = deque(maxlen=nb_batches)
         train_nll = deque(maxlen=nb_batches)
@@ -82,8 +84,8 @@ def svd(train, test, args, log=print):
         def feed_of(b):
             return {user_batch: b[0], item_batch: b[1], rate_batch: b[2], wins_batch: b[3], fails_batch: b[4]}
         # session mode: this driver owns the iterator, so batch i+1 is drawn (same RandomState order as the reference's
-        # loop: one draw per step) and handed to sess.prefetch as soon as step i has returned its predictions -- its
-        # packing, H2D copy and id sort then run under step i's table pass
+        # loop: one draw per step) and handed to sess.prefetch BEFORE step i is asked for -- its packing, H2D copy and id
+        # sort then overlap step i on the device
         ahead = None
         if not (args.mode == "stream" and not discrete) and total_steps > 0:
             ahead = next(iter_train)
@@ -103,17 +105,24 @@ def svd(train, test, args, log=print):
                 if report_at % nb_batches != 0:
                     continue  # the tail after the last full epoch is trained but not reported (:106)
             else:
-                train_users, train_items, train_rates, train_wins, train_fails = ahead
-                _, train_logits, train_infer = sess.run([train_op, logits, infer], feed_dict=feed_of(ahead))
+                cur = ahead
+                train_users, train_items, train_rates, train_wins, train_fails = cur
                 if i + 1 < total_steps:
                     ahead = next(iter_train)
                     sess.prefetch(feed_of(ahead))
+                _, train_logits, train_infer = sess.run([train_op, logits, infer], feed_dict=feed_of(cur))
                 if discrete:
-                    nll_batch = sess.run(cost, feed_dict={rate_batch: train_rates, logits: train_logits})
-                    proba_batch = ops.sigmoid(train_logits)
-                    train_acc.append(np.round(proba_batch) == train_rates)
-                    train_auc.append(roc_auc(train_rates, proba_batch))
-                    train_nll.append(nll_batch)
+                    if host_metrics:   # the reference's own host code (:94-98), kept as the cross-check
+                        nll_batch = sess.run(cost, feed_dict={rate_batch: train_rates, logits: train_logits})
+                        proba_batch = ops.sigmoid(train_logits)
+                        train_acc.append(np.mean(np.round(proba_batch) == train_rates))
+                        train_auc.append(roc_auc(train_rates, proba_batch))
+                        train_nll.append(nll_batch)
+                    else:                   # same three numbers from the step's device-resident logits and ratings
+                        mt = engine.last_step_metrics(len(train_users))
+                        train_acc.append(mt["n_correct"] / mt["n"])
+                        train_auc.append(mt["auc"])
+                        train_nll.append(mt["nll_sum"])
                 else:
                     train_se.append(np.power(train_rates - train_infer, 2))
                 report_at = i
@@ -125,12 +134,20 @@ def svd(train, test, args, log=print):
             # ---- report (svd_train_val.py:106-193) ----
             test_se, test_acc, test_nll, test_auc = [], [], [], 0.0
             for test_users, test_items, test_rates, test_wins, test_fails in iter_test:
+                if discrete and not host_metrics:
+                    # forward + ACC / AUC / NLL without the logits ever leaving the device (32 bytes come back)
+                    lg_dev, _ = engine.forward(test_users, test_items)
+                    mt = engine.binary_metrics(lg_dev, test_rates)
+                    test_acc.append(mt["n_correct"] / mt["n"])
+                    test_auc = mt["auc"]
+                    test_nll.append(mt["nll_sum"])
+                    continue
                 test_logits, test_infer = sess.run([logits, infer], feed_dict={
                     user_batch: test_users, item_batch: test_items, wins_batch: test_wins, fails_batch: test_fails})
                 if discrete:
                     nll_batch = sess.run(cost, feed_dict={rate_batch: test_rates, logits: test_logits})
                     proba_batch = ops.sigmoid(test_logits)
-                    test_acc.append(np.round(proba_batch) == test_rates)
+                    test_acc.append(np.mean(np.round(proba_batch) == test_rates))
                     test_auc = roc_auc(test_rates, proba_batch)
                     test_nll.append(nll_batch)
                 else:
@@ -152,7 +169,18 @@ def svd(train, test, args, log=print):
                 log("{:3d} TRAIN(size={:d}/{:d}, rmse={:f}) TEST(size={:d}, rmse={:f}) {:f}(s)".format(
                     epoch, last_batch, len(train["user"]), train_rmse, len(test["user"]), test_rmse, end - start))
             history.append(rec)
+            if writer is not None:
+                # svd_train_val.py:189-192: train_rmse / test_rmse under these two tags (NaN on the DISCRETE branch, where
+                # the reference's train_se stays empty; the branch's own numbers go out under tags of their own)
+                writer.add_summary(summary.make_scalar_summary("training_error", rec.get("train_rmse", float("nan"))), report_at)
+                writer.add_summary(summary.make_scalar_summary("test_error", rec.get("test_rmse", float("nan"))), report_at)
+                if discrete:
+                    for tag in ("train_macc", "train_mauc", "train_mnll", "test_macc", "test_auc", "test_mnll"):
+                        writer.add_summary(summary.make_scalar_summary(tag, rec[tag]), report_at)
+                writer.flush()
             start = end
+        if writer is not None:
+            writer.close()
         if args.checkpoint:
             path = os.path.join(config.BASE_DIR, args.checkpoint)
             log(path)
@@ -202,6 +230,10 @@ def main(argv=None):
     ap.add_argument("--item-num", dest="item_num", type=int, default=None)
     ap.add_argument("--mode", type=str, default="session", choices=["session", "stream"])
     ap.add_argument("--checkpoint", type=str, default="fm.ckpt")
+    ap.add_argument("--logdir", type=str, default="/tmp/svd/log",
+                    help="TensorBoard event files (svd_train_val.py:57); empty string = none")
+    ap.add_argument("--host-metrics", dest="host_metrics", action="store_true",
+                    help="DISCRETE branch: ACC / AUC / NLL with the reference's host code instead of on the device")
     args = ap.parse_args(argv)
     np.random.seed(config.SEED)  # svd_train_val.py:15
     train, val = load(args)

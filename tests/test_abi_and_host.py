@@ -47,6 +47,9 @@ int main(void) {
          offsetof(tfr_opt_scalars, se_ring), offsetof(tfr_opt_scalars, timeline));
   printf("%zu %zu %zu\n", offsetof(tfr_svd_tables, mu), offsetof(tfr_svd_tables, user_slot), offsetof(tfr_svd_step_ws, sort_ws));
   printf("%zu %zu %zu\n", sizeof(tfr_fm_tables), offsetof(tfr_fm_tables, w0), offsetof(tfr_fm_tables, slot));
+  printf("%zu %zu %zu %zu\n", sizeof(tfr_feed_set), offsetof(tfr_feed_set, workspace_bytes), offsetof(tfr_feed_set, ev_done),
+         offsetof(tfr_feed_set, copied));
+  printf("%zu\n", offsetof(tfr_opt_scalars, prefetch_cursor));
   return 0;
 }'''
     import tempfile
@@ -61,7 +64,8 @@ int main(void) {
            C.sizeof(_lib.SliceUpdate), _lib.OptScalars.global_step.offset, _lib.OptScalars.batch_cursor.offset,
            _lib.OptScalars.se_ring.offset, _lib.OptScalars.timeline.offset, _lib.SvdTables.mu.offset,
            _lib.SvdTables.user_slot.offset, _lib.StepWs.sort_ws.offset, C.sizeof(_lib.FmTables),
-           _lib.FmTables.w0.offset, _lib.FmTables.slot.offset]
+           _lib.FmTables.w0.offset, _lib.FmTables.slot.offset, C.sizeof(_lib.FeedSet), _lib.FeedSet.workspace_bytes.offset,
+           _lib.FeedSet.ev_done.offset, _lib.FeedSet.copied.offset, _lib.OptScalars.prefetch_cursor.offset]
     assert got == exp
 
 
@@ -239,3 +243,34 @@ def test_host_pack_feed_checked_rejects_out_of_range_ids():
     o3 = np.zeros(9, np.int32)
     assert L.tfr_host_pack_feed(users.ctypes.data, 3, 8, items.ctypes.data, 3, 8, r3.ctypes.data, 0, 8, 3, o3.ctypes.data) == 0
     assert list(o3[:3]) == [5, 1000000, -3]
+
+
+def test_tensorboard_event_file_round_trip(tmp_path):
+    """summary.FileWriter writes what tf.summary.FileWriter writes (svd_train_val.py:20-21,57,189-192): TFRecord framing
+    with masked CRC32-C, Event / Summary protos; read back by our reader and, when the package is there, by
+    TensorBoard's own EventFileLoader."""
+    from tf_recomm_b200 import summary
+    w = summary.FileWriter(str(tmp_path))
+    vals = [(0, "training_error", 2.63753), (0, "test_error", 2.587753), (900, "training_error", 0.9), (2 ** 33, "test_error", float("nan"))]
+    for step, tag, v in vals:
+        w.add_summary(summary.make_scalar_summary(tag, v), step)
+    w.close()
+    got = summary.read_events(w.path)
+    assert [(s, t) for s, t, _ in got] == [(s, t) for s, t, _ in vals]
+    for (_, _, a), (_, _, b) in zip(got, vals):
+        assert (np.isnan(a) and np.isnan(b)) or a == np.float32(b)
+    assert summary._crc32c(b"123456789") == 0xE3069283          # the CRC-32C check value
+    raw = bytearray(open(w.path, "rb").read())
+    raw[40] ^= 1
+    bad = tmp_path / "bad"
+    bad.write_bytes(bytes(raw))
+    with pytest.raises(ValueError):
+        summary.read_events(str(bad))
+    try:
+        from tensorboard.backend.event_processing.event_file_loader import EventFileLoader
+    except Exception:
+        return
+    evs = list(EventFileLoader(w.path).Load())
+    assert evs[0].file_version == "brain.Event:2"
+    seen = [(e.step, v.tag) for e in evs[1:] for v in e.summary.value]
+    assert seen == [(s, t) for s, t, _ in vals]

@@ -110,3 +110,42 @@ def test_driver_reads_the_reference_csv_layout(tmp_path, monkeypatch):
     assert len(rows) >= 5 and rows[-1][2] < rows[0][2]
     z = np.load(str(tmp_path / "fm.ckpt"))
     assert z["user_feat"].shape == (U, 8) and z["item_feat"].shape == (I, 8)
+
+
+def test_driver_fork_device_metrics_equal_host_metrics_and_tensorboard(tmp_path):
+    """DISCRETE branch: ACC / AUC / NLL computed on the device (tfr_binary_metrics) print the same lines as the reference's
+    host code (numpy sigmoid / round, sklearn-equivalent AUC); and the two runs leave the reference's TensorBoard scalars
+    `training_error` / `test_error` (svd_train_val.py:20-21,57,189-192) in an event file."""
+    from tf_recomm_b200 import summary
+    common = ["--synthetic", "ml1m", "--ratings", "30000", "--epochs", "2", "--batch", "500", "--dim", "20",
+              "--variant", "fork", "--lr", "0.005", "--reg", "0.01", "--checkpoint", os.devnull]
+    pat = (r"^\s*(\d+) TRAIN\(size=\d+/\d+, macc=([0-9.]+), mauc=([0-9.]+), mnll=([0-9.]+)\) "
+           r"TEST\(size=\d+, macc=([0-9.]+), auc=([0-9.]+), mnll=([0-9.]+)\)")
+    dev = re.findall(pat, _run(common + ["--logdir", str(tmp_path / "tb")]), flags=re.M)
+    host = re.findall(pat, _run(common + ["--logdir", "", "--host-metrics"]), flags=re.M)
+    assert len(dev) == len(host) >= 2
+    for a, b in zip(dev, host):
+        assert a[0] == b[0]
+        for x, y in zip(a[1:], b[1:]):
+            assert float(x) == pytest.approx(float(y), abs=2e-6)
+    files = list((tmp_path / "tb").iterdir())
+    assert len(files) == 1 and files[0].name.startswith("events.out.tfevents.")
+    ev = summary.read_events(str(files[0]))
+    tags = {t for _, t, _ in ev}
+    assert {"training_error", "test_error", "train_macc", "test_auc", "test_mnll"} <= tags
+    assert [s for s, t, _ in ev if t == "test_auc"][0] == 0        # the first report comes after ONE step (:106)
+
+
+def test_driver_readme_tensorboard_scalars(tmp_path):
+    from tf_recomm_b200 import summary
+    text = _run(["--synthetic", "ml1m", "--ratings", "30000", "--epochs", "3", "--batch", "1000", "--dim", "15",
+                 "--checkpoint", os.devnull, "--logdir", str(tmp_path / "log")])
+    rows = _errors(text)
+    ev = summary.read_events(str(next((tmp_path / "log").iterdir())))
+    tr = [(s, v) for s, t, v in ev if t == "training_error"]
+    te = [(s, v) for s, t, v in ev if t == "test_error"]
+    assert len(tr) == len(te) == len(rows)
+    nb = 27000 // 1000
+    for (e, a, b), (s1, v1), (s2, v2) in zip(rows, tr, te):
+        assert s1 == s2 == e * nb                                   # add_summary(summary, i), i = the step index
+        assert v1 == pytest.approx(a, abs=2e-6) and v2 == pytest.approx(b, abs=2e-6)

@@ -767,3 +767,156 @@ def test_out_of_range_ids_raise():
     for n in before:
         assert np.array_equal(before[n], after[n]), n    # nothing was launched
     assert eng.global_step == 0
+
+
+def _f64_scores(tabs):
+    """als3.py:112 as the reference computes it: numpy float64 of the (fp32-valued) tables."""
+    U64, V64 = tabs["user_feat"].astype(np.float64), tabs["item_feat"].astype(np.float64)
+    return ((U64 @ V64.T + tabs["user_bias"].astype(np.float64)[:, None]) + tabs["item_bias"].astype(np.float64)[None, :]) \
+        + float(tabs["mu"][0])
+
+
+def _rank_f64(M, k):
+    I = M.shape[1]
+    return np.stack([np.lexsort((np.arange(I), -M[u]))[:k] for u in range(M.shape[0])]).astype(np.int32)
+
+
+@pytest.mark.parametrize("U,I,d,k,n_cand,ties", [(300, 1000, 64, 50, 64, False), (129, 777, 128, 50, 64, True),
+                                                 (257, 40, 32, 50, 64, False), (64, 3000, 96, 1, 8, True),
+                                                 (500, 2048, 128, 10, 16, False)])
+def test_allpairs_topk_equals_float64_ranking(U, I, d, k, n_cand, ties):
+    """The fused ranking consumer (tensor-core candidates -> float64 rescore -> certificate -> exact fallback) returns
+    EXACTLY the ranking of the float64 score matrix of als3.py:112 / forward.py:47-61: same items in the same order
+    (lowest id on ties), whatever tf32 did to the tensor-core scores.  Exact ties between groups of items force rows
+    through the uncertified path."""
+    tabs = init.init_tables(U, I, d, seed=21, bias_init="truncated_normal")
+    tabs["user_feat"] *= 25; tabs["item_feat"] *= 25
+    if ties:
+        tabs["item_bias"][::5] = tabs["item_bias"][0]
+        tabs["item_feat"][::5] = tabs["item_feat"][0]
+    eng = SvdEngine(U, I, d, 1e-3, 0.05, tables=tabs)
+    idx, val, n_unc = eng.rank_all_users(k=k, n_cand=n_cand)
+    M = _f64_scores(tabs)
+    kk = min(k, I)
+    ref = _rank_f64(M, kk)
+    got = idx.cpu().numpy()
+    assert got.shape == (U, kk)
+    assert np.array_equal(got, ref), "%d rows differ (n_uncertified %d)" % (int((got != ref).any(axis=1).sum()), n_unc)
+    np.testing.assert_allclose(val.cpu().numpy(), np.take_along_axis(M, ref.astype(np.int64), axis=1), rtol=1e-12, atol=1e-12)
+    if ties:
+        assert n_unc > 0      # the exact path was exercised
+    assert 0 <= n_unc <= U
+
+
+def test_allpairs_top1_tf32_mismatch_rate_and_exact_mode():
+    """How often does the tensor-core (tf32) top-1 differ from the exact arg-max?  Measured against the float64 oracle
+    (als3.py:112); the exact mode (rank_all_users, k = 1) must agree with the oracle on every row."""
+    U, I, d = 2048, 4096, 128
+    tabs = init.init_tables(U, I, d, seed=5, bias_init="truncated_normal")
+    tabs["user_feat"] *= 25; tabs["item_feat"] *= 25
+    eng = SvdEngine(U, I, d, 1e-3, 0.05, tables=tabs)
+    M = _f64_scores(tabs)
+    exact = M.argmax(axis=1).astype(np.int32)
+    tf32 = eng.allpairs(want_scores=False, want_best=True, use_tensor_cores=True)["best_item"].cpu().numpy()
+    fp32 = eng.allpairs(want_scores=False, want_best=True, use_tensor_cores=False)["best_item"].cpu().numpy()
+    idx, _, n_unc = eng.rank_all_users(k=1, n_cand=8)
+    rate = float((tf32 != exact).mean())
+    print("all-pairs top-1 vs float64 oracle: tf32 mismatch rate %.4f %% (%d of %d rows), fp32 CUDA-core %d rows, exact mode "
+          "0 required, uncertified %d" % (100 * rate, int((tf32 != exact).sum()), U, int((fp32 != exact).sum()), n_unc))
+    PARITY_STATS.append(dict(what="allpairs top-1 tf32 vs float64 argmax", n=U, outside=int((tf32 != exact).sum()),
+                             rel_l2=rate, max_abs=0.0, rtol=0.0))
+    assert np.array_equal(idx.cpu().numpy()[:, 0], exact)
+    # where tf32 picks another item, that item's exact score is within the tf32 error bound of the best one
+    bad = np.nonzero(tf32 != exact)[0]
+    mag = np.abs(tabs["user_feat"]).astype(np.float64) @ np.abs(tabs["item_feat"]).astype(np.float64).T
+    for u in bad:
+        assert M[u, exact[u]] - M[u, tf32[u]] <= 2.0 ** -8 * mag[u].max()
+    assert rate <= 0.02
+
+
+@pytest.mark.parametrize("U,I,d,n", [(300, 500, 64, 20000), (1000, 129, 128, 5000), (130, 4000, 32, 1)])
+def test_allpairs_observed_pairs_squared_error(U, I, d, n):
+    """als3.py:110-120,139-143 (predict = M[user_ids, work_ids]; RMSE) consumed in the GEMM epilogue: per-user squared
+    error over the observed pairs, duplicates counted like fancy indexing counts them; scores are tf32 (bound below)."""
+    tabs = init.init_tables(U, I, d, seed=8, bias_init="truncated_normal")
+    tabs["user_feat"] *= 25; tabs["item_feat"] *= 25
+    eng = SvdEngine(U, I, d, 1e-3, 0.05, tables=tabs)
+    rng = np.random.default_rng(n)
+    users = zipf_ids(rng, U, n, 0.8); items = zipf_ids(rng, I, n, 1.0)
+    rates = rng.integers(1, 6, n).astype(np.float32)
+    if n > 10:
+        users[5], items[5] = users[4], items[4]          # a duplicated pair
+    rmse, row_se = eng.observed_rmse(users, items, rates)
+    M = _f64_scores(tabs)
+    pred = M[users, items]
+    err = pred - rates
+    ref_row = np.bincount(users, weights=err ** 2, minlength=U)
+    mag = np.abs(tabs["user_feat"]).astype(np.float64) @ np.abs(tabs["item_feat"]).astype(np.float64).T
+    e_s = 2.0 ** -9 * mag[users, items] + 1e-5                       # per-score tf32 bound
+    tol_row = np.bincount(users, weights=2 * np.abs(err) * e_s + e_s ** 2, minlength=U)
+    got = row_se.cpu().numpy()
+    assert np.all(np.abs(got - ref_row) <= tol_row + 1e-9), float(np.max(np.abs(got - ref_row) - tol_row))
+    assert np.all(got[np.bincount(users, minlength=U) == 0] == 0.0)
+    assert abs(rmse - np.sqrt(np.mean(err ** 2))) <= 2e-3 * max(1.0, np.sqrt(np.mean(err ** 2)))
+
+
+@pytest.mark.parametrize("n,ties", [(1, False), (2, False), (1000, False), (65536, True), (100021, True), (300000, False)])
+def test_binary_metrics_match_sklearn(n, ties):
+    """tfr_binary_metrics (device): summed sigmoid cross-entropy, #correct of round(sigmoid), roc_auc_score with tied
+    scores averaged -- against numpy / sklearn on the same fp32 probabilities (svd_train_val.py:94-98,138-143)."""
+    from sklearn.metrics import roc_auc_score
+    eng, _ = both(10, 10, 4, 1e-3, 0.05)
+    rng = np.random.default_rng(n)
+    logits = (rng.standard_normal(n) * (6.0 if ties else 2.0)).astype(np.float32)
+    if ties:
+        logits[::3] = np.round(logits[::3])          # many exactly tied scores, and saturated sigmoids
+        logits[5:50] = 30.0
+    labels = (rng.random(n) < 1.0 / (1.0 + np.exp(-logits * 0.7))).astype(np.float32)
+    if n <= 2:
+        labels[:] = [1.0, 0.0][:n]
+    m = eng.binary_metrics(logits, labels)
+    x = logits.astype(np.float32)
+    p = (np.float32(1.0) / (np.float32(1.0) + np.exp(-x))).astype(np.float32)          # ops.sigmoid, fp32
+    nll = np.sum(np.maximum(x, 0).astype(np.float64) - (x * labels).astype(np.float64) + np.log1p(np.exp(-np.abs(x))).astype(np.float64))
+    assert m["n"] == n and m["n_pos"] == int(labels.sum())
+    assert m["nll_sum"] == pytest.approx(nll, rel=1e-6, abs=1e-6)
+    ok = int(np.sum(np.round(p) == labels))
+    assert abs(m["n_correct"] - ok) <= max(1, n // 100000)          # round() may flip where p is within an ulp of 0.5
+    if 0 < labels.sum() < n:
+        assert m["auc"] == pytest.approx(roc_auc_score(labels, p), abs=1e-9)
+    else:
+        assert np.isnan(m["auc"])
+
+
+@pytest.mark.parametrize("agents", [["users", "items"], ["users", "items", "skills", "wins", "fails"],
+                                    ["items", "skills", "attempts", "item_wins", "item_fails"], ["skills"],
+                                    ["users", "items", "skills", "attempts", "wins", "fails", "item_wins", "item_fails"]])
+def test_ktm_design_matrix_built_on_device_equals_scipy(agents, golden_dir):
+    """fm.py:61-93 df_to_sparse built as CSR in HBM (count -> scan -> fill) equals the scipy hstack of the host encoder:
+    the reference's 7-event dummy dataset (diagram_pretty.tex:16-22,31) and a random event log."""
+    import json
+    import os
+    import pandas as pd
+    from scipy.sparse import csr_matrix
+    from tf_recomm_b200 import ktm
+    g = json.load(open(os.path.join(golden_dir, "ktm_encoder_dummy.json")))
+    cases = []
+    ev = np.array(g["rows_user_item_outcome"])
+    q = np.array(g["qmatrix"], dtype=np.float64)
+    cases.append((ev[:, 0], ev[:, 1], ev[:, 2].astype(np.float32), csr_matrix(q), 2, 3))
+    users, items, outcomes, qm = ktm.make_ktm_events(n_events=5000, user_num=60, item_num=300, n_skills=17, seed=3)
+    cases.append((users, items, outcomes, qm, 60, 300))
+    for users, items, outcomes, qm, U, I in cases:
+        sw, sf = ktm.skill_counters(users, items, outcomes, qm)
+        rng = np.random.default_rng(1)
+        df = pd.DataFrame(dict(user=users, item=items, outcome=outcomes, wins=rng.integers(0, 4, len(users)),
+                               fails=rng.integers(0, 3, len(users))))
+        ref = ktm.df_to_sparse(df, agents, U, I, qm, sw, sf)
+        indptr, indices, data, n_cols = ktm.df_to_sparse_device(df, agents, U, I, qm, sw, sf)
+        got = csr_matrix((data.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()), shape=(len(users), n_cols))
+        assert got.shape == ref.shape
+        assert np.array_equal(got.toarray(), ref.toarray().astype(np.float32))
+        a, b = got.copy(), ref.astype(np.float32)
+        for m in (a, b):
+            m.eliminate_zeros(); m.sort_indices()
+        assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices) and np.array_equal(a.data, b.data)

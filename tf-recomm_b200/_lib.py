@@ -57,6 +57,13 @@ class StepWs(C.Structure):
                 ("sort_ws", vp), ("sort_ws_bytes", i64), ("tile", i32), ("n_tiles", i32)]
 
 
+class FeedSet(C.Structure):
+    """Mirror of tfr_feed_set."""
+    _fields_ = [("h_feed", vp), ("d_feed", vp), ("d_out", vp), ("h_out", vp), ("workspace", vp), ("workspace_bytes", i64),
+                ("ev_h2d", vp), ("ev_sorted", vp), ("ev_pred", vp), ("ev_d2h", vp), ("ev_done", vp),
+                ("used", i32), ("copied", i32)]
+
+
 class FmTables(C.Structure):
     """Mirror of tfr_fm_tables."""
     _fields_ = [("n_feat", i32), ("dim", i32), ("w0", vp), ("W", vp), ("V", vp), ("m_w0", vp), ("v_w0", vp),
@@ -95,6 +102,17 @@ _PROTOS = {
     "tfr_svd_step_workspace_bytes": (i64, [i64, i32]),
     "tfr_svd_train_step": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, i64, vp, vp, i32, i32, vp, i64, vp,
                                      C.POINTER(vp), i32, C.POINTER(vp)]),
+    "tfr_svd_feed_prefetch": (C.c_int, [C.POINTER(SvdTables), vp, C.POINTER(FeedSet), vp, i32, i64, vp, i32, i64, vp, i32, i64,
+                                        i64, vp]),
+    "tfr_svd_feed_step": (C.c_int, [C.POINTER(SvdTables), vp, C.POINTER(FeedSet), i64, i32, i32, i32, vp, vp]),
+    "tfr_event_synchronize": (C.c_int, [vp]),
+    "tfr_binary_metrics_workspace_bytes": (i64, [i64]),
+    "tfr_binary_metrics": (C.c_int, [vp, vp, i64, vp, i64, vp, vp]),
+    "tfr_ktm_workspace_bytes": (i64, [i64]),
+    "tfr_ktm_csr_indptr": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(i32), C.POINTER(i32), i32,
+                                     vp, vp, i64, vp]),
+    "tfr_ktm_csr_fill": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(i32), C.POINTER(i32), i32,
+                                   vp, vp, vp, vp]),
     "tfr_event_create": (C.c_int, [C.POINTER(vp)]),
     "tfr_event_destroy": (C.c_int, [vp]),
     "tfr_svd_prefetch_batch": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, vp]),
@@ -117,6 +135,9 @@ _PROTOS = {
     "tfr_fm_train_step": (C.c_int, [C.POINTER(FmTables), vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, vp, i64, vp]),
     "tfr_allpairs_workspace_bytes": (i64, [i64, i64, i32, i32]),
     "tfr_allpairs": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, i64, i64, i32, vp, vp, vp, vp, i64, vp]),
+    "tfr_allpairs_topk_workspace_bytes": (i64, [i64, i64, i32, i32]),
+    "tfr_allpairs_consume": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
+                                       i64, vp]),
     "tfr_host_pack_feed": (C.c_int, [vp, i32, i64, vp, i32, i64, vp, i32, i64, i64, vp]),
     "tfr_host_pack_feed_checked": (C.c_int, [vp, i32, i64, vp, i32, i64, vp, i32, i64, i64, vp, i64, i64]),
     "tfr_opt_set_cursor": (C.c_int, [vp, i64, vp]),

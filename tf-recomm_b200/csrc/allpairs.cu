@@ -92,23 +92,96 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
 // share each quarter and split the tile's 128 item columns in halves.  Pipelines: item tiles double-buffered in
 // shared memory (full/empty mbarriers between TMA and MMA), accumulators double-buffered in TMEM (2 x 128 columns,
 // full/empty mbarriers between MMA and epilogue), so TMA, tensor cores and the epilogue of consecutive tiles overlap.
+//
+// Consumers of a tile, all in the epilogue's registers (the score matrix never exists unless `scores` is asked for):
+//   * top-1: running best item per user (lowest index on ties);
+//   * TOPK: the K best items per user by tensor-core score -- forward.py:47-61 ranks a user's scores and keeps 50.  A
+//     row's candidates live UNSORTED in its [K] slice of cand_val / cand_idx (global memory, L2-resident); the row's
+//     current K-th best score is the threshold a column has to reach to take the slow path (an insert under a per-row
+//     shared-memory lock: replace the minimum, rescan it).  After the first tiles almost no column does.  The caller
+//     rescores the candidates exactly and certifies the result (allpairs_rescore_kernel);
+//   * OBS: the squared error on the OBSERVED pairs, als3.py:110-120,139-143 (predict = M[user_ids, work_ids], then
+//     compute_rmse): the pairs come as CSR by user with ascending item ids; every row's thread walks its list as the
+//     tiles go by and accumulates (score - rating)^2 in float64.
 constexpr int AP_THREADS = 320, AP_EPI_WARPS = 8;
 enum { BAR_A = 0, BAR_FULL_B = 1, BAR_EMPTY_B = 3, BAR_TMEM_FULL = 5, BAR_TMEM_EMPTY = 7, AP_NBARS = 9 };
+constexpr int AP_MAX_CAND = 128;
 
-template <int KCHUNKS>
+struct ApConsumers {
+  float* scores;             // [n_users, n_items] or null
+  float* best_score;         // [n_users] or null
+  int32_t* best_item;        // [n_users] or null
+  float* cand_val;           // TOPK: [n_users, K]
+  int32_t* cand_idx;         // TOPK: [n_users, K]  (-1 = empty)
+  int K;
+  const int64_t* obs_indptr; // OBS: [n_users + 1]
+  const int32_t* obs_item;   // OBS: [nnz] ascending inside a user's range
+  const float* obs_rate;     // OBS: [nnz]
+  double* row_se;            // OBS: [n_users] sum over the user's observed pairs of (score - rating)^2
+};
+
+// order of the ranking: higher score first, lower item index on ties
+__device__ __forceinline__ bool ap_better(float s, int i, float s2, int i2) { return s > s2 || (s == s2 && i < i2); }
+
+// slow path of the TOPK consumer: (s, col) reaches the row's threshold.  r = row inside the CTA.
+__device__ __noinline__ void ap_topk_insert(float* __restrict__ cval, int32_t* __restrict__ cidx, int K, int* s_lock,
+                                            int* s_cnt, float* s_thr, int* s_minpos, int r, float s, int col) {
+  while (atomicCAS(&s_lock[r], 0, 1) != 0) {}
+  __threadfence_block();
+  const int cnt = s_cnt[r];
+  bool rescan = false;
+  if (cnt < K) {
+    __stcg(cval + cnt, s);
+    __stcg(cidx + cnt, col);
+    s_cnt[r] = cnt + 1;
+    rescan = cnt + 1 == K;
+  } else {
+    const int mp = s_minpos[r];
+    const float mv = __ldcg(cval + mp);
+    const int mi = __ldcg(cidx + mp);
+    if (ap_better(s, col, mv, mi)) {
+      __stcg(cval + mp, s);
+      __stcg(cidx + mp, col);
+      rescan = true;
+    }
+  }
+  if (rescan) {  // the list is full: find its worst entry, the row's new threshold
+    float mv = __ldcg(cval);
+    int mi = __ldcg(cidx), mp = 0;
+    for (int j = 1; j < K; ++j) {
+      const float v = __ldcg(cval + j);
+      const int i = __ldcg(cidx + j);
+      if (ap_better(mv, mi, v, i)) { mv = v; mi = i; mp = j; }
+    }
+    s_minpos[r] = mp;
+    s_thr[r] = mv;
+  }
+  __threadfence_block();
+  atomicExch(&s_lock[r], 0);
+}
+
+template <int KCHUNKS, bool TOPK, bool OBS>
 __global__ void __launch_bounds__(AP_THREADS, 1)
     allpairs_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const float* __restrict__ ub, const float* __restrict__ ib, const float* __restrict__ mu,
-                       int n_users, int n_items, float* __restrict__ scores, float* __restrict__ best_score,
-                       int32_t* __restrict__ best_item) {
+                       int n_users, int n_items, const ApConsumers cs) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // swizzle atoms: 1024 B
   uint8_t* sA = base;
   uint8_t* sB[2] = {base + KCHUNKS * AP_CHUNK_BYTES, base + 2 * KCHUNKS * AP_CHUNK_BYTES};
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + 3 * KCHUNKS * AP_CHUNK_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + AP_NBARS);
-  float* s_best = reinterpret_cast<float*>(tmem_slot + 4);       // [2][128] halves' best score per row
+  // barriers + TMEM slot live in the first 128 bytes after the tiles; the arrays behind them stay 16-byte aligned
+  // (s_bias is read with LDS.128, s_se holds doubles)
+  static_assert(AP_NBARS * 8 + 16 <= 128, "barrier block");
+  float* s_best = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);   // [2][128] halves' best score per row
   int32_t* s_besti = reinterpret_cast<int32_t*>(s_best + 256);   // [2][128]
+  float* s_bias = reinterpret_cast<float*>(s_besti + 256);       // [2][128] item bias + mu of the tile, by tile parity
+  float* s_thr = s_bias + 256;                                   // [128] TOPK: the row's threshold
+  int* s_cnt = reinterpret_cast<int*>(s_thr + 128);              // [128]
+  int* s_lock = s_cnt + 128;                                     // [128]
+  int* s_minpos = s_lock + 128;                                  // [128]
+  double* s_se = reinterpret_cast<double*>(s_minpos + 128);      // [2][128] OBS: halves' squared-error sums
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * AP_BM;
   const int n_tiles = (n_items + AP_BN - 1) / AP_BN;
@@ -125,6 +198,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < 128) { s_thr[tid] = -INFINITY; s_cnt[tid] = 0; s_lock[tid] = 0; s_minpos[tid] = 0; }
   if (warp == 1) {  // 256 TMEM columns = two 128x128 fp32 accumulators
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -183,31 +257,73 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
     const bool row_ok = row < n_users;
     const float bu = row_ok ? ub[row] : 0.0f;
     const float mu_ = *mu;
+    const int et = tid - 64;              // 0..255 among the epilogue threads
     float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains (column % 4)
     int32_t besti[4] = {-1, -1, -1, -1};
+    float* const cval = TOPK && row_ok ? cs.cand_val + (size_t)row * cs.K : nullptr;
+    int32_t* const cidx = TOPK && row_ok ? cs.cand_idx + (size_t)row * cs.K : nullptr;
+    // OBS: this row's observed pairs [op, oend), next one's item id / rating
+    int64_t op = 0, oend = 0;
+    int onext = 0x7fffffff;
+    float orate = 0.0f;
+    double se = 0.0;
+    if (OBS && row_ok) {
+      op = cs.obs_indptr[row];
+      oend = cs.obs_indptr[row + 1];
+      if (op < oend) { onext = cs.obs_item[op]; orate = cs.obs_rate[op]; }
+    }
     for (int t = 0; t < n_tiles; ++t) {
       const int acc = t & 1;
       const int n0 = t * AP_BN + half * 64;
-      // this lane's two item biases of the warp's 64 columns; exchanged by shuffle below
-      const float ib0 = (n0 + lane < n_items) ? __ldg(ib + n0 + lane) : 0.0f;
-      const float ib1 = (n0 + 32 + lane < n_items) ? __ldg(ib + n0 + 32 + lane) : 0.0f;
+      // the tile's item biases (+ mu: (dot + b_u) + (b_i + mu), the tensor-core path is tf32-approximate anyway) go
+      // to shared memory once per tile; a column's bias is then one broadcast LDS.128 per four columns
+      if (et < AP_BN) s_bias[acc * AP_BN + et] = (t * AP_BN + et < n_items) ? add_rn(__ldg(ib + t * AP_BN + et), mu_) : 0.0f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
+      float thr = TOPK ? s_thr[r_in_tile] : 0.0f;
+      if (OBS) {
+        while (onext < n0) {  // pairs of the columns the other half owns, or of earlier tiles
+          ++op;
+          if (op < oend) { onext = cs.obs_item[op]; orate = cs.obs_rate[op]; } else onext = 0x7fffffff;
+        }
+      }
       mbar_wait(&bars[BAR_TMEM_FULL + acc], (t >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         float v[32];
         tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * AP_BN + half * 64 + j * 32), v);
-        const float ibj = j ? ib1 : ib0;
+        const float4* sb4 = reinterpret_cast<const float4*>(s_bias + acc * AP_BN + half * 64 + j * 32);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int col = n0 + j * 32 + c;
-          const float bic = __shfl_sync(0xffffffffu, ibj, c);
-          float s = add_rn(v[c], bu);          // als3.py:112: ((U.V^T + W_user) + W_work) + bias
-          s = add_rn(s, bic);
-          s = add_rn(s, mu_);
-          const bool ok = row_ok && col < n_items;
-          if (scores && ok) scores[(size_t)row * n_items + col] = s;
-          if (ok && s > best[c & 3]) { best[c & 3] = s; besti[c & 3] = col; }
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 b4 = sb4[c4];
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c = c4 * 4 + q;
+            const int col = n0 + j * 32 + c;
+            const float s = add_rn(add_rn(v[c], bu), bb[q]);   // als3.py:112: U.V^T + W_user + W_work + bias
+            const bool ok = row_ok && col < n_items;
+            if (cs.scores && ok) cs.scores[(size_t)row * n_items + col] = s;
+            if (ok && s > best[q]) { best[q] = s; besti[q] = col; }
+            if (TOPK) {
+              if (ok && s >= thr) {
+                ap_topk_insert(cval, cidx, cs.K, s_lock, s_cnt, s_thr, s_minpos, r_in_tile, s, col);
+                thr = *reinterpret_cast<volatile float*>(&s_thr[r_in_tile]);
+              }
+            }
+            if (OBS) {
+              if (col == onext) {
+                const double d = (double)s - (double)orate;
+                se += d * d;
+                // duplicates of a pair (the same item twice in a user's list) all count, like fancy indexing does
+                do {
+                  ++op;
+                  if (op < oend) { onext = cs.obs_item[op]; orate = cs.obs_rate[op]; } else onext = 0x7fffffff;
+                  if (onext == col) { const double d2 = (double)s - (double)orate; se += d2 * d2; }
+                } while (onext == col);
+              }
+            }
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -222,6 +338,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
       if (best[q] > bs || (best[q] == bs && besti[q] >= 0 && (bi_ < 0 || besti[q] < bi_))) { bs = best[q]; bi_ = besti[q]; }
     s_best[half * 128 + r_in_tile] = bs;
     s_besti[half * 128 + r_in_tile] = bi_;
+    if (OBS) s_se[half * 128 + r_in_tile] = se;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -233,13 +350,183 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
       const float b1 = s_best[128 + tid];
       const int32_t i1 = s_besti[128 + tid];
       if (b1 > bs || (b1 == bs && i1 >= 0 && (bi_ < 0 || i1 < bi_))) { bs = b1; bi_ = i1; }
-      if (best_score) best_score[row] = bs;
-      if (best_item) best_item[row] = bi_;
+      if (cs.best_score) cs.best_score[row] = bs;
+      if (cs.best_item) cs.best_item[row] = bi_;
+      if (OBS) cs.row_se[row] = s_se[tid] + s_se[128 + tid];
+      if (TOPK) {  // fewer than K items in all: mark the unused candidate slots
+        for (int j = s_cnt[tid]; j < cs.K; ++j) {
+          __stcg(cs.cand_val + (size_t)row * cs.K + j, -INFINITY);
+          __stcg(cs.cand_idx + (size_t)row * cs.K + j, -1);
+        }
+      }
     }
   }
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ---- exact rescore of the tensor-core candidates, with a certificate --------------------------------------------------
+// The tensor cores rank with tf32 operands (fp32 words whose low 13 mantissa bits are ignored): a score is off by at most
+//   E_u = 2.01 * 2^-10 * ||u||_2 * max_i ||v_i||_2  (+ fp32 accumulation / bias roundings, covered by the 2^-9 used).
+// Every item OUTSIDE a row's K candidates has a tensor-core score <= T (the K-th best), hence an exact score <= T + E_u.
+// The candidates are rescored in float64 -- the reference's own precision: als3.py:112 is numpy float64 -- and ranked;
+// the first k of them are the exact top-k of the WHOLE row if the k-th exact score is > T + E_u.  Rows for which that
+// cannot be shown (near-ties deeper than the K - k spare candidates) are appended to `uncert` and redone exactly over
+// all items by allpairs_exact_rows_kernel.  One warp per row.
+__global__ void __launch_bounds__(256) allpairs_rescore_kernel(const float* __restrict__ U, const float* __restrict__ V,
+                                                               const float* __restrict__ ub, const float* __restrict__ ib,
+                                                               const float* __restrict__ mu, int n_users, int n_items, int dim,
+                                                               int64_t us, int64_t is, const float* __restrict__ cand_val,
+                                                               const int32_t* __restrict__ cand_idx, int K, int k,
+                                                               const float* __restrict__ vmax2, double* __restrict__ out_val,
+                                                               int32_t* __restrict__ out_idx, int32_t* __restrict__ uncert,
+                                                               int32_t* __restrict__ n_uncert) {
+  __shared__ double s_sc[8][AP_MAX_CAND];
+  __shared__ int s_ix[8][AP_MAX_CAND];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + w;
+  if (row >= n_users) return;
+  const float* urow = U + (size_t)row * us;
+  double un2 = 0.0;
+  for (int d = lane; d < dim; d += 32) un2 += (double)urow[d] * (double)urow[d];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) un2 += __shfl_xor_sync(0xffffffffu, un2, o);
+  float T = INFINITY;   // the worst tensor-core score among the candidates
+  int n_cand = 0;
+  for (int j = 0; j < K; ++j) {
+    const int it = cand_idx[(size_t)row * K + j];
+    double sc = -INFINITY;
+    if (it >= 0) {
+      const float* vrow = V + (size_t)it * is;
+      double acc = 0.0;
+      for (int d = lane; d < dim; d += 32) acc += (double)urow[d] * (double)vrow[d];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      sc = ((acc + (double)ub[row]) + (double)ib[it]) + (double)mu[0];   // als3.py:112, in float64 like numpy
+      T = fminf(T, cand_val[(size_t)row * K + j]);
+      ++n_cand;
+    }
+    if (lane == 0) { s_sc[w][j] = sc; s_ix[w][j] = it; }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    // insertion sort: score descending, item index ascending; empty slots (index -1, -inf) last
+    for (int a = 1; a < K; ++a) {
+      const double v = s_sc[w][a];
+      const int ix = s_ix[w][a];
+      int b = a - 1;
+      while (b >= 0 && ix >= 0 && (s_ix[w][b] < 0 || v > s_sc[w][b] || (v == s_sc[w][b] && ix < s_ix[w][b]))) {
+        s_sc[w][b + 1] = s_sc[w][b];
+        s_ix[w][b + 1] = s_ix[w][b];
+        --b;
+      }
+      s_sc[w][b + 1] = v;
+      s_ix[w][b + 1] = ix;
+    }
+    const int kk = k < n_items ? k : n_items;
+    for (int j = 0; j < k; ++j) {
+      out_val[(size_t)row * k + j] = j < n_cand ? s_sc[w][j] : -INFINITY;
+      out_idx[(size_t)row * k + j] = j < n_cand ? s_ix[w][j] : -1;
+    }
+    bool certified = n_cand >= n_items;   // every item is a candidate: nothing outside
+    if (!certified && n_cand >= kk) {
+      const double E = 0.001953125 * sqrt(un2) * sqrt((double)vmax2[0]);   // 2^-9 * ||u|| * max ||v||
+      certified = s_sc[w][kk - 1] > (double)T + E;
+    }
+    if (!certified) uncert[atomicAdd(n_uncert, 1)] = row;
+  }
+}
+
+// max over the item rows of ||v||^2 (float, atomicMax on the bit pattern of a non-negative float); out zeroed by the caller
+__global__ void allpairs_vmax2_kernel(const float* __restrict__ V, int n_items, int dim, int64_t is, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (it >= n_items) return;
+  const float* vrow = V + (size_t)it * is;
+  float n2 = 0.0f;
+  for (int d = lane; d < dim; d += 32) n2 = fmaf(vrow[d], vrow[d], n2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  n2 = n2 * 1.0001f;  // the float sum may round down
+  if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(n2));
+}
+
+// The uncertified rows, redone exactly over ALL items: a persistent CTA per row computes the row's float64 scores into
+// its scratch line, then picks the k best by k rounds of a block-wide arg-max (the total order of ap_better).
+__global__ void __launch_bounds__(1024) allpairs_exact_rows_kernel(const float* __restrict__ U, const float* __restrict__ V,
+                                                                  const float* __restrict__ ub, const float* __restrict__ ib,
+                                                                  const float* __restrict__ mu, int n_items, int dim,
+                                                                  int64_t us, int64_t is, const int32_t* __restrict__ uncert,
+                                                                  const int32_t* __restrict__ n_uncert, int k,
+                                                                  double* __restrict__ scratch, double* __restrict__ out_val,
+                                                                  int32_t* __restrict__ out_idx) {
+  __shared__ float s_u[512];
+  __shared__ double s_v[32];
+  __shared__ int s_i[32];
+  __shared__ double s_last_v;
+  __shared__ int s_last_i;
+  double* line = scratch + (size_t)blockIdx.x * n_items;
+  const int n = *n_uncert;
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    const int row = uncert[e];
+    __syncthreads();
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) s_u[d] = U[(size_t)row * us + d];
+    __syncthreads();
+    const double bu = (double)ub[row], m = (double)mu[0];
+    for (int it = threadIdx.x; it < n_items; it += blockDim.x) {
+      const float* vrow = V + (size_t)it * is;
+      double acc = 0.0;
+      for (int d = 0; d < dim; ++d) acc += (double)s_u[d] * (double)vrow[d];
+      line[it] = ((acc + bu) + (double)ib[it]) + m;
+    }
+    __syncthreads();
+    double last_v = INFINITY;
+    int last_i = -1;
+    for (int r = 0; r < k; ++r) {
+      double bv = -INFINITY;
+      int bi = -1;
+      for (int c = threadIdx.x; c < n_items; c += blockDim.x) {
+        const double v = line[c];
+        const bool after = v < last_v || (v == last_v && c > last_i);
+        if (after && (bi < 0 || v > bv || (v == bv && c < bi))) { bv = v; bi = c; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+      }
+      if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_i[threadIdx.x >> 5] = bi; }
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        bv = s_v[threadIdx.x];
+        bi = s_i[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) {
+          s_last_v = bv;
+          s_last_i = bi;
+          out_val[(size_t)row * k + r] = bi >= 0 ? bv : -INFINITY;
+          out_idx[(size_t)row * k + r] = bi;
+        }
+      }
+      __syncthreads();
+      last_v = s_last_v;
+      last_i = s_last_i;
+      if (last_i < 0) {
+        for (int rr = r + 1 + threadIdx.x; rr < k; rr += blockDim.x) {
+          out_val[(size_t)row * k + rr] = -INFINITY;
+          out_idx[(size_t)row * k + rr] = -1;
+        }
+        break;
+      }
+    }
   }
 }
 
@@ -433,6 +720,109 @@ extern "C" int64_t tfr_allpairs_workspace_bytes(int64_t n_users, int64_t n_items
   return 2 * align_up(n_users * tiles * 4, 256) + 256;
 }
 
+static int launch_allpairs_tc(const float* user_feat, const float* item_feat, const float* user_bias,
+                              const float* item_bias, const float* mu, int64_t n_users, int64_t n_items, int32_t dim,
+                              int64_t user_stride, int64_t item_stride, const ApConsumers& cs, cudaStream_t st) {
+  if (dim % 32 != 0 || dim > 128) {
+    set_error("tcgen05 all-pairs path needs dim %% 32 == 0 and dim <= 128 (got %d): pass use_tensor_cores = 0", dim);
+    return TFR_ERR_INVALID;
+  }
+  TFR_CHECK_ARG(((uintptr_t)user_feat % 16 == 0) && ((uintptr_t)item_feat % 16 == 0));
+  CUtensorMap ma, mb;
+  int rc;
+  if ((rc = make_map(&ma, user_feat, n_users, dim, user_stride))) return rc;
+  if ((rc = make_map(&mb, item_feat, n_items, dim, item_stride))) return rc;
+  const int kch = dim / 32;
+  const size_t smem = (size_t)3 * kch * AP_CHUNK_BYTES + 1024 + 128 + (2 * 256 + 256 + 4 * 128) * 4 + 256 * 8 + 64;
+  const unsigned grid = (unsigned)((n_users + AP_BM - 1) / AP_BM);
+  const bool topk = cs.cand_val != nullptr, obs = cs.obs_indptr != nullptr;
+#define TFR_AP_LAUNCH(KC_, TK_, OB_)                                                                                   \
+  {                                                                                                                    \
+    TFR_CUDA(cudaFuncSetAttribute(allpairs_tc_kernel<KC_, TK_, OB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    allpairs_tc_kernel<KC_, TK_, OB_><<<grid, AP_THREADS, smem, st>>>(ma, mb, user_bias, item_bias, mu, (int)n_users,   \
+                                                                      (int)n_items, cs);                              \
+  }
+#define TFR_AP_CASE(KC_)                                          \
+  if (kch == KC_) {                                               \
+    if (topk && obs) TFR_AP_LAUNCH(KC_, true, true)               \
+    else if (topk) TFR_AP_LAUNCH(KC_, true, false)                \
+    else if (obs) TFR_AP_LAUNCH(KC_, false, true)                 \
+    else TFR_AP_LAUNCH(KC_, false, false)                         \
+  }
+  TFR_AP_CASE(1) TFR_AP_CASE(2) TFR_AP_CASE(3) TFR_AP_CASE(4)
+#undef TFR_AP_CASE
+#undef TFR_AP_LAUNCH
+  TFR_LAUNCH_CHECK();
+  return TFR_OK;
+}
+
+static int ap_exact_ctas() { return 2 * sm_count(); }
+
+extern "C" int64_t tfr_allpairs_topk_workspace_bytes(int64_t n_users, int64_t n_items, int32_t k, int32_t n_cand) {
+  if (n_users < 0 || n_items < 0 || k <= 0 || n_cand < k || n_cand > AP_MAX_CAND) return TFR_ERR_INVALID;
+  return 256 + 2 * align_up(n_users * (int64_t)n_cand * 4, 256) + align_up(n_users * 4, 256) +
+         align_up((int64_t)ap_exact_ctas() * n_items * 8, 256) + 256;
+}
+
+// Per-user top-k ranking over ALL items (forward.py:47-61 for every user at once) and / or the squared error on the
+// observed pairs (als3.py:110-120,139-143), consumed in the epilogue of the tcgen05 GEMM.
+extern "C" int tfr_allpairs_consume(const float* user_feat, const float* item_feat, const float* user_bias,
+                                    const float* item_bias, const float* mu, int64_t n_users, int64_t n_items, int32_t dim,
+                                    int64_t user_stride, int64_t item_stride, int32_t k, int32_t n_cand, double* topk_val,
+                                    int32_t* topk_idx, int32_t* n_uncertified, const int64_t* obs_indptr,
+                                    const int32_t* obs_item, const float* obs_rate, double* row_se, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  if (user_stride == 0) user_stride = dim;
+  if (item_stride == 0) item_stride = dim;
+  TFR_CHECK_ARG(user_stride >= dim && item_stride >= dim);
+  TFR_CHECK_ARG(n_users >= 0 && n_items >= 0 && dim > 0 && n_users < ((int64_t)1 << 31) && n_items < ((int64_t)1 << 31));
+  const bool topk = k > 0;
+  const bool obs = obs_indptr != nullptr;
+  TFR_CHECK_ARG(topk || obs);
+  TFR_CHECK_ARG(!topk || (topk_val && topk_idx && n_uncertified && n_cand >= k && n_cand <= AP_MAX_CAND && dim <= 512));
+  TFR_CHECK_ARG(!obs || (obs_item && obs_rate && row_se));
+  if (n_users == 0 || n_items == 0) return TFR_OK;
+  TFR_CHECK_ARG(user_feat && item_feat && user_bias && item_bias && mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  ApConsumers cs;
+  memset(&cs, 0, sizeof(cs));
+  float* vmax2 = nullptr;
+  int32_t* uncert = nullptr;
+  double* scratch = nullptr;
+  if (topk) {
+    if (!workspace || workspace_bytes < tfr_allpairs_topk_workspace_bytes(n_users, n_items, k, n_cand)) {
+      set_error("all-pairs top-k workspace too small");
+      return TFR_ERR_WORKSPACE;
+    }
+    char* w = reinterpret_cast<char*>(align_up((int64_t)(uintptr_t)workspace, 256));
+    vmax2 = reinterpret_cast<float*>(w); w += 256;
+    cs.cand_val = reinterpret_cast<float*>(w); w += align_up(n_users * (int64_t)n_cand * 4, 256);
+    cs.cand_idx = reinterpret_cast<int32_t*>(w); w += align_up(n_users * (int64_t)n_cand * 4, 256);
+    uncert = reinterpret_cast<int32_t*>(w); w += align_up(n_users * 4, 256);
+    scratch = reinterpret_cast<double*>(w);
+    cs.K = n_cand;
+    TFR_CUDA(cudaMemsetAsync(vmax2, 0, 256, st));
+    TFR_CUDA(cudaMemsetAsync(n_uncertified, 0, sizeof(int32_t), st));
+  }
+  if (obs) { cs.obs_indptr = obs_indptr; cs.obs_item = obs_item; cs.obs_rate = obs_rate; cs.row_se = row_se; }
+  int rc = launch_allpairs_tc(user_feat, item_feat, user_bias, item_bias, mu, n_users, n_items, dim, user_stride,
+                              item_stride, cs, st);
+  if (rc) return rc;
+  if (topk) {
+    allpairs_vmax2_kernel<<<(unsigned)((n_items * 32 + 255) / 256), 256, 0, st>>>(item_feat, (int)n_items, dim, item_stride, vmax2);
+    TFR_LAUNCH_CHECK();
+    allpairs_rescore_kernel<<<(unsigned)((n_users + 7) / 8), 256, 0, st>>>(
+        user_feat, item_feat, user_bias, item_bias, mu, (int)n_users, (int)n_items, dim, user_stride, item_stride,
+        cs.cand_val, cs.cand_idx, n_cand, k, vmax2, topk_val, topk_idx, uncert, n_uncertified);
+    TFR_LAUNCH_CHECK();
+    allpairs_exact_rows_kernel<<<(unsigned)ap_exact_ctas(), 1024, 0, st>>>(user_feat, item_feat, user_bias, item_bias, mu,
+                                                                         (int)n_items, dim, user_stride, item_stride, uncert,
+                                                                         n_uncertified, k, scratch, topk_val, topk_idx);
+    TFR_LAUNCH_CHECK();
+  }
+  return TFR_OK;
+}
+
 extern "C" int tfr_allpairs(const float* user_feat, const float* item_feat, const float* user_bias,
                             const float* item_bias, const float* mu, int64_t n_users, int64_t n_items, int32_t dim,
                             int64_t user_stride, int64_t item_stride, int32_t use_tensor_cores, float* scores,
@@ -446,28 +836,11 @@ extern "C" int tfr_allpairs(const float* user_feat, const float* item_feat, cons
   TFR_CHECK_ARG(user_feat && item_feat && user_bias && item_bias && mu && (scores || best_score || best_item));
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tensor_cores) {
-    if (dim % 32 != 0 || dim > 128) {
-      set_error("tcgen05 all-pairs path needs dim %% 32 == 0 and dim <= 128 (got %d): pass use_tensor_cores = 0", dim);
-      return TFR_ERR_INVALID;
-    }
-    TFR_CHECK_ARG(((uintptr_t)user_feat % 16 == 0) && ((uintptr_t)item_feat % 16 == 0));
-    CUtensorMap ma, mb;
-    int rc;
-    if ((rc = make_map(&ma, user_feat, n_users, dim, user_stride))) return rc;
-    if ((rc = make_map(&mb, item_feat, n_items, dim, item_stride))) return rc;
-    const int kch = dim / 32;
-    const size_t smem = (size_t)3 * kch * AP_CHUNK_BYTES + 1024 + AP_NBARS * 8 + 16 + 2 * 256 * 4;
-    const unsigned grid = (unsigned)((n_users + AP_BM - 1) / AP_BM);
-#define TFR_AP_CASE(KC_)                                                                                      \
-  if (kch == KC_) {                                                                                           \
-    TFR_CUDA(cudaFuncSetAttribute(allpairs_tc_kernel<KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    allpairs_tc_kernel<KC_><<<grid, AP_THREADS, smem, st>>>(ma, mb, user_bias, item_bias, mu, (int)n_users, (int)n_items,   \
-                                                     scores, best_score, best_item);                          \
-  }
-    TFR_AP_CASE(1) TFR_AP_CASE(2) TFR_AP_CASE(3) TFR_AP_CASE(4)
-#undef TFR_AP_CASE
-    TFR_LAUNCH_CHECK();
-    return TFR_OK;
+    ApConsumers cs;
+    memset(&cs, 0, sizeof(cs));
+    cs.scores = scores; cs.best_score = best_score; cs.best_item = best_item;
+    return launch_allpairs_tc(user_feat, item_feat, user_bias, item_bias, mu, n_users, n_items, dim, user_stride,
+                              item_stride, cs, st);
   }
   const int tiles = (int)((n_items + 63) / 64);
   float* tile_best = nullptr;

@@ -402,6 +402,68 @@ extern "C" int tfr_host_pack_feed(const void* users_host, int32_t users_dtype, i
                                     rates_host, rates_dtype, rates_stride, n, staging_host, 0, 0);
 }
 
+// ---- the feed path in two calls -------------------------------------------------------------------------------------------
+extern "C" int tfr_svd_feed_prefetch(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set, const void* users_host,
+                                     int32_t users_dtype, int64_t users_stride, const void* items_host, int32_t items_dtype,
+                                     int64_t items_stride, const void* rates_host, int32_t rates_dtype, int64_t rates_stride,
+                                     int64_t B, void* side_stream) {
+  TFR_CHECK_ARG(t && opt && set && B > 0 && t->dim > 0 && side_stream);
+  TFR_CHECK_ARG(set->h_feed && set->d_feed && set->workspace && set->ev_h2d && set->ev_sorted && set->ev_done);
+  tfr_svd_step_ws ws;
+  int rc = tfr_svd_step_carve(set->workspace, set->workspace_bytes, B, t->dim, &ws);
+  if (rc) return rc;
+  cudaStream_t side = (cudaStream_t)side_stream;
+  if (set->used) TFR_CUDA(cudaEventSynchronize((cudaEvent_t)set->ev_h2d));  // the previous copy out of h_feed is done
+  if ((rc = tfr_host_pack_feed_checked(users_host, users_dtype, users_stride, items_host, items_dtype, items_stride,
+                                       rates_host, rates_dtype, rates_stride, B, set->h_feed, t->user_num, t->item_num)))
+    return rc;
+  // the step that last used this set's device buffers has finished (device-side wait, the host does not block)
+  if (set->used) TFR_CUDA(cudaStreamWaitEvent(side, (cudaEvent_t)set->ev_done, 0));
+  TFR_CUDA(cudaMemcpyAsync(set->d_feed, set->h_feed, 12 * (size_t)B, cudaMemcpyHostToDevice, side));
+  TFR_CUDA(cudaEventRecord((cudaEvent_t)set->ev_h2d, side));
+  const int32_t* ids = static_cast<const int32_t*>(set->d_feed);
+  if ((rc = tfr_dedup_sort_pairs_tl(ids, (int64_t)t->user_num + 1, ws.su_ids, ws.su_pos, ids + B, (int64_t)t->item_num + 1,
+                                    ws.si_ids, ws.si_pos, B, ws.sort_ws, ws.sort_ws_bytes, opt, side)))
+    return rc;
+  TFR_CUDA(cudaEventRecord((cudaEvent_t)set->ev_sorted, side));
+  set->used = 1;
+  return TFR_OK;
+}
+
+extern "C" int tfr_svd_feed_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set, int64_t B, int32_t flags,
+                                 int32_t var_mask, int32_t fetch, void* stream, void* copy_stream) {
+  TFR_CHECK_ARG(t && opt && set && B > 0 && set->used && set->d_feed && set->d_out && fetch >= 0 && fetch <= 2);
+  TFR_CHECK_ARG(fetch == 0 || (copy_stream && set->h_out && set->ev_pred && set->ev_d2h));
+  cudaStream_t s0 = (cudaStream_t)stream, sc = (cudaStream_t)copy_stream;
+  TFR_CUDA(cudaStreamWaitEvent(s0, (cudaEvent_t)set->ev_sorted, 0));
+  if (set->copied) TFR_CUDA(cudaStreamWaitEvent(s0, (cudaEvent_t)set->ev_d2h, 0));  // d_out is about to be overwritten
+  const int32_t* ids = static_cast<const int32_t*>(set->d_feed);
+  const float* rates = reinterpret_cast<const float*>(ids + 2 * B);
+  int rc = run_step(t, opt, ids, ids + B, rates, B, set->d_out, set->d_out + B, flags, var_mask, set->workspace,
+                    set->workspace_bytes, stream, nullptr, 0, nullptr, true, 1);
+  if (rc) return rc;
+  if (fetch) {
+    // the predictions come from the PRE-update tables (A.7): they go back while the table pass runs
+    TFR_CUDA(cudaEventRecord((cudaEvent_t)set->ev_pred, s0));
+    TFR_CUDA(cudaStreamWaitEvent(sc, (cudaEvent_t)set->ev_pred, 0));
+    const size_t off = fetch == 1 ? (size_t)B : 0, cnt = fetch == 1 ? (size_t)B : 2 * (size_t)B;
+    TFR_CUDA(cudaMemcpyAsync(set->h_out + off, set->d_out + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    TFR_CUDA(cudaEventRecord((cudaEvent_t)set->ev_d2h, sc));
+    set->copied = 1;
+  }
+  if ((rc = run_step(t, opt, ids, ids + B, rates, B, set->d_out, set->d_out + B, flags, var_mask, set->workspace,
+                     set->workspace_bytes, stream, nullptr, 0, nullptr, true, 2)))
+    return rc;
+  TFR_CUDA(cudaEventRecord((cudaEvent_t)set->ev_done, s0));
+  return TFR_OK;
+}
+
+extern "C" int tfr_event_synchronize(void* event) {
+  TFR_CHECK_ARG(event);
+  TFR_CUDA(cudaEventSynchronize((cudaEvent_t)event));
+  return TFR_OK;
+}
+
 extern "C" int tfr_event_create(void** event_out) {
   TFR_CHECK_ARG(event_out);
   cudaEvent_t ev = nullptr;

@@ -206,6 +206,80 @@ class SvdEngine:
                                       bi.data_ptr() if want_best else None, ws.data_ptr(), nbytes, self._stream()))
         return dict(scores=scores, best_score=bs, best_item=bi)
 
+    # ---- DISCRETE-branch metrics on the device (svd_train_val.py:94-98,138-143) ----------------------------------------
+    def binary_metrics(self, logits, labels):
+        """-> dict(nll_sum, n_correct, auc, n_pos, n): summed sigmoid cross-entropy (cost_nll), number of correct
+        round(sigmoid(logits)), roc_auc_score(labels, sigmoid(logits)) -- computed on the device (tfr_binary_metrics:
+        sort-based AUC reusing the step's radix sort); 32 bytes come back instead of the logits."""
+        lg, lb = self._dev_f32(logits), self._dev_f32(labels)
+        n = lg.numel()
+        nbytes = check(self.L.tfr_binary_metrics_workspace_bytes(n))
+        key = ("metrics_ws", nbytes)
+        ws = self._stage.get(key)
+        if ws is None:
+            ws = self._stage[key] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        out = torch.empty(4, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.L.tfr_binary_metrics(lg.data_ptr(), lb.data_ptr(), n, ws.data_ptr(), nbytes, out.data_ptr(),
+                                            self._stream()))
+        o = out.cpu().numpy()
+        return dict(nll_sum=float(o[0]), n_correct=int(round(o[1])), auc=float(o[2]), n_pos=int(round(o[3])), n=n)
+
+    def last_step_metrics(self, B):
+        """binary_metrics of the step train_step_host issued LAST, from its device-resident logits and ratings (the
+        staging set it used): the DISCRETE branch's per-step train metrics without a second pass over host arrays."""
+        hs = self._host_state.get(B)
+        if hs is None:
+            raise TfrError("no host-fed step of batch size %d has run" % B)
+        k = (hs["next"] - 1 - len(hs["pending"])) % self.N_FEED_SETS
+        st = self._host_set(B, k)
+        return self.binary_metrics(st["d_out"][:B], st["d_feed"][2 * B:].view(torch.float32))
+
+    # ---- all-pairs consumers fused into the GEMM epilogue ------------------------------------------------------------
+    def rank_all_users(self, k=50, n_cand=None):
+        """forward.py:47-61 for EVERY user in one sweep of the tcgen05 GEMM: -> (items [U, k] int32, scores [U, k]
+        float64, n_uncertified).  Identical to ranking the float64 score matrix of als3.py:112 (score descending, lowest
+        item id on ties): tensor-core candidates, float64 rescore, certificate, exact fallback (tfr_allpairs_consume)."""
+        k = int(min(k, self.I))
+        if n_cand is None:
+            n_cand = min(128, max(k + 14, 8))
+        dev = self.device
+        idx = torch.empty(self.U, k, dtype=torch.int32, device=dev)
+        val = torch.empty(self.U, k, dtype=torch.float64, device=dev)
+        n_unc = torch.zeros(1, dtype=torch.int32, device=dev)
+        nbytes = check(self.L.tfr_allpairs_topk_workspace_bytes(self.U, self.I, k, n_cand))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(self.L.tfr_allpairs_consume(self.t["user_feat"].data_ptr(), self.t["item_feat"].data_ptr(),
+                                              self.t["user_bias"].data_ptr(), self.t["item_bias"].data_ptr(),
+                                              self.t["mu"].data_ptr(), self.U, self.I, self.d, self.feat_stride,
+                                              self.feat_stride, k, n_cand, val.data_ptr(), idx.data_ptr(), n_unc.data_ptr(),
+                                              None, None, None, None, ws.data_ptr(), nbytes, self._stream()))
+        return idx, val, int(n_unc.item())
+
+    def observed_rmse(self, users, items, rates):
+        """als3.py:110-120,139-143: RMSE of M[user_ids, work_ids] against the ratings, with M = U.V^T + biases consumed
+        tile by tile in the GEMM epilogue (never materialised).  -> (rmse, row_se [U] float64)."""
+        self._check_ids(users, items)
+        dev = self.device
+        u = torch.as_tensor(np.asarray(users), device=dev).to(torch.int64)
+        i = torch.as_tensor(np.asarray(items), device=dev).to(torch.int64)
+        r = torch.as_tensor(np.asarray(rates), device=dev).to(torch.float32)
+        order = torch.argsort(u * self.I + i, stable=True)     # CSR by user, item ids ascending inside a user
+        indptr = torch.zeros(self.U + 1, dtype=torch.int64, device=dev)
+        indptr[1:] = torch.cumsum(torch.bincount(u, minlength=self.U), 0)
+        it = i[order].to(torch.int32).contiguous()
+        rt = r[order].contiguous()
+        row_se = torch.empty(self.U, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(self.L.tfr_allpairs_consume(self.t["user_feat"].data_ptr(), self.t["item_feat"].data_ptr(),
+                                              self.t["user_bias"].data_ptr(), self.t["item_bias"].data_ptr(),
+                                              self.t["mu"].data_ptr(), self.U, self.I, self.d, self.feat_stride,
+                                              self.feat_stride, 0, 0, None, None, None, indptr.data_ptr(), it.data_ptr(),
+                                              rt.data_ptr(), row_se.data_ptr(), None, 0, self._stream()))
+        n = max(int(u.numel()), 1)
+        return float(torch.sqrt(row_se.sum() / n)), row_se
+
     # ---- ranking: forward.py:47-61 get_ranking (every item scored for one user, sorted, first 50 kept) --------------
     def get_ranking(self, users, k=50):
         """-> (items [n, k] int32, scores [n, k]) for a user id or a sequence of them: the k best items of each user in
@@ -255,105 +329,88 @@ class SvdEngine:
             a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
         return a, a.ctypes.data, self._FEED_DTYPES[a.dtype], (a.strides[0] if a.size else a.itemsize)
 
-    # The feed path is a two-set pipeline.  prefetch_host(batch) packs the columns into one pinned staging buffer (value
-    # cast + range check in C), copies it to the device and sorts its ids on the SIDE stream -- all of which needs no
-    # table data, so it runs under the previous step's table pass.  train_step_host(batch) then issues forward +
-    # segment sums, copies the predictions (they come from the PRE-update tables) back on a copy stream
-    # while the Adam pass runs, and returns as soon as the predictions are on the host.  A driver that owns its
-    # iterator (svd_train_val.py) hands over batch t+1 right after step t returns; a plain sess.run(feed_dict) without
-    # a prefetch does the same work in line.  Every reuse of a staging buffer is ordered by an event: the pinned
-    # buffer is never repacked while a copy from it is queued (also with fetch=False, which does not synchronise).
+    # The feed path is a ring of staging sets driven by two C calls (tfr_svd_feed_prefetch / tfr_svd_feed_step).
+    # prefetch_host(batch) packs the columns into a pinned staging buffer (value cast + range check in C), copies it to
+    # the device and sorts its ids on the SIDE stream -- all of which needs no table data, so it runs under the previous
+    # step's table pass.  train_step_host(batch) then issues forward + segment sums, copies the predictions (they come
+    # from the PRE-update tables) back on a copy stream while the Adam pass runs, and returns as soon as the
+    # predictions are on the host.  A driver that owns its iterator (svd_train_val.py) hands over batch t+1 BEFORE it
+    # asks for step t (two batches may be pending), so that its host work overlaps step t on the device; a plain
+    # sess.run(feed_dict) without a prefetch does the same work in line.  Every reuse of a staging set is ordered by
+    # its events: the pinned buffer is never repacked while a copy from it is queued (also with fetch=False, which does
+    # not synchronise), the device buffers never overwritten while a step still reads them.
+    N_FEED_SETS = 3
+
     def _host_set(self, B, k):
         key = ("host", B, k)
         st = self._stage.get(key)
         if st is None:
             ws = self.workspace((B, "h", k))
-            carved = StepWs()
-            check(self.L.tfr_svd_step_carve(ws.data_ptr(), ws.numel(), B, self.d, C.byref(carved)))
+            fs = _lib.FeedSet()
             st = dict(h_feed=torch.empty(3 * B, dtype=torch.int32).pin_memory(),
                       d_feed=torch.empty(3 * B, dtype=torch.int32, device=self.device),
                       d_out=torch.empty(2 * B, dtype=torch.float32, device=self.device),
-                      h_out=torch.empty(2 * B, dtype=torch.float32).pin_memory(),
-                      ws=ws, carved=carved, used=False, copied=False,
-                      ev_h2d=torch.cuda.Event(), ev_sorted=torch.cuda.Event(), ev_pred=torch.cuda.Event(),
-                      ev_d2h=torch.cuda.Event(), ev_done=torch.cuda.Event())
+                      h_out=torch.empty(2 * B, dtype=torch.float32).pin_memory(), ws=ws, fs=fs, events=[])
+            fs.h_feed, fs.d_feed = st["h_feed"].data_ptr(), st["d_feed"].data_ptr()
+            fs.d_out, fs.h_out = st["d_out"].data_ptr(), st["h_out"].data_ptr()
+            fs.workspace, fs.workspace_bytes = ws.data_ptr(), ws.numel()
+            with torch.cuda.device(self.device):
+                for f in ("ev_h2d", "ev_sorted", "ev_pred", "ev_d2h", "ev_done"):
+                    ev = C.c_void_p()
+                    check(self.L.tfr_event_create(C.byref(ev)))
+                    setattr(fs, f, ev.value)
+                    st["events"].append(ev.value)
             self._stage[key] = st
         return st
 
     def prefetch_host(self, users, items, rates):
-        """Hands over the NEXT batch early: pack -> H2D -> id sort on the side stream, under whatever the main stream
-        is doing (normally the previous step's table pass).  The following train_step_host must get these very
-        arrays; a different batch simply drops the prefetched one."""
+        """Hands over a coming batch early: pack -> H2D -> id sort on the side stream, under whatever the main stream
+        is doing (normally the current step's table pass).  Up to N_FEED_SETS - 1 batches may be pending; they must be
+        stepped in the order they were handed over (train_step_host with these very arrays) -- a different batch
+        drops everything that is pending."""
         B = len(users)
-        hs = self._host_state.setdefault(B, dict(next=0, pending=None))
-        k = hs["pending"][0] if hs["pending"] is not None else hs["next"]
+        hs = self._host_state.setdefault(B, dict(next=0, pending=[]))
+        if len(hs["pending"]) >= self.N_FEED_SETS - 1:
+            raise TfrError("too many batches pending: step one before prefetching another")
+        k = hs["next"]
+        hs["next"] = (k + 1) % self.N_FEED_SETS
         st = self._host_set(B, k)
         ku, pu, du, su = self._feed_col(users)
         ki, pi, di, si = self._feed_col(items)
         kr, pr, dr, sr = self._feed_col(rates)
-        if st["used"]:
-            st["ev_h2d"].synchronize()   # the previous copy out of this pinned buffer has completed
-        # value cast float64 -> int32, like TF feeding an int32 placeholder (A.7), straight into the pinned buffer;
-        # ids outside the tables are an error here, before anything is launched (TF's lookup raises as well)
-        check(self.L.tfr_host_pack_feed_checked(pu, du, su, pi, di, si, pr, dr, sr, B, st["h_feed"].data_ptr(),
-                                                self.U, self.I))
-        side = self.side_streams[0]
         with torch.cuda.device(self.device):
-            if st["used"]:
-                side.wait_event(st["ev_done"])   # the step that last used this set's device buffers has finished
-            with torch.cuda.stream(side):
-                st["d_feed"].copy_(st["h_feed"], non_blocking=True)
-                st["ev_h2d"].record(side)
-                w = st["carved"]
-                d = st["d_feed"]
-                check(self.L.tfr_dedup_sort_pairs_tl(d.data_ptr(), self.U + 1, w.su_ids, w.su_pos, d.data_ptr() + 4 * B,
-                                                     self.I + 1, w.si_ids, w.si_pos, B, w.sort_ws, w.sort_ws_bytes,
-                                                     self.opt.data_ptr(), side.cuda_stream))
-                st["ev_sorted"].record(side)
-        st["used"] = True
-        hs["pending"] = (k, users, items, rates)
+            check(self.L.tfr_svd_feed_prefetch(C.byref(self.tables_struct), self.opt.data_ptr(), C.byref(st["fs"]), pu, du,
+                                               su, pi, di, si, pr, dr, sr, B, self.side_streams[0].cuda_stream))
+        hs["pending"].append((k, users, items, rates))
 
     def train_step_host(self, users, items, rates, fetch=True):
         B = len(users)
-        hs = self._host_state.setdefault(B, dict(next=0, pending=None))
+        hs = self._host_state.setdefault(B, dict(next=0, pending=[]))
         pend = hs["pending"]
-        if pend is None or pend[1] is not users or pend[2] is not items or pend[3] is not rates:
+        if not pend or pend[0][1] is not users or pend[0][2] is not items or pend[0][3] is not rates:
+            pend.clear()   # not the batch that was handed over: drop what is pending
             self.prefetch_host(users, items, rates)
-            pend = hs["pending"]
-        k = pend[0]
-        hs["pending"], hs["next"] = None, 1 - k
+        k = pend.pop(0)[0]
         st = self._host_set(B, k)
-        d = st["d_feed"]
+        # the README head is the identity (infer == logits): one array goes back instead of two
+        identity_head = not (self.flags & LOSS_SIGMOID_CE)
+        mode = 0 if not fetch else (1 if identity_head else 2)
         with torch.cuda.device(self.device):
-            main = torch.cuda.current_stream(self.device)
-            main.wait_event(st["ev_sorted"])
-            if st["copied"]:
-                main.wait_event(st["ev_d2h"])   # d_out is about to be overwritten: its last copy out must be done
-
-            def phase(p):
-                check(self.L.tfr_svd_train_step_presorted(C.byref(self.tables_struct), self.opt.data_ptr(), d.data_ptr(),
-                                                          d.data_ptr() + 4 * B, d.data_ptr() + 8 * B, B,
-                                                          st["d_out"].data_ptr(), st["d_out"].data_ptr() + 4 * B,
-                                                          self.flags, self.var_mask, p, st["ws"].data_ptr(),
-                                                          st["ws"].numel(), main.cuda_stream))
-            phase(1)
-            if fetch:
-                st["ev_pred"].record(main)
-                self._copy_stream.wait_event(st["ev_pred"])
-                with torch.cuda.stream(self._copy_stream):
-                    st["h_out"].copy_(st["d_out"], non_blocking=True)
-                    st["ev_d2h"].record(self._copy_stream)
-                st["copied"] = True
-            phase(2)
-            st["ev_done"].record(main)
+            check(self.L.tfr_svd_feed_step(C.byref(self.tables_struct), self.opt.data_ptr(), C.byref(st["fs"]), B,
+                                           self.flags, self.var_mask, mode, self._stream(), self._copy_stream.cuda_stream))
         if not fetch:
             return None
-        st["ev_d2h"].synchronize()
-        out = st["h_out"].numpy().copy()   # one copy out of the pinned buffer; the two results are views of it
+        check(self.L.tfr_event_synchronize(st["fs"].ev_d2h))
+        if identity_head:
+            out = st["h_out"][B:].numpy().copy()   # one copy out of the pinned buffer
+            return out, out
+        out = st["h_out"].numpy().copy()
         return out[:B], out[B:]
 
+    def d2h_bytes(self, B):
+        return (4 if not (self.flags & LOSS_SIGMOID_CE) else 8) * B
+
     h2d_bytes = staticmethod(lambda B: 12 * B)
-    d2h_bytes = staticmethod(lambda B: 8 * B)
 
     # ---- device-resident training data + pre-drawn index stream (dataio.ShuffleIterator on the device) ------
     def set_train_data(self, col_user, col_item, col_rate):
@@ -377,6 +434,11 @@ class SvdEngine:
             if getattr(self, "_fj_events", None) is not None and self._fj_events[k_]:
                 self.L.tfr_event_destroy(self._fj_events[k_])
                 self._fj_events[k_] = None
+        for st in getattr(self, "_stage", {}).values():
+            if isinstance(st, dict) and st.get("events"):
+                for ev in st["events"]:
+                    self.L.tfr_event_destroy(ev)
+                st["events"] = []
 
     def __del__(self):
         try:

@@ -66,6 +66,72 @@ def df_to_sparse(df, active_agents, user_num, item_num, qmatrix=None, skill_wins
     return hstack([X[a] for a in active_agents if a != "extra"]).tocsr()
 
 
+def df_to_sparse_device(df, active_agents, user_num, item_num, qmatrix=None, skill_wins=None, skill_fails=None,
+                        device=None):
+    """df_to_sparse built as CSR directly in HBM (tfr_ktm_csr_indptr / tfr_ktm_csr_fill: count -> scan -> fill): the
+    event columns, the q-matrix and the per-event skill counters are uploaded once, the design matrix itself never
+    exists on the host.  -> (indptr int64 [n+1], indices int32 [nnz], data float32 [nnz], n_cols), torch CUDA tensors.
+    Same matrix as df_to_sparse (explicit zeros of the counter blocks kept, zero sums of `attempts` dropped, as scipy
+    does)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    from ._lib import check
+    L = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.TfrError("tf-recomm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback for this path")
+    dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+    n = len(df)
+    if qmatrix is None:
+        qmatrix = diags([1.0] * item_num).tocsr()
+    q = csr_matrix(qmatrix)
+    n_skills = q.shape[1]
+    width = dict(users=user_num, items=item_num, skills=n_skills, attempts=n_skills, wins=n_skills, fails=n_skills,
+                 item_wins=item_num, item_fails=item_num)
+    agents = [a for a in active_agents if a != "extra"]
+    need_counters = [a for a in agents if a in ("attempts", "wins", "fails")]
+    if need_counters and skill_wins is None:
+        raise ValueError("agents %s need skill_wins.npz / skill_fails.npz" % need_counters)
+    kinds = (C.c_int32 * 8)(*[AGENT_ORDER.index(a) for a in agents])
+    col0, at = [], 0
+    for a in agents:
+        col0.append(at)
+        at += width[a]
+    col0_arr = (C.c_int32 * 8)(*col0)
+
+    def up(a, dt):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+
+    def csr3(m):
+        if m is None:
+            return None, None, None
+        m = csr_matrix(m, copy=True)
+        m.sort_indices()   # column order inside a row (explicit zeros stay): the blocks are emitted in this order
+        return up(m.indptr, np.int64), up(m.indices, np.int32), up(m.data, np.float32)
+    user, item = up(df["user"], np.int32), up(df["item"], np.int32)
+    if n and (int(user.min()) < 0 or int(user.max()) >= user_num or int(item.min()) < 0 or int(item.max()) >= item_num):
+        raise _lib.TfrError("indices out of range in the event log")
+    wins_col, fails_col = up(df["wins"], np.float32), up(df["fails"], np.float32)
+    qp, qi, qd = csr3(q)
+    swp, swi, swd = csr3(skill_wins)
+    sfp, sfi, sfd = csr3(skill_fails)
+    ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    nbytes = check(L.tfr_ktm_workspace_bytes(n))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    indptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        common = (user.data_ptr(), item.data_ptr(), wins_col.data_ptr(), fails_col.data_ptr(), ptr(qp), ptr(qi), ptr(qd),
+                  ptr(swp), ptr(swi), ptr(swd), ptr(sfp), ptr(sfi), ptr(sfd), n, kinds, col0_arr, len(agents))
+        check(L.tfr_ktm_csr_indptr(*common, indptr.data_ptr(), ws.data_ptr(), nbytes, st))
+        nnz = int(indptr[-1].item())
+        indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
+        data = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)[:nnz]
+        check(L.tfr_ktm_csr_fill(*common, indptr.data_ptr(), indices.data_ptr() if nnz else None,
+                                 data.data_ptr() if nnz else None, st) if nnz else 0)
+    return indptr, indices, data, at
+
+
 def load_dataset(dataset, data_folder="data"):
     """What fm.py:34-51 loads: (df, config, qmatrix, skill_wins | None, skill_fails | None)."""
     from . import dataio
