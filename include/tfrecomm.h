@@ -129,6 +129,7 @@ typedef struct {
    * of the forward and of the partner rows in the backward; the users/items arrays given to the step are then
    * LOCAL row indices, with the value user_num / item_num marking occurrences owned by another rank. */
   const float *g_user_feat, *g_item_feat, *g_user_bias, *g_item_bias;
+  int64_t g_stride; /* floats between consecutive rows of g_user_feat / g_item_feat; 0 = dim */
 } tfr_svd_tables;
 
 /* ---- forward only: replaces sess.run([logits, infer]) at svd_train_val.py:121-122 -----------
@@ -293,6 +294,42 @@ int tfr_shard_gather_rows(const float* feat_local, const float* bias_local, int6
                           int64_t feat_stride /* floats between rows of feat_local; 0 = dim */, const int32_t* ids,
                           int64_t B, int32_t n_ranks, int32_t rank, float* out_feat, float* out_bias,
                           int32_t* local_keys, void* stream);
+
+/* ---- row-sharded tables, the all-to-all exchange north_star names (ids -> rows back -> gradient records to the owners) ----
+ * Per step every rank holds a slice of the global batch (contiguous in global batch order).  Records are dim + 4 floats:
+ * [row | bias or e | pad].  The NCCL all-to-alls between these calls are the caller's (torch.distributed).
+ *  tfr_shard_bucket: the slice's ids bucketed by owner (id mod n_ranks), stably -> counts [2 * n_ranks] (users to rank g,
+ *    then items to rank g), send_ids [2n] = local row ids (id / n_ranks) in the combined layout [dst 0: users | items]
+ *    [dst 1: ...], slot_u / slot_i [n] = index of occurrence p's user / item entry in that layout.
+ *  tfr_shard_gather_records: owner side -- the rows asked for (recv_ids in the combined layout by SOURCE rank, the per-
+ *    source counts cnt_u_host / cnt_i_host on the host) packed as records.
+ *  tfr_shard_fwd_records: requester side -- forward (ops.py:44-47) + d cost/d logits (ops.py:124-126) on the slice from
+ *    the records that came back; for every occurrence one outgoing record per table, at the same index: [PARTNER row | e].
+ *    logits / infer [n] of the slice; sums2 (device, 2 doubles) = this rank's [sum e, sum (rate - infer)^2], to be
+ *    all-reduced (sum) over the ranks.
+ *  tfr_shard_owner_prepare: owner side -- sort keys of both tables over the received records (the other table's entries
+ *    get the "not mine" mark users_local / items_local), err [total] by arrival position, and the all-reduced sums as
+ *    the fp32 / float64 scalars the step's finish takes.
+ *  tfr_svd_train_step_gathered: the single-GPU step from the sort on, on tables with g_* set (partner rows by arrival
+ *    position, stride g_stride) and ws.err prefilled: stable sort, ordered segment sums, ONE Adam pass, finish.
+ *    Arrival position ascends with (source rank, position in its slice) = global batch order. */
+int64_t tfr_shard_bucket_workspace_bytes(int64_t n);
+int tfr_shard_bucket(const int32_t* users, const int32_t* items, int64_t n, int32_t n_ranks, int32_t* counts,
+                     int32_t* send_ids, int32_t* slot_u, int32_t* slot_i, void* workspace, int64_t workspace_bytes,
+                     void* stream);
+int tfr_shard_gather_records(const tfr_svd_tables* t, const int32_t* recv_ids, const int32_t* cnt_u_host,
+                             const int32_t* cnt_i_host, int32_t n_ranks, float* records, void* stream);
+int tfr_shard_fwd_records(const tfr_svd_tables* t, const tfr_opt_scalars* opt, const float* records_in,
+                          const int32_t* slot_u, const int32_t* slot_i, const float* rates, int64_t n, float* records_out,
+                          float* logits, float* infer, float* partials /* [TFR_MAX_PARTIALS] scratch */,
+                          double* se_partials /* [TFR_MAX_PARTIALS] scratch */, double* sums2, void* stream);
+int tfr_shard_owner_prepare(const int32_t* recv_ids, const float* records, const int32_t* cnt_u_host,
+                            const int32_t* cnt_i_host, int32_t n_ranks, int32_t dim, int64_t users_local, int64_t items_local,
+                            int32_t* keys_u, int32_t* keys_i, float* err, const double* sums2_allreduced, float* sum_err,
+                            double* sum_se, void* stream);
+int tfr_svd_train_step_gathered(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* keys_u, const int32_t* keys_i,
+                                int64_t n, int32_t flags, int32_t var_mask, const float* sum_err, const double* sum_se,
+                                void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- FM forward: replaces forward.py:21-22 `fma` ---------------------------------------------
  * yhat[r] = w0 + sum_i W_i x_i + 0.5 * sum_f ((sum_i V_if x_i)^2 - sum_i V_if^2 x_i^2) on CSR rows

@@ -19,7 +19,10 @@ RTOL = 1e-5   # north_star: per-step parameters within 1e-5 relative (fp32)
 ATOL = 2e-7   # absolute floor for entries near zero (tables are O(1e-2), updates O(lr))
 
 
-EXEMPT = 1e-3   # fraction of entries allowed outside the element-wise bound (see assert_fp32_close)
+# Fraction of an array's entries allowed outside the element-wise bound (see assert_fp32_close).  Measured over every
+# comparison of this file (round 2, B200: 116 M entries in 1,786 arrays): 239 entries outside in all (2e-6), worst single
+# array 8 of 128,000 (6.3e-5); the ML-25M full-size run: 66 of 20.8 M (3e-6) -- gpurun_out/parity_stats.json, DESIGN.md 4.
+EXEMPT = 1e-4
 PARITY_STATS = []   # every assert_fp32_close call: what, size, relative L2, entries outside, max abs error
 
 
@@ -60,11 +63,11 @@ def both(U, I, d, lr, reg, flags=0, var_mask=31, seed=1, bias_init="truncated_no
 
 
 def assert_fp32_close(got, ref, what, max_abs=None, rtol=RTOL):
-    """The 1e-5 bar, stated so that it is attainable in fp32: (1) the relative L2 error of the whole array is
-    <= 1e-5; (2) element-wise |d| <= 1e-5*|ref| + 1e-5*rms(ref) for all but <= 0.1% of the entries.  The
-    exempted entries are sums that cancel (a gradient sum ~0 whose sign any fp32 summation order can flip, which
-    Adam's m/(sqrt(v)+eps) then turns into a step of up to lr): no two fp32 orders agree on those, TF's own
-    included.  (3) optionally a hard bound on the largest absolute error."""
+    """The 1e-5 bar: (1) the relative L2 error of the whole array is <= 1e-5; (2) element-wise |d| <= 1e-5*|ref| +
+    1e-5*rms(ref) for all but <= EXEMPT (1e-4) of the entries -- sums whose terms cancel, so that the fp32 result
+    depends on the order of the adds (the kernel's dot products and tile-boundary regrouping differ from the oracle's
+    order); measured rates are two orders of magnitude below the allowance; (3) optionally a hard bound on the largest
+    absolute error."""
     got = np.asarray(got, np.float64).reshape(-1)
     ref = np.asarray(ref, np.float64).reshape(-1)
     d = np.abs(got - ref)
@@ -781,19 +784,20 @@ def _rank_f64(M, k):
     return np.stack([np.lexsort((np.arange(I), -M[u]))[:k] for u in range(M.shape[0])]).astype(np.int32)
 
 
-@pytest.mark.parametrize("U,I,d,k,n_cand,ties", [(300, 1000, 64, 50, 64, False), (129, 777, 128, 50, 64, True),
-                                                 (257, 40, 32, 50, 64, False), (64, 3000, 96, 1, 8, True),
-                                                 (500, 2048, 128, 10, 16, False)])
+@pytest.mark.parametrize("U,I,d,k,n_cand,ties", [(300, 1000, 64, 50, 64, 0), (129, 777, 128, 50, 64, 5),
+                                                 (257, 40, 32, 50, 64, 0), (64, 3000, 96, 1, 8, 5),
+                                                 (500, 2048, 128, 10, 16, 0), (70, 900, 64, 50, 64, 1)])
 def test_allpairs_topk_equals_float64_ranking(U, I, d, k, n_cand, ties):
     """The fused ranking consumer (tensor-core candidates -> float64 rescore -> certificate -> exact fallback) returns
     EXACTLY the ranking of the float64 score matrix of als3.py:112 / forward.py:47-61: same items in the same order
-    (lowest id on ties), whatever tf32 did to the tensor-core scores.  Exact ties between groups of items force rows
-    through the uncertified path."""
+    (lowest id on ties), whatever tf32 did to the tensor-core scores.  ties = 5: every fifth item is a copy of item 0
+    (exact ties inside the ranking); ties = 1: ALL items are copies of item 0, so no row can be certified (the k-th
+    exact score equals the worst candidate's) and every row goes through the exact fallback."""
     tabs = init.init_tables(U, I, d, seed=21, bias_init="truncated_normal")
     tabs["user_feat"] *= 25; tabs["item_feat"] *= 25
     if ties:
-        tabs["item_bias"][::5] = tabs["item_bias"][0]
-        tabs["item_feat"][::5] = tabs["item_feat"][0]
+        tabs["item_bias"][::ties] = tabs["item_bias"][0]
+        tabs["item_feat"][::ties] = tabs["item_feat"][0]
     eng = SvdEngine(U, I, d, 1e-3, 0.05, tables=tabs)
     idx, val, n_unc = eng.rank_all_users(k=k, n_cand=n_cand)
     M = _f64_scores(tabs)
@@ -803,8 +807,8 @@ def test_allpairs_topk_equals_float64_ranking(U, I, d, k, n_cand, ties):
     assert got.shape == (U, kk)
     assert np.array_equal(got, ref), "%d rows differ (n_uncertified %d)" % (int((got != ref).any(axis=1).sum()), n_unc)
     np.testing.assert_allclose(val.cpu().numpy(), np.take_along_axis(M, ref.astype(np.int64), axis=1), rtol=1e-12, atol=1e-12)
-    if ties:
-        assert n_unc > 0      # the exact path was exercised
+    if ties == 1:
+        assert n_unc == U     # the exact path was exercised, for every row
     assert 0 <= n_unc <= U
 
 
@@ -920,3 +924,81 @@ def test_ktm_design_matrix_built_on_device_equals_scipy(agents, golden_dir):
         for m in (a, b):
             m.eliminate_zeros(); m.sort_indices()
         assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices) and np.array_equal(a.data, b.data)
+
+
+# ---- the all-to-all exchange of the row-sharded path (north_star) emulated on ONE GPU: G virtual ranks, every NCCL
+# all_to_all_single replaced by the slicing it performs -----------------------------------------------------------------
+def _a2a_emulated_step(engs, users, items, rates):
+    from tf_recomm_b200 import sharding
+    G = len(engs)
+    B = len(users)
+    cuts = [sharding.batch_slice(B, G, r) for r in range(G)]
+    plans = [e.a2a_bucket(users[lo:hi], items[lo:hi]) for e, (lo, hi) in zip(engs, cuts)]
+    cnt = np.stack([p["counts"].cpu().numpy() for p in plans]).astype(np.int64)        # [src, 2G]
+    per_dst = cnt[:, :G] + cnt[:, G:]                                                   # [src, dst] entries src sends to dst
+    send_off = np.concatenate([np.zeros((G, 1), np.int64), np.cumsum(per_dst, axis=1)], axis=1)   # [src, dst]
+    recv_off = np.concatenate([np.zeros((1, G), np.int64), np.cumsum(per_dst, axis=0)], axis=0)   # [src, dst]: offset at dst
+
+    def a2a(bufs):        # bufs[src]: rows in src's combined send layout -> list over dst of the received buffers
+        return [torch.cat([bufs[s][send_off[s, g]:send_off[s, g + 1]] for s in range(G)]) for g in range(G)]
+
+    def a2a_back(bufs):   # bufs[dst]: rows in dst's receive layout -> list over src, in src's send layout
+        return [torch.cat([bufs[g][recv_off[s, g]:recv_off[s + 1, g]] for g in range(G)]) for s in range(G)]
+    recv_ids = a2a([p["send_ids"] for p in plans])
+    recs = [e.a2a_gather(recv_ids[g], cnt[:, g], cnt[:, G + g]) for g, e in enumerate(engs)]
+    rec_in = a2a_back(recs)
+    fw = [e.a2a_forward(p, rec_in[s], rates[lo:hi]) for s, (e, p, (lo, hi)) in enumerate(zip(engs, plans, cuts))]
+    sums = torch.stack([f[3] for f in fw]).sum(0)                                      # the all-reduce
+    grads_in = a2a([f[0] for f in fw])
+    for g, e in enumerate(engs):
+        e.a2a_owner_step(recv_ids[g], grads_in[g], cnt[:, g], cnt[:, G + g], sums.clone(), plans[g]["n"])
+    return np.concatenate([f[1].cpu().numpy() for f in fw]), np.concatenate([f[2].cpu().numpy() for f in fw])
+
+
+@pytest.mark.parametrize("G,U,I,d,B,flags", [(2, 301, 157, 20, 500, 0), (4, 1000, 333, 128, 2048, 0), (8, 97, 61, 15, 203, 0),
+                                             (3, 50, 7, 32, 64, 0), (4, 400, 90, 64, 1000, _lib.FORK_FLAGS & ~_lib.OPT_SGD)])
+def test_sharded_a2a_step_matches_oracle(G, U, I, d, B, flags):
+    """ids -> rows back -> gradient records to the owners, each rank forwarding only its B/G slice and summing only the
+    rows it owns: the re-assembled shards follow the single-table oracle, and every occurrence's prediction matches."""
+    from tf_recomm_b200.sharded import ShardedSvdEngine
+    rng = np.random.default_rng(G * 100 + d)
+    tabs = init.init_tables(U, I, d, seed=2, bias_init="truncated_normal")
+    orc = oracle.SvdOracle(tabs["mu"], tabs["user_bias"], tabs["item_bias"], tabs["user_feat"], tabs["item_feat"], 1e-3, 0.05,
+                           flags=flags)
+    engs = [ShardedSvdEngine(U, I, d, 1e-3, 0.05, rank=r, world=G, tables=tabs, flags=flags) for r in range(G)]
+    for step in range(6):
+        users, items, rates = make_batch(rng, U, I, B, binary=bool(flags))
+        logits, infer = _a2a_emulated_step(engs, users, items, rates)
+        ref_logits, ref_infer = orc.train_step(users, items, rates)
+        np.testing.assert_allclose(logits, ref_logits, rtol=RTOL, atol=1e-6)
+        for name in ("user_feat", "item_feat", "user_bias", "item_bias"):
+            assert_fp32_close(eng_table(engs, name, G), getattr(orc, name), "a2a step %d %s" % (step, name), max_abs=4e-3 + 1e-6)
+        for e in engs:
+            assert_fp32_close(e.local.t["mu"].cpu().numpy(), orc.mu, "a2a mu")
+            assert e.local.global_step == step + 1 and e.local.live_slots() == 0
+
+
+def test_sharded_a2a_agrees_with_allreduce_exchange():
+    """The two exchanges feed the same ordered segment sums with the same per-occurrence errors (the a2a forward uses the
+    forward kernel's arithmetic and reduction order); only the fold of sum_b e_b for bias_global differs (per-slice sums
+    all-reduced against one fold over the batch), so the shards agree to fp32 rounding."""
+    from tf_recomm_b200.sharded import ShardedSvdEngine
+    G, U, I, d, B = 4, 500, 200, 128, 1024
+    rng = np.random.default_rng(3)
+    tabs = init.init_tables(U, I, d, seed=2, bias_init="truncated_normal")
+    ea = [ShardedSvdEngine(U, I, d, 1e-3, 0.05, rank=r, world=G, tables=tabs) for r in range(G)]
+    eb = [ShardedSvdEngine(U, I, d, 1e-3, 0.05, rank=r, world=G, tables=tabs) for r in range(G)]
+    for step in range(4):
+        users, items, rates = make_batch(rng, U, I, B)
+        _a2a_emulated_step(ea, users, items, rates)
+        du, di, dr = (eb[0].local._dev_i32(users), eb[0].local._dev_i32(items), eb[0].local._dev_f32(rates))
+        bufs = [e._buffers(B) for e in eb]
+        for e, b in zip(eb, bufs):
+            e.gather_owned(du, di, b)
+        total = torch.stack([b["flat"] for b in bufs]).sum(0)
+        for e, b in zip(eb, bufs):
+            b["flat"].copy_(total)
+            e.local_step(b, dr)
+    for name in ("user_feat", "item_feat", "user_bias", "item_bias"):
+        a, b = eng_table(ea, name, G), eng_table(eb, name, G)
+        assert_fp32_close(a, b, "a2a vs all-reduce " + name, rtol=1e-6)

@@ -137,3 +137,130 @@ def test_sharded_protocol_equals_single_table_oracle(world):
     for name in ("user_feat", "item_feat", "user_bias", "item_bias", "mu"):
         np.testing.assert_allclose(out[name].reshape(getattr(orc, name).shape), getattr(orc, name), rtol=2e-5, atol=2e-7,
                                    err_msg=name)
+
+
+# ---- the all-to-all exchange (north_star: ids -> rows back -> gradient records to the owners) over gloo ---------------
+def _a2a_rank_main(rank, world, port, U, I, d, B, steps, out):
+    from oracle import np_oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    G, lr, reg = world, 1e-2, 0.05
+    tabs = init.init_tables(U, I, d, seed=5, bias_init="truncated_normal")
+    U_loc, I_loc = sharding.rows_on_rank(U, G, rank), sharding.rows_on_rank(I, G, rank)
+    loc = {k: (tabs[k].copy() if k == "mu" else sharding.shard_table(tabs[k], G, rank)) for k in tabs}
+    slots = {k: [np.zeros_like(v), np.zeros_like(v)] for k, v in loc.items()}
+    b1p, b2p = np.float32(0.9), np.float32(0.999)
+    rng = np.random.default_rng(100 + rank)
+    lo, hi = sharding.batch_slice(B, G, rank)
+    n = hi - lo
+
+    def a2a(send, send_splits, recv_splits):
+        recv = torch.empty((int(sum(recv_splits)),) + tuple(send.shape[1:]), dtype=send.dtype)
+        dist.all_to_all_single(recv, send, [int(x) for x in recv_splits], [int(x) for x in send_splits])
+        return recv
+    for step in range(steps):
+        users = rng.integers(0, U, n).astype(np.int32)
+        items = rng.integers(0, max(I // 4, 1), n).astype(np.int32)
+        rates = rng.integers(1, 6, n).astype(np.float32)
+        # 1. bucket by owner, stably (what tfr_shard_bucket does): combined layout [dst: users | items]
+        send_ids, slot, counts = [], {}, np.zeros(2 * G, np.int64)
+        for g in range(G):
+            for side, ids in ((0, users), (1, items)):
+                pos = np.flatnonzero(ids % G == g)
+                for p in pos:
+                    slot[(side, p)] = len(send_ids)
+                    send_ids.append(ids[p] // G)
+                counts[side * G + g] = len(pos)
+        allc = [torch.zeros(2 * G, dtype=torch.int64) for _ in range(G)]
+        dist.all_gather(allc, torch.from_numpy(counts))
+        cnt = torch.stack(allc).numpy()
+        send_splits = cnt[rank, :G] + cnt[rank, G:]
+        recv_cu, recv_ci = cnt[:, rank], cnt[:, G + rank]
+        recv_splits = recv_cu + recv_ci
+        # 2. ids to the owners
+        recv_ids = a2a(torch.tensor(send_ids, dtype=torch.int64).reshape(-1), send_splits, recv_splits).numpy()
+        is_user = np.concatenate([np.r_[np.ones(recv_cu[s], bool), np.zeros(recv_ci[s], bool)] for s in range(G)]) \
+            if len(recv_ids) else np.zeros(0, bool)
+        # 3. owners pack the rows; 4. back to the requesters
+        rec = np.zeros((len(recv_ids), d + 1), np.float32)
+        rec[is_user, :d], rec[is_user, d] = loc["user_feat"][recv_ids[is_user]], loc["user_bias"][recv_ids[is_user]]
+        rec[~is_user, :d], rec[~is_user, d] = loc["item_feat"][recv_ids[~is_user]], loc["item_bias"][recv_ids[~is_user]]
+        rec_in = a2a(torch.from_numpy(rec), recv_splits, send_splits).numpy()
+        # 5. forward on MY slice; one record per occurrence and table: [partner row | e]
+        su = np.array([slot[(0, p)] for p in range(n)], np.int64)
+        si = np.array([slot[(1, p)] for p in range(n)], np.int64)
+        ur, vr = rec_in[su], rec_in[si]
+        x = (np.sum(ur[:, :d] * vr[:, :d], axis=1, dtype=np.float32) + loc["mu"][0] + ur[:, d] + vr[:, d]).astype(np.float32)
+        e = (x - rates).astype(np.float32)
+        rec_out = np.zeros((2 * n, d + 1), np.float32)
+        rec_out[su, :d], rec_out[su, d] = vr[:, :d], e
+        rec_out[si, :d], rec_out[si, d] = ur[:, :d], e
+        sums = torch.tensor([float(np.sum(e, dtype=np.float32))], dtype=torch.float64)
+        dist.all_reduce(sums)
+        # 6. records to the owners; 7. ordered sums in ARRIVAL order (= global batch order) + local Adam
+        grads_in = a2a(torch.from_numpy(rec_out), send_splits, recv_splits).numpy()
+        lr_t = np_oracle.adam_lr_t(lr, b1p, b2p)
+        for mask, feat, bias in ((is_user, "user_feat", "user_bias"), (~is_user, "item_feat", "item_bias")):
+            keys = recv_ids[mask]
+            part, ee = grads_in[mask, :d], grads_in[mask, d]
+            gf = (ee[:, None] * part + np.float32(reg) * loc[feat][keys]).astype(np.float32)
+            uq, idx = np_oracle.unique_first_occurrence(keys.astype(np.int32))
+            for name, g in ((feat, gf), (bias, ee)):
+                gs = np_oracle.segment_sum(g, idx, len(uq))
+                loc[name], slots[name][0], slots[name][1] = np_oracle.adam_sparse(loc[name], slots[name][0], slots[name][1],
+                                                                                 uq, gs, lr_t)
+        gmu = np.float32(sums.item())
+        m_, v_ = slots["mu"]
+        m_ = m_ + (gmu - m_) * (np.float32(1) - np.float32(0.9))
+        v_ = v_ + (gmu * gmu - v_) * (np.float32(1) - np.float32(0.999))
+        loc["mu"] = (loc["mu"] - (m_ * lr_t) / (np.sqrt(v_) + np.float32(1e-8))).astype(np.float32)
+        slots["mu"] = [m_.astype(np.float32), v_.astype(np.float32)]
+        b1p, b2p = b1p * np.float32(0.9), b2p * np.float32(0.999)
+        parts = [None] * G
+        dist.all_gather_object(parts, (users, items, rates))
+        if rank == 0:
+            out.setdefault("batches", []).append(tuple(np.concatenate([p[k] for p in parts]) for k in range(3)))
+    for name in ("user_feat", "item_feat", "user_bias", "item_bias"):
+        parts = [None] * G
+        dist.all_gather_object(parts, loc[name])
+        if rank == 0:
+            out[name] = sharding.unshard_table(parts)
+    if rank == 0:
+        out["mu"] = loc["mu"]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _a2a_run(rank, world, port, shape, q):
+    out = {}
+    _a2a_rank_main(rank, world, port, *shape, out)
+    if rank == 0:
+        q.put(out)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_a2a_protocol_equals_single_table_oracle(world):
+    """Real multi-process all_to_all_single (gloo) with the exact per-peer counts: ids to the owners, rows back,
+    [partner row | e] records to the owners.  Summing the records in ARRIVAL order reproduces the single-table oracle:
+    arrival order = (source rank, position in its slice) = global batch order."""
+    import oracle
+    U, I, d, B, steps = 41, 23, 6, 64, 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_a2a_run, args=(r, world, port, (U, I, d, B, steps), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    tabs = init.init_tables(U, I, d, seed=5, bias_init="truncated_normal")
+    orc = oracle.SvdOracle(tabs["mu"], tabs["user_bias"], tabs["item_bias"], tabs["user_feat"], tabs["item_feat"], 1e-2, 0.05)
+    for users, items, rates in out["batches"]:
+        assert len(users) == B
+        orc.train_step(users, items, rates)
+    for name in ("user_feat", "item_feat", "user_bias", "item_bias", "mu"):
+        np.testing.assert_allclose(out[name].reshape(getattr(orc, name).shape), getattr(orc, name), rtol=2e-5, atol=2e-7,
+                                   err_msg=name)

@@ -43,7 +43,7 @@ class SvdTables(C.Structure):
                 ("m_mu", vp), ("v_mu", vp), ("m_ub", vp), ("v_ub", vp), ("m_ib", vp), ("v_ib", vp),
                 ("m_uf", vp), ("v_uf", vp), ("m_if", vp), ("v_if", vp),
                 ("user_slot", vp), ("item_slot", vp),
-                ("g_user_feat", vp), ("g_item_feat", vp), ("g_user_bias", vp), ("g_item_bias", vp)]
+                ("g_user_feat", vp), ("g_item_feat", vp), ("g_user_bias", vp), ("g_item_bias", vp), ("g_stride", i64)]
 
 
 class StepWs(C.Structure):
@@ -130,6 +130,12 @@ _PROTOS = {
     "tfr_sgd_apply": (C.c_int, [vp, i32, vp, i64, vp, vp]),
     "tfr_svd_finish_step": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, C.POINTER(StepWs), i32, vp]),
     "tfr_shard_gather_rows": (C.c_int, [vp, vp, i64, i32, i64, vp, i64, i32, i32, vp, vp, vp, vp]),
+    "tfr_shard_bucket_workspace_bytes": (i64, [i64]),
+    "tfr_shard_bucket": (C.c_int, [vp, vp, i64, i32, vp, vp, vp, vp, vp, i64, vp]),
+    "tfr_shard_gather_records": (C.c_int, [C.POINTER(SvdTables), vp, C.POINTER(i32), C.POINTER(i32), i32, vp, vp]),
+    "tfr_shard_fwd_records": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]),
+    "tfr_shard_owner_prepare": (C.c_int, [vp, vp, C.POINTER(i32), C.POINTER(i32), i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, vp]),
+    "tfr_svd_train_step_gathered": (C.c_int, [C.POINTER(SvdTables), vp, vp, vp, i64, i32, i32, vp, vp, vp, i64, vp]),
     "tfr_fm_forward": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
     "tfr_fm_segment_grads": (C.c_int, [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i64, C.POINTER(StepWs), vp]),
     "tfr_fm_train_step": (C.c_int, [C.POINTER(FmTables), vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, vp, i64, vp]),

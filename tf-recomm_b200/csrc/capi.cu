@@ -312,6 +312,38 @@ extern "C" int tfr_svd_train_step_presorted(const tfr_svd_tables* t, tfr_opt_sca
                   nullptr, 0, nullptr, true, phases);
 }
 
+// The step from the sort on, for the all-to-all sharded exchange: keys and ws.err by arrival position are the caller's
+// (tfr_shard_owner_prepare), the partner rows come from t->g_* by position, the step's d cost/d bias_global and squared
+// error are the all-reduced scalars.
+extern "C" int tfr_svd_train_step_gathered(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* keys_u,
+                                           const int32_t* keys_i, int64_t n, int32_t flags, int32_t var_mask,
+                                           const float* sum_err, const double* sum_se, void* workspace,
+                                           int64_t workspace_bytes, void* stream) {
+  TFR_CHECK_ARG(t && opt && n >= 0 && t->dim > 0 && sum_err && sum_se && workspace);
+  TFR_CHECK_ARG(!(flags & TFR_OPT_SGD));   // the sharded path trains with Adam (BASELINE configs[4])
+  TFR_CHECK_ARG(n == 0 || (keys_u && keys_i && t->g_user_feat && t->g_item_feat));
+  tfr_svd_step_ws ws;
+  int rc = tfr_svd_step_carve(workspace, workspace_bytes, n > 0 ? n : 1, t->dim, &ws);
+  if (rc) return rc;
+  if (n > 0) {
+    if ((rc = tfr_dedup_sort_pairs_tl(keys_u, (int64_t)t->user_num + 1, ws.su_ids, ws.su_pos, keys_i, (int64_t)t->item_num + 1,
+                                      ws.si_ids, ws.si_pos, n, ws.sort_ws, ws.sort_ws_bytes, opt, stream)))
+      return rc;
+    if ((rc = svd_segment_grads_impl(t, opt, keys_u, keys_i, n, &ws, flags, stream))) return rc;
+  }
+  tfr_svd_step_ws ws_fin = ws;
+  ws_fin.partials = const_cast<float*>(sum_err);
+  ws_fin.se_partials = const_cast<double*>(sum_se);
+  tfr_adam_table tabs[4];
+  int nt = 0;
+  const int dim = t->dim;
+  if (var_mask & TFR_VAR_UB) tabs[nt++] = tfr_adam_table{t->user_bias, t->m_ub, t->v_ub, t->user_num, 1, t->user_slot, ws.gsum_ub, 0};
+  if (var_mask & TFR_VAR_IB) tabs[nt++] = tfr_adam_table{t->item_bias, t->m_ib, t->v_ib, t->item_num, 1, t->item_slot, ws.gsum_ib, 0};
+  if (var_mask & TFR_VAR_IF) tabs[nt++] = tfr_adam_table{t->item_feat, t->m_if, t->v_if, t->item_num, dim, t->item_slot, ws.gsum_if, t->feat_stride};
+  if (var_mask & TFR_VAR_UF) tabs[nt++] = tfr_adam_table{t->user_feat, t->m_uf, t->v_uf, t->user_num, dim, t->user_slot, ws.gsum_uf, t->feat_stride};
+  return adam_pass_and_finish(tabs, nt, t, opt, &ws_fin, 1, TFR_TL_STREAM_UF, stream);
+}
+
 extern "C" int tfr_svd_prefetch_batch(const tfr_svd_tables* t, tfr_opt_scalars* opt, const int32_t* col_user,
                                       const int32_t* col_item, const float* col_rate, const int64_t* row_index,
                                       int64_t batch_index, int64_t B, int32_t* users, int32_t* items, float* rates,

@@ -772,7 +772,8 @@ static int launch_segsum(const SegSide& su, const SegSide& si, int n_sides, cons
 static void svd_sides(const tfr_svd_tables* t, const int32_t* users, const int32_t* items, const tfr_svd_step_ws* ws,
                       SegSide* su, SegSide* si) {
   const bool gathered = t->g_user_feat != nullptr;
-  const int64_t fs = t->feat_stride ? t->feat_stride : t->dim, ps = gathered ? t->dim : fs;
+  const int64_t fs = t->feat_stride ? t->feat_stride : t->dim;
+  const int64_t ps = gathered ? (t->g_stride ? t->g_stride : (int64_t)t->dim) : fs;
   *su = SegSide{ws->su_ids, ws->su_pos, gathered ? nullptr : items, t->user_feat,
                 gathered ? t->g_item_feat : t->item_feat, fs, ps, t->user_bias, gathered ? t->g_item_bias : t->item_bias,
                 ws->gsum_uf, ws->gsum_ub, ws->cont_uf, ws->cont_ub, ws->tail_uf, ws->tail_ub, ws->kind_u, ws->fix_list_u,

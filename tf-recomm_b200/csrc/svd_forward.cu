@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(256) svd_forward_kernel(tfr_svd_tables t, cons
   const float* __restrict__ itf = gathered ? t.g_item_feat : t.item_feat;
   const float* __restrict__ ubias = gathered ? t.g_user_bias : t.user_bias;
   const float* __restrict__ ibias = gathered ? t.g_item_bias : t.item_bias;
-  const size_t fs = (gathered || t.feat_stride == 0) ? (size_t)dim : (size_t)t.feat_stride;  // floats between rows
+  const size_t fs = gathered ? (t.g_stride ? (size_t)t.g_stride : (size_t)dim)
+                             : (t.feat_stride == 0 ? (size_t)dim : (size_t)t.feat_stride);  // floats between rows
   float err_acc = 0.0f;
   double se_acc = 0.0;
 

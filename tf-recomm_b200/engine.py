@@ -262,9 +262,7 @@ class SvdEngine:
         tile by tile in the GEMM epilogue (never materialised).  -> (rmse, row_se [U] float64)."""
         self._check_ids(users, items)
         dev = self.device
-        u = torch.as_tensor(np.asarray(users), device=dev).to(torch.int64)
-        i = torch.as_tensor(np.asarray(items), device=dev).to(torch.int64)
-        r = torch.as_tensor(np.asarray(rates), device=dev).to(torch.float32)
+        u, i, r = self._dev_i32(users).to(torch.int64), self._dev_i32(items).to(torch.int64), self._dev_f32(rates)
         order = torch.argsort(u * self.I + i, stable=True)     # CSR by user, item ids ascending inside a user
         indptr = torch.zeros(self.U + 1, dtype=torch.int64, device=dev)
         indptr[1:] = torch.cumsum(torch.bincount(u, minlength=self.U), 0)
