@@ -92,6 +92,8 @@ def in_run_parity_check(eng, torch, dist, w, world, rank, dev, steps=3):
     for _ in range(steps):
         us, it, rt = _draw_slice(torch, gen, hi - lo, w["U"], w["I"], dev)
         logits, _ = eng.step(us, it, rt)
+        if logits.numel() != hi - lo:      # the all-reduce exchange computes every rank's predictions: keep my slice
+            logits = logits[lo:hi]
         parts = [None] * G
         dist.all_gather_object(parts, (us.cpu().numpy(), it.cpu().numpy(), rt.cpu().numpy(), logits.cpu().numpy()))
         if rank == 0:

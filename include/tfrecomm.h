@@ -88,6 +88,7 @@ typedef struct {
                             driver's trailing-window train RMSE (svd_train_val.py:59,104,108) needs one
                             read per epoch instead of one per step                            */
   int64_t se_ring_len;
+  uint32_t chunk_ctr[4]; /* per-table chunk counters of the table pass's dynamic scheduling; 0 between steps */
   uint64_t* timeline;    /* optional debug buffer [2][TFR_TL_SLOTS] of %globaltimer ns: earliest block entry and
                             latest warp exit of every kernel of the step (there is no nsys on the box); null = off */
 } tfr_opt_scalars;

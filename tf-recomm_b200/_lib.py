@@ -33,7 +33,8 @@ class OptScalars(C.Structure):
                 ("one_minus_beta1", f32), ("one_minus_beta2", f32),
                 ("flags", i32), ("var_mask", i32),
                 ("global_step", i64), ("batch_cursor", i64), ("prefetch_cursor", i64), ("se_sum", C.c_double),
-                ("g_mu", f32), ("ticket", C.c_uint32), ("se_ring", vp), ("se_ring_len", i64), ("timeline", vp)]
+                ("g_mu", f32), ("ticket", C.c_uint32), ("se_ring", vp), ("se_ring_len", i64),
+                ("chunk_ctr", C.c_uint32 * 4), ("timeline", vp)]
 
 
 class SvdTables(C.Structure):

@@ -63,15 +63,19 @@ struct StreamArgs {
   int partition;
   uint32_t cta_begin[5];
   int ld_hint, st_hint;
+  int tl_every;   // debug timeline: every CTA stamps its exit (the true end of the pass, not a sample)
+  int dynamic;    // 1: warps take chunks off opt->chunk_ctr[table] (needs fin: the last CTA resets the counters)
   int copy_only;  // experiment (TFR_STREAM_COPY_ONLY=1): same loads and stores, no arithmetic -- the memory ceiling
 };
 
-template <int UNROLL>
+constexpr uint32_t DYN_TRIPS = 8;
+
+template <int UNROLL, bool DYNAMIC>
 __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_constant__ StreamArgs a,
                                                                 const tfr_opt_scalars* __restrict__ opt, int tl_slot) {
   pdl_wait();                // the fix-up's summed gradients and slot maps are complete
   pdl_launch_dependents();   // the next step's segment sums may become resident as this grid drains
-  TlScope tl_scope(opt, tl_slot);
+  TlScope tl_scope(opt, tl_slot, a.tl_every != 0);
   const AdamK k = load_k(opt);
   const uint32_t stamp = (uint32_t)opt->global_step;
   uint32_t stride = gridDim.x * blockDim.x;
@@ -104,15 +108,16 @@ __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_
       float4* const pv = reinterpret_cast<float4*>(t.var);
       float4* const pm = reinterpret_cast<float4*>(t.m);
       float4* const pz = reinterpret_cast<float4*>(t.v);
-#pragma unroll 1
-      for (uint32_t q0 = gtid; q0 < n4; q0 += stride * UNROLL) {
+      // one trip: UNROLL units per thread, `us` units apart, the first at q0
+      auto trip = [&](uint32_t q0, uint32_t us) {
+
         float4 x[UNROLL], y[UNROLL], z[UNROLL], g[UNROLL];
         bool has[UNROLL];
         size_t at[UNROLL];
         uint32_t row[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-          const uint32_t q = q0 + u * stride;
+          const uint32_t q = q0 + u * us;
           if (q < n4) {
             row[u] = sh >= 0 ? (q >> sh) : (q / upr);
             at[u] = dense ? (size_t)q : (size_t)row[u] * spr + (q - row[u] * upr);
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-          const uint32_t q = q0 + u * stride;
+          const uint32_t q = q0 + u * us;
           has[u] = false;
           if (q < n4 && t.slot) {
             const int64_t sl = t.slot[row[u]];
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-          const uint32_t q = q0 + u * stride;
+          const uint32_t q = q0 + u * us;
           if (q >= n4) continue;
           if (a.copy_only) {
           } else if (has[u]) {
@@ -151,6 +156,28 @@ __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_
           st_hint_f4(pv + at[u], x[u], a.st_hint);
           st_hint_f4(pm + at[u], y[u], a.st_hint);
           st_hint_f4(pz + at[u], z[u], a.st_hint);
+        }
+      };
+      if constexpr (!DYNAMIC) {
+#pragma unroll 1
+        for (uint32_t q0 = gtid; q0 < n4; q0 += stride * UNROLL) trip(q0, stride);
+      } else {
+        // dynamic: a WARP takes the next chunk of DYN_TRIPS * 32 * UNROLL consecutive units off a per-table counter, so
+        // that the persistent grid's warps finish together whatever their SM's share of the memory system was
+        constexpr uint32_t CHUNK = DYN_TRIPS * 32u * UNROLL;
+        const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll 1
+        for (;;) {
+          uint32_t c = 0;
+          if (lane == 0) c = atomicAdd(&a.fin.opt->chunk_ctr[tb], 1u);
+          c = __shfl_sync(0xffffffffu, c, 0);
+          if ((uint64_t)c * CHUNK >= n4) break;
+          const uint32_t base = c * CHUNK + lane;
+#pragma unroll 1
+          for (uint32_t t_ = 0; t_ < DYN_TRIPS; ++t_) {
+            const uint32_t q0 = base + t_ * 32u * UNROLL;
+            if (q0 < n4) trip(q0, 32u);
+          }
         }
       }
     } else {
@@ -185,7 +212,10 @@ __global__ void __launch_bounds__(512, 2) adam_stream_multi_kernel(const __grid_
     if (s_last && threadIdx.x < 32) {
       finish_step_scalars(a.fin.mu, a.fin.m_mu, a.fin.v_mu, a.fin.opt, a.fin.partials, a.fin.se_partials,
                           a.fin.n_partials);
-      if (threadIdx.x == 0) a.fin.opt->ticket = 0;
+      if (threadIdx.x == 0) {
+        a.fin.opt->ticket = 0;
+        for (int i = 0; i < 4; ++i) a.fin.opt->chunk_ctr[i] = 0;
+      }
     }
   }
 }
@@ -312,6 +342,7 @@ __global__ void opt_init_kernel(tfr_opt_scalars* opt, float lr, float reg, float
   opt->flags = flags; opt->var_mask = var_mask;
   opt->global_step = 0; opt->batch_cursor = 0; opt->prefetch_cursor = 0;
   opt->se_sum = 0.0; opt->g_mu = 0.0f; opt->ticket = 0u;
+  for (int i = 0; i < 4; ++i) opt->chunk_ctr[i] = 0u;
   opt->se_ring = nullptr; opt->se_ring_len = 0; opt->timeline = nullptr;
 }
 
@@ -341,6 +372,8 @@ static int launch_stream_chunks(const StreamTab* chunks, int n_chunks, const tfr
   a.n_tabs = n_chunks;
   a.total_units = (uint32_t)units;
   a.copy_only = tune(TUNE_STREAM_COPY_ONLY);
+  a.dynamic = (fin && tune(TUNE_STREAM_DYNAMIC)) ? 1 : 0;
+  a.tl_every = tune(TUNE_TL_EVERY_CTA);
   a.ld_hint = tune(TUNE_STREAM_LD);
   a.st_hint = tune(TUNE_STREAM_ST);
   // persistent grid: 2 CTAs x 448 threads x 64 registers per SM, 2 units per thread and trip.  448, not 512: two
@@ -378,12 +411,15 @@ static int launch_stream_chunks(const StreamTab* chunks, int n_chunks, const tfr
     grid = at;
   }
   const bool pdl = tune(TUNE_PDL) != 0;
-  if (cfg_unroll >= 4) {
-    TFR_PREP(adam_stream_multi_kernel<4>);
-    TFR_CUDA(launch_kernel(adam_stream_multi_kernel<4>, dim3((unsigned)grid), dim3(cfg_threads), 0, st, pdl, a, opt, tl_slot));
+  if (a.dynamic) {
+    TFR_PREP((adam_stream_multi_kernel<2, true>));
+    TFR_CUDA(launch_kernel(adam_stream_multi_kernel<2, true>, dim3((unsigned)grid), dim3(cfg_threads), 0, st, pdl, a, opt, tl_slot));
+  } else if (cfg_unroll >= 4) {
+    TFR_PREP((adam_stream_multi_kernel<4, false>));
+    TFR_CUDA(launch_kernel(adam_stream_multi_kernel<4, false>, dim3((unsigned)grid), dim3(cfg_threads), 0, st, pdl, a, opt, tl_slot));
   } else {
-    TFR_PREP(adam_stream_multi_kernel<2>);
-    TFR_CUDA(launch_kernel(adam_stream_multi_kernel<2>, dim3((unsigned)grid), dim3(cfg_threads), 0, st, pdl, a, opt, tl_slot));
+    TFR_PREP((adam_stream_multi_kernel<2, false>));
+    TFR_CUDA(launch_kernel(adam_stream_multi_kernel<2, false>, dim3((unsigned)grid), dim3(cfg_threads), 0, st, pdl, a, opt, tl_slot));
   }
   return TFR_OK;
 }

@@ -123,41 +123,85 @@ struct ApConsumers {
 // order of the ranking: higher score first, lower item index on ties
 __device__ __forceinline__ bool ap_better(float s, int i, float s2, int i2) { return s > s2 || (s == s2 && i < i2); }
 
-// slow path of the TOPK consumer: (s, col) reaches the row's threshold.  r = row inside the CTA.
-__device__ __noinline__ void ap_topk_insert(float* __restrict__ cval, int32_t* __restrict__ cidx, int K, int* s_lock,
-                                            int* s_cnt, float* s_thr, int* s_minpos, int r, float s, int col) {
-  while (atomicCAS(&s_lock[r], 0, 1) != 0) {}
-  __threadfence_block();
-  const int cnt = s_cnt[r];
-  bool rescan = false;
-  if (cnt < K) {
-    __stcg(cval + cnt, s);
-    __stcg(cidx + cnt, col);
-    s_cnt[r] = cnt + 1;
-    rescan = cnt + 1 == K;
-  } else {
-    const int mp = s_minpos[r];
-    const float mv = __ldcg(cval + mp);
-    const int mi = __ldcg(cidx + mp);
-    if (ap_better(s, col, mv, mi)) {
-      __stcg(cval + mp, s);
-      __stcg(cidx + mp, col);
-      rescan = true;
+// Slow path of the TOPK consumer, WARP-COOPERATIVE: (s, col) of the row `r` (inside the CTA) reaches that row's
+// threshold.  All 32 lanes of the calling warp take part (the caller loops over its lanes that need an insert): each
+// lane holds K / 32 entries of the row's list, two butterfly reductions find the worst entry before and after the
+// replacement -- ~40 warp instructions per insert instead of a 2K-load scan executed by one lane while 31 wait.
+// The other half's warp may work on the same row: a per-row lock (shared memory), list accesses through L2 (.cg).
+// Returns the row's new threshold (the same value on every lane).
+template <int KPL>   // entries per lane: K <= 32 * KPL
+__device__ __forceinline__ float ap_topk_insert_warp(float* __restrict__ cval, int32_t* __restrict__ cidx, int K, int* s_lock,
+                                                     int* s_cnt, float* s_thr, int r, float s, int col, int lane) {
+  if (lane == 0) {
+    while (atomicCAS(&s_lock[r], 0, 1) != 0) {}
+    __threadfence_block();
+  }
+  __syncwarp();
+  const int cnt = *reinterpret_cast<volatile int*>(&s_cnt[r]);
+  float new_thr;
+  if (cnt < K) {   // the list is not full yet: append; the threshold stays -inf until it is
+    if (lane == 0) {
+      __stcg(cval + cnt, s);
+      __stcg(cidx + cnt, col);
+      s_cnt[r] = cnt + 1;
+    }
+    new_thr = -INFINITY;
+    if (cnt + 1 < K) {
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); atomicExch(&s_lock[r], 0); }
+      return new_thr;
+    }
+    __syncwarp();
+  }
+  // this lane's entries; worst = the one every other entry is `better` than
+  float v[KPL];
+  int ix[KPL];
+  float wv = INFINITY;
+  int wi = -1, wp = -1;
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) {
+    const int p = lane + 32 * j;
+    v[j] = INFINITY; ix[j] = -1;
+    if (p < K) {
+      v[j] = __ldcg(cval + p);
+      ix[j] = __ldcg(cidx + p);
+      if (wp < 0 || ap_better(wv, wi, v[j], ix[j])) { wv = v[j]; wi = ix[j]; wp = p; }
     }
   }
-  if (rescan) {  // the list is full: find its worst entry, the row's new threshold
-    float mv = __ldcg(cval);
-    int mi = __ldcg(cidx), mp = 0;
-    for (int j = 1; j < K; ++j) {
-      const float v = __ldcg(cval + j);
-      const int i = __ldcg(cidx + j);
-      if (ap_better(mv, mi, v, i)) { mv = v; mi = i; mp = j; }
+  auto warp_worst = [&](float& xv, int& xi, int& xp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, xv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, xi, o);
+      const int op = __shfl_xor_sync(0xffffffffu, xp, o);
+      if (op >= 0 && (xp < 0 || ap_better(xv, xi, ov, oi))) { xv = ov; xi = oi; xp = op; }
     }
-    s_minpos[r] = mp;
-    s_thr[r] = mv;
+  };
+  warp_worst(wv, wi, wp);
+  if (cnt >= K && ap_better(s, col, wv, wi)) {   // replaces the worst entry
+    if (lane == (wp & 31)) {
+      __stcg(cval + wp, s);
+      __stcg(cidx + wp, col);
+    }
+    wv = INFINITY; wi = -1;
+    int np = -1;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const int p = lane + 32 * j;
+      if (p == wp) { v[j] = s; ix[j] = col; }
+      if (p < K && (np < 0 || ap_better(wv, wi, v[j], ix[j]))) { wv = v[j]; wi = ix[j]; np = p; }
+    }
+    wp = np;
+    warp_worst(wv, wi, wp);
   }
-  __threadfence_block();
-  atomicExch(&s_lock[r], 0);
+  new_thr = wv;
+  __syncwarp();
+  if (lane == 0) {
+    s_thr[r] = new_thr;
+    __threadfence_block();
+    atomicExch(&s_lock[r], 0);
+  }
+  return new_thr;
 }
 
 template <int KCHUNKS, bool TOPK, bool OBS>
@@ -180,7 +224,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
   float* s_thr = s_bias + 256;                                   // [128] TOPK: the row's threshold
   int* s_cnt = reinterpret_cast<int*>(s_thr + 128);              // [128]
   int* s_lock = s_cnt + 128;                                     // [128]
-  int* s_minpos = s_lock + 128;                                  // [128]
+  int* s_minpos = s_lock + 128;                                  // [128] (unused: the cooperative insert rescans)
   double* s_se = reinterpret_cast<double*>(s_minpos + 128);      // [2][128] OBS: halves' squared-error sums
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * AP_BM;
@@ -264,14 +308,20 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
     int32_t* const cidx = TOPK && row_ok ? cs.cand_idx + (size_t)row * cs.K : nullptr;
     // OBS: this row's observed pairs [op, oend), next one's item id / rating
     int64_t op = 0, oend = 0;
-    int onext = 0x7fffffff;
-    float orate = 0.0f;
+    int onext = 0x7fffffff, onext2 = 0x7fffffff;   // the next pair's item id, and the one after it (fetched ahead: a
+    float orate = 0.0f, orate2 = 0.0f;             // hit then never waits for a load it has just issued)
     double se = 0.0;
     if (OBS && row_ok) {
       op = cs.obs_indptr[row];
       oend = cs.obs_indptr[row + 1];
       if (op < oend) { onext = cs.obs_item[op]; orate = cs.obs_rate[op]; }
+      if (op + 1 < oend) { onext2 = cs.obs_item[op + 1]; orate2 = cs.obs_rate[op + 1]; }
     }
+    auto obs_advance = [&]() {   // on to the next pair of this row
+      ++op;
+      onext = onext2; orate = orate2;
+      if (op + 1 < oend) { onext2 = cs.obs_item[op + 1]; orate2 = cs.obs_rate[op + 1]; } else onext2 = 0x7fffffff;
+    };
     for (int t = 0; t < n_tiles; ++t) {
       const int acc = t & 1;
       const int n0 = t * AP_BN + half * 64;
@@ -281,10 +331,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
       float thr = TOPK ? s_thr[r_in_tile] : 0.0f;
       if (OBS) {
-        while (onext < n0) {  // pairs of the columns the other half owns, or of earlier tiles
-          ++op;
-          if (op < oend) { onext = cs.obs_item[op]; orate = cs.obs_rate[op]; } else onext = 0x7fffffff;
-        }
+        while (onext < n0) obs_advance();  // pairs of the columns the other half owns, or of earlier tiles
       }
       mbar_wait(&bars[BAR_TMEM_FULL + acc], (t >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -306,20 +353,27 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
             if (cs.scores && ok) cs.scores[(size_t)row * n_items + col] = s;
             if (ok && s > best[q]) { best[q] = s; besti[q] = col; }
             if (TOPK) {
-              if (ok && s >= thr) {
-                ap_topk_insert(cval, cidx, cs.K, s_lock, s_cnt, s_thr, s_minpos, r_in_tile, s, col);
-                thr = *reinterpret_cast<volatile float*>(&s_thr[r_in_tile]);
+              // lanes whose column reaches their row's threshold; the warp serves them one after the other, together
+              unsigned need = __ballot_sync(0xffffffffu, ok && s >= thr);
+              while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                const float bs = __shfl_sync(0xffffffffu, s, src);
+                const int bcol = __shfl_sync(0xffffffffu, col, src);
+                const int brow = quarter * 32 + src;
+                const float nt = ap_topk_insert_warp<AP_MAX_CAND / 32>(cs.cand_val + (size_t)(m0 + brow) * cs.K,
+                                                                       cs.cand_idx + (size_t)(m0 + brow) * cs.K, cs.K, s_lock,
+                                                                       s_cnt, s_thr, brow, bs, bcol, lane);
+                if (lane == src) thr = nt;
               }
             }
             if (OBS) {
               if (col == onext) {
-                const double d = (double)s - (double)orate;
-                se += d * d;
                 // duplicates of a pair (the same item twice in a user's list) all count, like fancy indexing does
                 do {
-                  ++op;
-                  if (op < oend) { onext = cs.obs_item[op]; orate = cs.obs_rate[op]; } else onext = 0x7fffffff;
-                  if (onext == col) { const double d2 = (double)s - (double)orate; se += d2 * d2; }
+                  const double d = (double)s - (double)orate;
+                  se += d * d;
+                  obs_advance();
                 } while (onext == col);
               }
             }

@@ -36,13 +36,13 @@ const TuneEntry kTune[TUNE_COUNT] = {
     {"SMEM_CARVEOUT", 62},   // 141 KB of shared memory on every kernel of the step: four CTAs of the segment-sum kernel
                              // (32 KB each) per SM, and enough L1 for the LDG pass (100 %: pass 125 -> 149 us)
     {"TILES_CARVEOUT", -1}, {"SEG_MAX_UNITS", 0}, {"SEG_TILE", 0}, {"STREAM_COPY_ONLY", 0}, {"STREAM_LD", 2},
-    {"STREAM_ST", 0}, {"STREAM_CTAS_PER_SM", 2}, {"STREAM_UNROLL", 2}, {"STREAM_THREADS", 448},
+    {"STREAM_ST", 0}, {"STREAM_CTAS_PER_SM", 2}, {"STREAM_UNROLL", 2}, {"STREAM_THREADS", 448}, {"STREAM_DYNAMIC", 0},
     // the TMA-bulk ring pass is OFF by default: alone it matches the LDG pass (135 vs 137 us at the ML-25M shape), in
     // situ -- the next batch's id sort competing for issue slots with its 16 consumer warps per SM -- it loses (150-157
     // vs 125 us); profiles/r02_pass_ring_vs_ldg.md
     {"PASS_RING", 0},
     {"RING_STAGES", 4}, {"RING_STAGE_KB", 24}, {"RING_THREADS", 320}, {"RING_L2_HINT", 2}, {"RING_CTAS_PER_SM", 2},
-    {"RING_SLOT_MODE", 1},
+    {"RING_SLOT_MODE", 1}, {"TL_EVERY_CTA", 0},
     // programmatic dependent launch along tiles -> fix-up -> pass: no gain at the ML-25M shape (178.2 vs 177.5 us per
     // step) and a loss at the ML-1M shape (the early-resident dependents delay the side stream's id sort: 53 vs 37 us)
     {"PDL", 0},

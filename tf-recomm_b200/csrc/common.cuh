@@ -21,10 +21,11 @@ enum TuneKey {
   TUNE_SEG_TILE,          // segment sums: force tiles of 8 / 16 / 32 entries (0 = heuristic)
   TUNE_STREAM_COPY_ONLY,  // LDG pass without arithmetic (memory ceiling experiment)
   TUNE_STREAM_LD, TUNE_STREAM_ST,  // cache hints of the LDG pass (0 = .cs, 1 = default, 2 = .cg, 3 = .lu / .wt)
-  TUNE_STREAM_CTAS_PER_SM, TUNE_STREAM_UNROLL, TUNE_STREAM_THREADS,
+  TUNE_STREAM_CTAS_PER_SM, TUNE_STREAM_UNROLL, TUNE_STREAM_THREADS, TUNE_STREAM_DYNAMIC,
   TUNE_PASS_RING,         // 1: interleaved tables take the TMA-bulk ring pass (adam_ring.cu), 0: the LDG pass
   TUNE_RING_STAGES, TUNE_RING_STAGE_KB, TUNE_RING_THREADS, TUNE_RING_L2_HINT, TUNE_RING_CTAS_PER_SM,
   TUNE_RING_SLOT_MODE,
+  TUNE_TL_EVERY_CTA,      // debug timeline: the pass's exit stamp from every CTA instead of a sample
   TUNE_PDL,               // 1: programmatic dependent launch along the step's critical path (see pdl_wait)
   TUNE_COUNT
 };

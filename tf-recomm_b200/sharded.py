@@ -187,7 +187,7 @@ class ShardedSvdEngine:
         e, dev = self.local, self.device
         total = int(sum(cnt_u) + sum(cnt_i))
         cap = 1 << max(10, (max(total, 1) - 1).bit_length())
-        ws = e.workspace(("a2a", cap))
+        ws = e.workspace((cap, "a2a"))
         b = self._a2a_bufs(n_slice)
         carved = _lib.StepWs()
         check(self.L.tfr_svd_step_carve(ws.data_ptr(), ws.numel(), max(total, 1), self.d, C.byref(carved)))
