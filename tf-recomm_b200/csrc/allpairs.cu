@@ -42,6 +42,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "LAB_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+// the same wait for the two single-thread roles (TMA producer, MMA issuer): they wait for the epilogue most of the time,
+// and a bare try_wait loop takes issue slots from the epilogue warps that share their schedulers (ncu: SYNCS + YIELD + BRA
+// were 40 % of the instructions the kernel executed) -- sleep between polls
+__device__ __forceinline__ void mbar_wait_polite(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(200);
+  }
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -111,8 +128,10 @@ struct ApConsumers {
   float* scores;             // [n_users, n_items] or null
   float* best_score;         // [n_users] or null
   int32_t* best_item;        // [n_users] or null
-  float* cand_val;           // TOPK: [n_users, K]
-  int32_t* cand_idx;         // TOPK: [n_users, K]  (-1 = empty)
+  float* cand_val;           // TOPK: [n_users, 2, 4K]: one buffer per row and column half
+  int32_t* cand_idx;         // TOPK: [n_users, 2, 4K]
+  int32_t* cand_cnt;         // TOPK: [n_users, 2] entries in the buffer at the end of the sweep
+  float* cand_thr;           // TOPK: [n_users, 2] the buffer's threshold: no dropped column scored above it
   int K;
   const int64_t* obs_indptr; // OBS: [n_users + 1]
   const int32_t* obs_item;   // OBS: [nnz] ascending inside a user's range
@@ -123,85 +142,97 @@ struct ApConsumers {
 // order of the ranking: higher score first, lower item index on ties
 __device__ __forceinline__ bool ap_better(float s, int i, float s2, int i2) { return s > s2 || (s == s2 && i < i2); }
 
-// Slow path of the TOPK consumer, WARP-COOPERATIVE: (s, col) of the row `r` (inside the CTA) reaches that row's
-// threshold.  All 32 lanes of the calling warp take part (the caller loops over its lanes that need an insert): each
-// lane holds K / 32 entries of the row's list, two butterfly reductions find the worst entry before and after the
-// replacement -- ~40 warp instructions per insert instead of a 2K-load scan executed by one lane while 31 wait.
-// The other half's warp may work on the same row: a per-row lock (shared memory), list accesses through L2 (.cg).
-// Returns the row's new threshold (the same value on every lane).
-template <int KPL>   // entries per lane: K <= 32 * KPL
-__device__ __forceinline__ float ap_topk_insert_warp(float* __restrict__ cval, int32_t* __restrict__ cidx, int K, int* s_lock,
-                                                     int* s_cnt, float* s_thr, int r, float s, int col, int lane) {
-  if (lane == 0) {
-    while (atomicCAS(&s_lock[r], 0, 1) != 0) {}
-    __threadfence_block();
-  }
-  __syncwarp();
-  const int cnt = *reinterpret_cast<volatile int*>(&s_cnt[r]);
-  float new_thr;
-  if (cnt < K) {   // the list is not full yet: append; the threshold stays -inf until it is
-    if (lane == 0) {
-      __stcg(cval + cnt, s);
-      __stcg(cidx + cnt, col);
-      s_cnt[r] = cnt + 1;
-    }
-    new_thr = -INFINITY;
-    if (cnt + 1 < K) {
-      __syncwarp();
-      if (lane == 0) { __threadfence_block(); atomicExch(&s_lock[r], 0); }
-      return new_thr;
-    }
-    __syncwarp();
-  }
-  // this lane's entries; worst = the one every other entry is `better` than
-  float v[KPL];
-  int ix[KPL];
-  float wv = INFINITY;
-  int wi = -1, wp = -1;
+// TOPK consumer.  Each epilogue warp keeps its OWN candidate buffer per row (the two warps that share a row's TMEM lanes
+// split the columns in halves: a row has two buffers, merged by the rescore), so nothing is shared between warps: a
+// buffer's length and threshold live in the registers of the row's lane.
+//   hot path:   a column whose score exceeds the row's threshold is APPENDED by the row's own lane (two stores, nothing
+//               waits for them);
+//   slow path:  when a buffer of C = 4K entries is full, the warp COMPACTS it together: a radix select over the scores'
+//               order-preserving keys finds the K-th best, the K best entries (lowest item index on ties) are kept and the
+//               K-th best score becomes the threshold.  A row-half sees ~K ln(N/K) appends in all, i.e. two or three
+//               compactions per sweep -- against one latency-bound list scan PER INSERT in the first version
+//               (profiles/r02_allpairs_ncu_full.md).
+// Columns arrive in ascending index order, so an entry appended later never beats a kept one of equal score.
+constexpr int AP_EPL = 4 * AP_MAX_CAND / 32;   // buffer entries per lane at the largest C
+struct ApListState { int cnt; float thr; };
+__device__ __forceinline__ uint32_t ap_key(float f) {   // unsigned order == float order
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ int warp_sum_i(int x) {
 #pragma unroll
-  for (int j = 0; j < KPL; ++j) {
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+// (not inlined: called from a 64-times unrolled column loop).  The buffer holds `cnt` (<= C) entries; afterwards its first
+// min(cnt, K) slots hold the K best and the returned threshold is the K-th best score (-inf if cnt < K).
+__device__ __noinline__ ApListState ap_compact_warp(float* __restrict__ cval, int32_t* __restrict__ cidx, int cnt, int K,
+                                                    int lane) {
+  ApListState out;
+  if (cnt <= K) { out.cnt = cnt; out.thr = cnt == K ? INFINITY : -INFINITY; }
+  float v[AP_EPL];
+  int ix[AP_EPL];
+  uint32_t key[AP_EPL];
+  bool valid[AP_EPL];
+#pragma unroll
+  for (int j = 0; j < AP_EPL; ++j) {
     const int p = lane + 32 * j;
-    v[j] = INFINITY; ix[j] = -1;
-    if (p < K) {
-      v[j] = __ldcg(cval + p);
-      ix[j] = __ldcg(cidx + p);
-      if (wp < 0 || ap_better(wv, wi, v[j], ix[j])) { wv = v[j]; wi = ix[j]; wp = p; }
-    }
+    valid[j] = p < cnt;
+    v[j] = 0.0f; ix[j] = 0x7fffffff; key[j] = 0u;
+    if (valid[j]) { v[j] = __ldcg(cval + p); ix[j] = __ldcg(cidx + p); key[j] = ap_key(v[j]); }
   }
-  auto warp_worst = [&](float& xv, int& xi, int& xp) {
+  if (cnt < K) return out;   // (uniform) nothing to drop yet
+  // K-th largest key
+  uint32_t tk = 0u;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = tk | (1u << bit);
+    int c = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, xv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, xi, o);
-      const int op = __shfl_xor_sync(0xffffffffu, xp, o);
-      if (op >= 0 && (xp < 0 || ap_better(xv, xi, ov, oi))) { xv = ov; xi = oi; xp = op; }
-    }
-  };
-  warp_worst(wv, wi, wp);
-  if (cnt >= K && ap_better(s, col, wv, wi)) {   // replaces the worst entry
-    if (lane == (wp & 31)) {
-      __stcg(cval + wp, s);
-      __stcg(cidx + wp, col);
-    }
-    wv = INFINITY; wi = -1;
-    int np = -1;
-#pragma unroll
-    for (int j = 0; j < KPL; ++j) {
-      const int p = lane + 32 * j;
-      if (p == wp) { v[j] = s; ix[j] = col; }
-      if (p < K && (np < 0 || ap_better(wv, wi, v[j], ix[j]))) { wv = v[j]; wi = ix[j]; np = p; }
-    }
-    wp = np;
-    warp_worst(wv, wi, wp);
+    for (int j = 0; j < AP_EPL; ++j) c += (valid[j] && key[j] >= cand) ? 1 : 0;
+    if (warp_sum_i(c) >= K) tk = cand;
   }
-  new_thr = wv;
+  int n_gt = 0, n_eq = 0;
+#pragma unroll
+  for (int j = 0; j < AP_EPL; ++j) {
+    n_gt += (valid[j] && key[j] > tk) ? 1 : 0;
+    n_eq += (valid[j] && key[j] == tk) ? 1 : 0;
+  }
+  n_gt = warp_sum_i(n_gt);
+  n_eq = warp_sum_i(n_eq);
+  const int need_eq = K - n_gt;   // >= 1: how many of the entries that tie with the K-th best are kept
+  int it = 0x7fffffff;            // they are the ones with the lowest item index: the need_eq-th smallest index among them
+  if (n_eq > need_eq) {
+    uint32_t ip = 0u;             // largest x with #{ties: idx < x} < need_eq  ==  the need_eq-th smallest tie index
+#pragma unroll 1
+    for (int bit = 30; bit >= 0; --bit) {
+      const uint32_t cand = ip | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int j = 0; j < AP_EPL; ++j) c += (valid[j] && key[j] == tk && (uint32_t)ix[j] < cand) ? 1 : 0;
+      if (warp_sum_i(c) < need_eq) ip = cand;
+    }
+    it = (int)ip;
+  }
+  __syncwarp();   // every lane holds its entries in registers: the buffer may be overwritten
+  int base = 0;
+#pragma unroll
+  for (int j = 0; j < AP_EPL; ++j) {
+    const bool keep = valid[j] && (key[j] > tk || (key[j] == tk && ix[j] <= it));
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int pos = base + __popc(m & ((1u << lane) - 1u));
+      __stcg(cval + pos, v[j]);
+      __stcg(cidx + pos, ix[j]);
+    }
+    base += __popc(m);
+  }
   __syncwarp();
-  if (lane == 0) {
-    s_thr[r] = new_thr;
-    __threadfence_block();
-    atomicExch(&s_lock[r], 0);
-  }
-  return new_thr;
+  // the K-th best score back from its key (the inverse of ap_key)
+  const float t0 = __uint_as_float((tk & 0x80000000u) ? (tk & 0x7fffffffu) : ~tk);
+  out.cnt = base;
+  out.thr = t0;
+  return out;
 }
 
 template <int KCHUNKS, bool TOPK, bool OBS>
@@ -220,12 +251,8 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
   static_assert(AP_NBARS * 8 + 16 <= 128, "barrier block");
   float* s_best = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);   // [2][128] halves' best score per row
   int32_t* s_besti = reinterpret_cast<int32_t*>(s_best + 256);   // [2][128]
-  float* s_bias = reinterpret_cast<float*>(s_besti + 256);       // [2][128] item bias + mu of the tile, by tile parity
-  float* s_thr = s_bias + 256;                                   // [128] TOPK: the row's threshold
-  int* s_cnt = reinterpret_cast<int*>(s_thr + 128);              // [128]
-  int* s_lock = s_cnt + 128;                                     // [128]
-  int* s_minpos = s_lock + 128;                                  // [128] (unused: the cooperative insert rescans)
-  double* s_se = reinterpret_cast<double*>(s_minpos + 128);      // [2][128] OBS: halves' squared-error sums
+  float* s_bias = reinterpret_cast<float*>(s_besti + 256);       // [8][64] item bias + mu of each epilogue warp's columns
+  double* s_se = reinterpret_cast<double*>(s_bias + 512);        // [2][128] OBS: halves' squared-error sums
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * AP_BM;
   const int n_tiles = (n_items + AP_BN - 1) / AP_BN;
@@ -242,7 +269,6 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < 128) { s_thr[tid] = -INFINITY; s_cnt[tid] = 0; s_lock[tid] = 0; s_minpos[tid] = 0; }
   if (warp == 1) {  // 256 TMEM columns = two 128x128 fp32 accumulators
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -260,7 +286,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
       for (int c = 0; c < KCHUNKS; ++c) tma_load_2d(sA + c * AP_CHUNK_BYTES, &tmA, c * AP_KC, m0, &bars[BAR_A]);
       for (int t = 0; t < n_tiles; ++t) {
         const int buf = t & 1;
-        if (t >= 2) mbar_wait(&bars[BAR_EMPTY_B + buf], ((t >> 1) - 1) & 1);  // MMAs of tile t-2 have read the buffer
+        if (t >= 2) mbar_wait_polite(&bars[BAR_EMPTY_B + buf], ((t >> 1) - 1) & 1);  // MMAs of tile t-2 have read the buffer
         mbar_expect_tx(&bars[BAR_FULL_B + buf], kTileBytes);
 #pragma unroll
         for (int c = 0; c < KCHUNKS; ++c)
@@ -274,8 +300,8 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
       const uint32_t a0 = smem_u32(sA);
       for (int t = 0; t < n_tiles; ++t) {
         const int buf = t & 1, acc = t & 1;
-        mbar_wait(&bars[BAR_FULL_B + buf], (t >> 1) & 1);
-        if (t >= 2) mbar_wait(&bars[BAR_TMEM_EMPTY + acc], ((t >> 1) - 1) & 1);  // epilogue drained accumulator acc
+        mbar_wait_polite(&bars[BAR_FULL_B + buf], (t >> 1) & 1);
+        if (t >= 2) mbar_wait_polite(&bars[BAR_TMEM_EMPTY + acc], ((t >> 1) - 1) & 1);  // epilogue drained accumulator acc
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t b0 = smem_u32(sB[buf]);
 #pragma unroll
@@ -301,11 +327,16 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
     const bool row_ok = row < n_users;
     const float bu = row_ok ? ub[row] : 0.0f;
     const float mu_ = *mu;
-    const int et = tid - 64;              // 0..255 among the epilogue threads
     float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains (column % 4)
     int32_t besti[4] = {-1, -1, -1, -1};
-    float* const cval = TOPK && row_ok ? cs.cand_val + (size_t)row * cs.K : nullptr;
-    int32_t* const cidx = TOPK && row_ok ? cs.cand_idx + (size_t)row * cs.K : nullptr;
+    int lcnt = 0;               // TOPK: length and threshold of this lane's row's buffer (this warp's half of the columns)
+    float thr = -INFINITY;
+    const int K = cs.K, C = 4 * cs.K;     // kept entries / buffer capacity
+    float* const cand_val = cs.cand_val;
+    int32_t* const cand_idx = cs.cand_idx;
+    float* const scores = cs.scores;
+    float* const my_val = TOPK ? cs.cand_val + ((size_t)(row_ok ? row : 0) * 2 + half) * (size_t)C : nullptr;
+    int32_t* const my_idx = TOPK ? cs.cand_idx + ((size_t)(row_ok ? row : 0) * 2 + half) * (size_t)C : nullptr;
     // OBS: this row's observed pairs [op, oend), next one's item id / rating
     int64_t op = 0, oend = 0;
     int onext = 0x7fffffff, onext2 = 0x7fffffff;   // the next pair's item id, and the one after it (fetched ahead: a
@@ -327,9 +358,16 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
       const int n0 = t * AP_BN + half * 64;
       // the tile's item biases (+ mu: (dot + b_u) + (b_i + mu), the tensor-core path is tf32-approximate anyway) go
       // to shared memory once per tile; a column's bias is then one broadcast LDS.128 per four columns
-      if (et < AP_BN) s_bias[acc * AP_BN + et] = (t * AP_BN + et < n_items) ? add_rn(__ldg(ib + t * AP_BN + et), mu_) : 0.0f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
-      float thr = TOPK ? s_thr[r_in_tile] : 0.0f;
+      // (per WARP: its own 64 columns, two per lane -- no barrier between the epilogue warps)
+      {
+        float* const wb = s_bias + (size_t)ew * 64;
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          const int cc = n0 + lane + 32 * x;
+          wb[lane + 32 * x] = cc < n_items ? add_rn(__ldg(ib + cc), mu_) : 0.0f;
+        }
+        __syncwarp();
+      }
       if (OBS) {
         while (onext < n0) obs_advance();  // pairs of the columns the other half owns, or of earlier tiles
       }
@@ -339,7 +377,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
       for (int j = 0; j < 2; ++j) {
         float v[32];
         tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * AP_BN + half * 64 + j * 32), v);
-        const float4* sb4 = reinterpret_cast<const float4*>(s_bias + acc * AP_BN + half * 64 + j * 32);
+        const float4* sb4 = reinterpret_cast<const float4*>(s_bias + (size_t)ew * 64 + j * 32);
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
           const float4 b4 = sb4[c4];
@@ -350,21 +388,14 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
             const int col = n0 + j * 32 + c;
             const float s = add_rn(add_rn(v[c], bu), bb[q]);   // als3.py:112: U.V^T + W_user + W_work + bias
             const bool ok = row_ok && col < n_items;
-            if (cs.scores && ok) cs.scores[(size_t)row * n_items + col] = s;
+            if (scores && ok) scores[(size_t)row * n_items + col] = s;
             if (ok && s > best[q]) { best[q] = s; besti[q] = col; }
             if (TOPK) {
-              // lanes whose column reaches their row's threshold; the warp serves them one after the other, together
-              unsigned need = __ballot_sync(0xffffffffu, ok && s >= thr);
-              while (need) {
-                const int src = __ffs(need) - 1;
-                need &= need - 1;
-                const float bs = __shfl_sync(0xffffffffu, s, src);
-                const int bcol = __shfl_sync(0xffffffffu, col, src);
-                const int brow = quarter * 32 + src;
-                const float nt = ap_topk_insert_warp<AP_MAX_CAND / 32>(cs.cand_val + (size_t)(m0 + brow) * cs.K,
-                                                                       cs.cand_idx + (size_t)(m0 + brow) * cs.K, cs.K, s_lock,
-                                                                       s_cnt, s_thr, brow, bs, bcol, lane);
-                if (lane == src) thr = nt;
+              // hot path: the row's own lane appends (two stores); compaction is checked once per 32-column chunk
+              if (ok && s > thr) {
+                __stcg(my_val + lcnt, s);
+                __stcg(my_idx + lcnt, col);
+                ++lcnt;
               }
             }
             if (OBS) {
@@ -377,6 +408,19 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
                 } while (onext == col);
               }
             }
+          }
+        }
+        if (TOPK) {
+          // a chunk appends at most 32 entries per row: a buffer with less than that left is compacted now, by the whole
+          // warp, one row after the other
+          unsigned full = __ballot_sync(0xffffffffu, lcnt > C - 32);
+          while (full) {
+            const int src = __ffs(full) - 1;
+            full &= full - 1;
+            const int bcnt = __shfl_sync(0xffffffffu, lcnt, src);
+            const size_t list = ((size_t)(m0 + quarter * 32 + src) * 2 + half) * (size_t)C;
+            const ApListState ns = ap_compact_warp(cand_val + list, cand_idx + list, bcnt, K, lane);
+            if (lane == src) { lcnt = ns.cnt; thr = ns.thr; }
           }
         }
       }
@@ -393,6 +437,10 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
     s_best[half * 128 + r_in_tile] = bs;
     s_besti[half * 128 + r_in_tile] = bi_;
     if (OBS) s_se[half * 128 + r_in_tile] = se;
+    if (TOPK && row_ok) {   // the buffer's final length and threshold, for the rescore
+      cs.cand_cnt[(size_t)row * 2 + half] = lcnt;
+      cs.cand_thr[(size_t)row * 2 + half] = thr;
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -407,12 +455,6 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
       if (cs.best_score) cs.best_score[row] = bs;
       if (cs.best_item) cs.best_item[row] = bi_;
       if (OBS) cs.row_se[row] = s_se[tid] + s_se[128 + tid];
-      if (TOPK) {  // fewer than K items in all: mark the unused candidate slots
-        for (int j = s_cnt[tid]; j < cs.K; ++j) {
-          __stcg(cs.cand_val + (size_t)row * cs.K + j, -INFINITY);
-          __stcg(cs.cand_idx + (size_t)row * cs.K + j, -1);
-        }
-      }
     }
   }
   if (warp == 1) {
@@ -424,70 +466,97 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
 // ---- exact rescore of the tensor-core candidates, with a certificate --------------------------------------------------
 // The tensor cores rank with tf32 operands (fp32 words whose low 13 mantissa bits are ignored): a score is off by at most
 //   E_u = 2.01 * 2^-10 * ||u||_2 * max_i ||v_i||_2  (+ fp32 accumulation / bias roundings, covered by the 2^-9 used).
-// Every item OUTSIDE a row's K candidates has a tensor-core score <= T (the K-th best), hence an exact score <= T + E_u.
-// The candidates are rescored in float64 -- the reference's own precision: als3.py:112 is numpy float64 -- and ranked;
-// the first k of them are the exact top-k of the WHOLE row if the k-th exact score is > T + E_u.  Rows for which that
-// cannot be shown (near-ties deeper than the K - k spare candidates) are appended to `uncert` and redone exactly over
-// all items by allpairs_exact_rows_kernel.  One warp per row.
-__global__ void __launch_bounds__(256) allpairs_rescore_kernel(const float* __restrict__ U, const float* __restrict__ V,
-                                                               const float* __restrict__ ub, const float* __restrict__ ib,
-                                                               const float* __restrict__ mu, int n_users, int n_items, int dim,
-                                                               int64_t us, int64_t is, const float* __restrict__ cand_val,
-                                                               const int32_t* __restrict__ cand_idx, int K, int k,
-                                                               const float* __restrict__ vmax2, double* __restrict__ out_val,
-                                                               int32_t* __restrict__ out_idx, int32_t* __restrict__ uncert,
-                                                               int32_t* __restrict__ n_uncert) {
-  __shared__ double s_sc[8][AP_MAX_CAND];
-  __shared__ int s_ix[8][AP_MAX_CAND];
+// Every item that is NOT in a row's two buffers scored at most T = max of the buffers' thresholds on the tensor cores,
+// hence at most T + E_u exactly (a buffer that never had to drop anything has threshold -inf).  The candidates are
+// rescored in float64 -- the reference's own precision: als3.py:112 is numpy float64 -- and the k best picked (score
+// descending, lowest item index on ties); they are the exact top-k of the WHOLE row if the k-th exact score is > T + E_u.
+// Rows for which that cannot be shown (near-ties deeper than the spare candidates) are appended to `uncert` and redone
+// exactly over all items by allpairs_exact_rows_kernel.  One warp per row.
+constexpr int RS_WARPS = 2;
+__global__ void __launch_bounds__(32 * RS_WARPS) allpairs_rescore_kernel(
+    const float* __restrict__ U, const float* __restrict__ V, const float* __restrict__ ub, const float* __restrict__ ib,
+    const float* __restrict__ mu, int n_users, int n_items, int dim, int64_t us, int64_t is,
+    const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_cnt,
+    const float* __restrict__ cand_thr, int K, int k, const float* __restrict__ vmax2, double* __restrict__ out_val,
+    int32_t* __restrict__ out_idx, int32_t* __restrict__ uncert, int32_t* __restrict__ n_uncert) {
+  __shared__ double s_sc[RS_WARPS][8 * AP_MAX_CAND];
+  __shared__ int s_ix[RS_WARPS][8 * AP_MAX_CAND];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + w;
+  const int row = blockIdx.x * RS_WARPS + w;
   if (row >= n_users) return;
+  const int C = 4 * K;
+  __shared__ float s_u[RS_WARPS][512];
   const float* urow = U + (size_t)row * us;
   double un2 = 0.0;
-  for (int d = lane; d < dim; d += 32) un2 += (double)urow[d] * (double)urow[d];
+  for (int d = lane; d < dim; d += 32) {
+    const float x = urow[d];
+    s_u[w][d] = x;
+    un2 += (double)x * (double)x;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) un2 += __shfl_xor_sync(0xffffffffu, un2, o);
-  float T = INFINITY;   // the worst tensor-core score among the candidates
-  int n_cand = 0;
-  for (int j = 0; j < K; ++j) {
-    const int it = cand_idx[(size_t)row * K + j];
-    double sc = -INFINITY;
-    if (it >= 0) {
-      const float* vrow = V + (size_t)it * is;
-      double acc = 0.0;
-      for (int d = lane; d < dim; d += 32) acc += (double)urow[d] * (double)vrow[d];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      sc = ((acc + (double)ub[row]) + (double)ib[it]) + (double)mu[0];   // als3.py:112, in float64 like numpy
-      T = fminf(T, cand_val[(size_t)row * K + j]);
-      ++n_cand;
+  __syncwarp();
+  const int cnt0 = min(cand_cnt[(size_t)row * 2], C), cnt1 = min(cand_cnt[(size_t)row * 2 + 1], C);
+  const float T = fmaxf(cand_thr[(size_t)row * 2], cand_thr[(size_t)row * 2 + 1]);
+  const int n = cnt0 + cnt1;
+  // a candidate per lane at a time: the lanes' row gathers are independent and in flight together (one warp walking
+  // the candidates one by one paid two dependent global latencies per candidate)
+  const bool vec = (dim % 4 == 0) && (is % 4 == 0) && (((uintptr_t)V & 15u) == 0);
+  for (int c = lane; c < n; c += 32) {
+    const size_t at = c < cnt0 ? (size_t)row * 2 * C + c : ((size_t)row * 2 + 1) * C + (c - cnt0);
+    const int it = cand_idx[at];
+    const float* vrow = V + (size_t)it * is;
+    double acc = 0.0;
+    if (vec) {
+      for (int d = 0; d < dim; d += 4) {
+        const float4 q = ld_gather_f4(reinterpret_cast<const float4*>(vrow + d));
+        acc += (double)s_u[w][d] * (double)q.x;
+        acc += (double)s_u[w][d + 1] * (double)q.y;
+        acc += (double)s_u[w][d + 2] * (double)q.z;
+        acc += (double)s_u[w][d + 3] * (double)q.w;
+      }
+    } else {
+      for (int d = 0; d < dim; ++d) acc += (double)s_u[w][d] * (double)vrow[d];
     }
-    if (lane == 0) { s_sc[w][j] = sc; s_ix[w][j] = it; }
+    s_sc[w][c] = ((acc + (double)ub[row]) + (double)ib[it]) + (double)mu[0];   // als3.py:112, in float64 like numpy
+    s_ix[w][c] = it;
   }
   __syncwarp();
+  // k rounds of a warp-wide arg-max over the candidates that come AFTER the previous pick in the total order
+  double last_v = INFINITY, kth = -INFINITY;
+  int last_i = -1, got = 0;
+  for (int r = 0; r < k; ++r) {
+    double bv = -INFINITY;
+    int bi = -1;
+    for (int c = lane; c < n; c += 32) {
+      const double v = s_sc[w][c];
+      const int i = s_ix[w][c];
+      const bool after = v < last_v || (v == last_v && i > last_i);
+      if (after && (bi < 0 || v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      out_val[(size_t)row * k + r] = bi >= 0 ? bv : -INFINITY;
+      out_idx[(size_t)row * k + r] = bi;
+    }
+    if (bi < 0) {
+      if (lane == 0)
+        for (int rr = r + 1; rr < k; ++rr) { out_val[(size_t)row * k + rr] = -INFINITY; out_idx[(size_t)row * k + rr] = -1; }
+      break;
+    }
+    last_v = bv; last_i = bi; kth = bv; ++got;
+  }
   if (lane == 0) {
-    // insertion sort: score descending, item index ascending; empty slots (index -1, -inf) last
-    for (int a = 1; a < K; ++a) {
-      const double v = s_sc[w][a];
-      const int ix = s_ix[w][a];
-      int b = a - 1;
-      while (b >= 0 && ix >= 0 && (s_ix[w][b] < 0 || v > s_sc[w][b] || (v == s_sc[w][b] && ix < s_ix[w][b]))) {
-        s_sc[w][b + 1] = s_sc[w][b];
-        s_ix[w][b + 1] = s_ix[w][b];
-        --b;
-      }
-      s_sc[w][b + 1] = v;
-      s_ix[w][b + 1] = ix;
-    }
     const int kk = k < n_items ? k : n_items;
-    for (int j = 0; j < k; ++j) {
-      out_val[(size_t)row * k + j] = j < n_cand ? s_sc[w][j] : -INFINITY;
-      out_idx[(size_t)row * k + j] = j < n_cand ? s_ix[w][j] : -1;
-    }
-    bool certified = n_cand >= n_items;   // every item is a candidate: nothing outside
-    if (!certified && n_cand >= kk) {
+    bool certified = T == -INFINITY;   // nothing was ever dropped: every rankable item is a candidate
+    if (!certified && got >= kk) {
       const double E = 0.001953125 * sqrt(un2) * sqrt((double)vmax2[0]);   // 2^-9 * ||u|| * max ||v||
-      certified = s_sc[w][kk - 1] > (double)T + E;
+      certified = kth > (double)T + E;
     }
     if (!certified) uncert[atomicAdd(n_uncert, 1)] = row;
   }
@@ -787,7 +856,7 @@ static int launch_allpairs_tc(const float* user_feat, const float* item_feat, co
   if ((rc = make_map(&ma, user_feat, n_users, dim, user_stride))) return rc;
   if ((rc = make_map(&mb, item_feat, n_items, dim, item_stride))) return rc;
   const int kch = dim / 32;
-  const size_t smem = (size_t)3 * kch * AP_CHUNK_BYTES + 1024 + 128 + (2 * 256 + 256 + 4 * 128) * 4 + 256 * 8 + 64;
+  const size_t smem = (size_t)3 * kch * AP_CHUNK_BYTES + 1024 + 128 + (2 * 256 + 512) * 4 + 256 * 8 + 64;
   const unsigned grid = (unsigned)((n_users + AP_BM - 1) / AP_BM);
   const bool topk = cs.cand_val != nullptr, obs = cs.obs_indptr != nullptr;
 #define TFR_AP_LAUNCH(KC_, TK_, OB_)                                                                                   \
@@ -814,7 +883,7 @@ static int ap_exact_ctas() { return 2 * sm_count(); }
 
 extern "C" int64_t tfr_allpairs_topk_workspace_bytes(int64_t n_users, int64_t n_items, int32_t k, int32_t n_cand) {
   if (n_users < 0 || n_items < 0 || k <= 0 || n_cand < k || n_cand > AP_MAX_CAND) return TFR_ERR_INVALID;
-  return 256 + 2 * align_up(n_users * (int64_t)n_cand * 4, 256) + align_up(n_users * 4, 256) +
+  return 256 + 2 * align_up(8 * n_users * (int64_t)n_cand * 4, 256) + 3 * align_up(2 * n_users * 4, 256) +
          align_up((int64_t)ap_exact_ctas() * n_items * 8, 256) + 256;
 }
 
@@ -850,25 +919,31 @@ extern "C" int tfr_allpairs_consume(const float* user_feat, const float* item_fe
     }
     char* w = reinterpret_cast<char*>(align_up((int64_t)(uintptr_t)workspace, 256));
     vmax2 = reinterpret_cast<float*>(w); w += 256;
-    cs.cand_val = reinterpret_cast<float*>(w); w += align_up(n_users * (int64_t)n_cand * 4, 256);
-    cs.cand_idx = reinterpret_cast<int32_t*>(w); w += align_up(n_users * (int64_t)n_cand * 4, 256);
-    uncert = reinterpret_cast<int32_t*>(w); w += align_up(n_users * 4, 256);
+    cs.cand_val = reinterpret_cast<float*>(w); w += align_up(8 * n_users * (int64_t)n_cand * 4, 256);
+    cs.cand_idx = reinterpret_cast<int32_t*>(w); w += align_up(8 * n_users * (int64_t)n_cand * 4, 256);
+    cs.cand_cnt = reinterpret_cast<int32_t*>(w); w += align_up(2 * n_users * 4, 256);
+    cs.cand_thr = reinterpret_cast<float*>(w); w += align_up(2 * n_users * 4, 256);
+    uncert = reinterpret_cast<int32_t*>(w); w += align_up(2 * n_users * 4, 256);
     scratch = reinterpret_cast<double*>(w);
     cs.K = n_cand;
     TFR_CUDA(cudaMemsetAsync(vmax2, 0, 256, st));
     TFR_CUDA(cudaMemsetAsync(n_uncertified, 0, sizeof(int32_t), st));
   }
   if (obs) { cs.obs_indptr = obs_indptr; cs.obs_item = obs_item; cs.obs_rate = obs_rate; cs.row_se = row_se; }
-  int rc = launch_allpairs_tc(user_feat, item_feat, user_bias, item_bias, mu, n_users, n_items, dim, user_stride,
-                              item_stride, cs, st);
+  const int stages = tune(TUNE_AP_STAGES);
+  int rc = TFR_OK;
+  if (!topk || (stages & 1))
+    rc = launch_allpairs_tc(user_feat, item_feat, user_bias, item_bias, mu, n_users, n_items, dim, user_stride, item_stride,
+                            cs, st);
   if (rc) return rc;
-  if (topk) {
+  if (topk && (stages & 2)) {
     allpairs_vmax2_kernel<<<(unsigned)((n_items * 32 + 255) / 256), 256, 0, st>>>(item_feat, (int)n_items, dim, item_stride, vmax2);
     TFR_LAUNCH_CHECK();
-    allpairs_rescore_kernel<<<(unsigned)((n_users + 7) / 8), 256, 0, st>>>(
+    allpairs_rescore_kernel<<<(unsigned)((n_users + RS_WARPS - 1) / RS_WARPS), 32 * RS_WARPS, 0, st>>>(
         user_feat, item_feat, user_bias, item_bias, mu, (int)n_users, (int)n_items, dim, user_stride, item_stride,
-        cs.cand_val, cs.cand_idx, n_cand, k, vmax2, topk_val, topk_idx, uncert, n_uncertified);
+        cs.cand_val, cs.cand_idx, cs.cand_cnt, cs.cand_thr, n_cand, k, vmax2, topk_val, topk_idx, uncert, n_uncertified);
     TFR_LAUNCH_CHECK();
+    if (stages & 4)
     allpairs_exact_rows_kernel<<<(unsigned)ap_exact_ctas(), 1024, 0, st>>>(user_feat, item_feat, user_bias, item_bias, mu,
                                                                          (int)n_items, dim, user_stride, item_stride, uncert,
                                                                          n_uncertified, k, scratch, topk_val, topk_idx);

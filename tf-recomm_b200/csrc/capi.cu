@@ -42,7 +42,7 @@ const TuneEntry kTune[TUNE_COUNT] = {
     // vs 125 us); profiles/r02_pass_ring_vs_ldg.md
     {"PASS_RING", 0},
     {"RING_STAGES", 4}, {"RING_STAGE_KB", 24}, {"RING_THREADS", 320}, {"RING_L2_HINT", 2}, {"RING_CTAS_PER_SM", 2},
-    {"RING_SLOT_MODE", 1}, {"TL_EVERY_CTA", 0},
+    {"RING_SLOT_MODE", 1}, {"AP_STAGES", 7}, {"TL_EVERY_CTA", 0},
     // programmatic dependent launch along tiles -> fix-up -> pass: no gain at the ML-25M shape (178.2 vs 177.5 us per
     // step) and a loss at the ML-1M shape (the early-resident dependents delay the side stream's id sort: 53 vs 37 us)
     {"PDL", 0},

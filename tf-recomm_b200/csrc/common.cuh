@@ -25,6 +25,7 @@ enum TuneKey {
   TUNE_PASS_RING,         // 1: interleaved tables take the TMA-bulk ring pass (adam_ring.cu), 0: the LDG pass
   TUNE_RING_STAGES, TUNE_RING_STAGE_KB, TUNE_RING_THREADS, TUNE_RING_L2_HINT, TUNE_RING_CTAS_PER_SM,
   TUNE_RING_SLOT_MODE,
+  TUNE_AP_STAGES,         // debug: which stages of tfr_allpairs_consume's ranking run (1 sweep | 2 rescore | 4 exact rows)
   TUNE_TL_EVERY_CTA,      // debug timeline: the pass's exit stamp from every CTA instead of a sample
   TUNE_PDL,               // 1: programmatic dependent launch along the step's critical path (see pdl_wait)
   TUNE_COUNT
