@@ -282,28 +282,34 @@ def run_workload(name, args, torch, with_e2e=True, with_roofline=True, sample_cl
     if with_e2e:
         rng = np.random.default_rng(3)
         batches = []
-        for _ in range(min(args.steps, 50) + 3):
+        for _ in range(min(args.steps, 200) + 12):
             rows = rng.integers(0, n_train, B)
             batches.append((cols[0][rows].astype(np.float64), cols[1][rows].astype(np.float64),
                             cols[2][rows].astype(np.float64)))   # float64 columns: what ShuffleIterator yields
-        # the driver's loop (svd_train_val.py): batch t+1 is handed over, then step t is asked for and returns its
-        # predictions (host) -- the packing, H2D copy and id sort of t+1 run under step t.  Every step's H2D (12 B / rating) and D2H
-        # (8 B / rating) are inside the timed region.
-        for b in batches[:3]:
-            eng.train_step_host(*b)
+        # the driver's loop (svd_train_val.py): batches t+1 and t+2 have been handed over when step t is asked for and
+        # returns its predictions (host) -- t+2 is packed and copied by the feed worker thread while the ids of t+1 are
+        # sorted under step t's table pass.  Every step's H2D (12 B / rating) and D2H (4 or 8 B / rating) are inside
+        # the timed region.
+        AHEAD, WARM = 2, 12
+
+        def feed_loop(bs):
+            for j in range(min(AHEAD, len(bs))):
+                eng.prefetch_host(*bs[j])
+            for j in range(len(bs)):
+                if j + AHEAD < len(bs):
+                    eng.prefetch_host(*bs[j + AHEAD])   # handed over before step j is asked for
+                eng.train_step_host(*bs[j])
+        # warm-up in the same pattern: every staging set and every step graph (one per staging set, captured on first use)
+        feed_loop(batches[:WARM])
         torch.cuda.synchronize()
-        eng.prefetch_host(*batches[3])
-        t0 = time.perf_counter()
-        for j in range(3, len(batches)):
-            if j + 1 < len(batches):
-                eng.prefetch_host(*batches[j + 1])   # handed over before step j is asked for: overlaps it on the device
-            eng.train_step_host(*batches[j])
+        t0 = time.perf_counter()   # (the priming hand-overs are inside: every timed step's H2D is counted)
+        feed_loop(batches[WARM:])
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        n = len(batches) - 3
+        n = len(batches) - WARM
         res["e2e"] = {"value": B * n / dt, "unit": "ratings/s", "h2d_bytes_per_step": eng.h2d_bytes(B),
                       "d2h_bytes_per_step": eng.d2h_bytes(B), "ms_per_step": dt / n * 1e3, "steps": n,
-                      "path": "SvdEngine.train_step_host + prefetch_host of the next batch (what Session.run([train_op, logits, "
+                      "path": "SvdEngine.train_step_host + prefetch_host two batches ahead (what Session.run([train_op, logits, "
                               "infer], feed_dict) / Session.prefetch call; the loop of svd_train_val.py)"}
     if with_roofline and w["d"] % 4 == 0:
         res["roofline"] = kernel_roofline(eng, w, cols, min(args.steps, 20), torch, peak, peak_src)

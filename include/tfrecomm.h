@@ -409,10 +409,11 @@ int tfr_host_pack_feed(const void* users_host, int32_t users_dtype, int64_t user
                        int32_t items_dtype, int64_t items_stride, const void* rates_host, int32_t rates_dtype,
                        int64_t rates_stride, int64_t n, void* staging_host /* 12 * n bytes */);
 
-/* ---- the feed_dict step, host side AND device side in two calls (what Session.prefetch / Session.run issue) -------------
+/* ---- the feed_dict step (what Session.prefetch / Session.run issue) -----------------------------------------------------
  * One staging set of the feed path; all memory and the five events (cudaEvent_t, tfr_event_create) are the caller's.
- * Two or three sets are used round-robin.  Every reuse is ordered by the set's events: the pinned buffer is never repacked
- * while a copy out of it is queued, the device buffers never overwritten while a step still reads them. */
+ * Three or four sets are used round-robin.  Every reuse is ordered by the set's events (or by the step stream itself): the
+ * pinned buffer is never repacked while a copy out of it is queued, the device buffers never overwritten while a step
+ * still reads them. */
 typedef struct {
   void* h_feed;      /* pinned host, 12 * B bytes: [users int32 | items int32 | rates float32]                 */
   void* d_feed;      /* device, same layout                                                                    */
@@ -421,22 +422,59 @@ typedef struct {
   void* workspace;   /* tfr_svd_step_workspace_bytes(B, dim)                                                   */
   int64_t workspace_bytes;
   void *ev_h2d, *ev_sorted, *ev_pred, *ev_d2h, *ev_done;
-  int32_t used;      /* set by the library: the set has been through a prefetch / a step before               */
+  int32_t used;      /* set by the library: the set has been staged before (its events have a history)        */
   int32_t copied;    /* set by the library: a copy out of d_out has been issued                               */
+  int32_t sorted;    /* set by the library: the batch's ids are sorted (or their sort is queued)               */
+  int32_t staged;    /* set by the library: h_feed holds a packed batch that has not gone to the device        */
+  uint32_t* d_sync;  /* device, 2 words, zero-initialised by the caller (graph steps: CTA counter, delivery count)  */
+  uint32_t* h_flag;  /* pinned host, 1 word, zero-initialised by the caller (graph steps: the delivery count)       */
+  uint32_t deliver_seq; /* set by the library: *h_flag >= deliver_seq once the last graph step's predictions are in h_out */
+  uint32_t reserved;
 } tfr_feed_set;
-/* pack (tfr_host_pack_feed_checked: value cast + range check) -> H2D copy -> id sort, the last two on side_stream: needs no
- * table data, so it runs under whatever the step stream is doing (normally the previous step's table pass).  Blocks
- * the HOST only on ev_h2d of the set's previous use (the pinned buffer must be free to repack). */
+/* tfr_svd_feed_stage: HOST ONLY -- pack (tfr_host_pack_feed_checked: value cast + range check) into h_feed.  Needs nothing of
+ * the model, blocks only on ev_h2d of the set's previous use (the pinned buffer must be free to repack), touches no stream:
+ * it may run on any host thread (the engine's feed worker).
+ * tfr_svd_feed_sort: H2D copy of the staged batch + the sort of its ids on side_stream, behind after_event when one is
+ * given (NULL: as soon as the set's previous step has finished). */
+int tfr_svd_feed_stage(const tfr_svd_tables* t, tfr_feed_set* set, const void* users_host, int32_t users_dtype,
+                       int64_t users_stride, const void* items_host, int32_t items_dtype, int64_t items_stride,
+                       const void* rates_host, int32_t rates_dtype, int64_t rates_stride, int64_t B);
+int tfr_svd_feed_sort(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set, int64_t B, void* side_stream,
+                      void* after_event);
+/* stage + sort (after_event = NULL) in one call. */
 int tfr_svd_feed_prefetch(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set, const void* users_host,
                           int32_t users_dtype, int64_t users_stride, const void* items_host, int32_t items_dtype,
                           int64_t items_stride, const void* rates_host, int32_t rates_dtype, int64_t rates_stride,
                           int64_t B, void* side_stream);
 /* forward + segment sums -> [copy of the predictions to h_out on copy_stream, beside the table pass] -> Adam pass / SGD.
  * fetch: 0 = nothing, 1 = infer only (B floats into h_out[B..2B); the README head has logits == infer), 2 = logits and
- * infer.  Asynchronous: the caller waits on set->ev_d2h (tfr_event_synchronize) before reading h_out. */
+ * infer.  Asynchronous: the caller waits on set->ev_d2h (tfr_event_synchronize) before reading h_out.
+ * next_set (optional): a STAGED set -- its tfr_svd_feed_sort is queued on side_stream behind this step's forward
+ * (after_event = this set's ev_pred). */
 int tfr_svd_feed_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set, int64_t B, int32_t flags,
-                      int32_t var_mask, int32_t fetch, void* stream, void* copy_stream);
+                      int32_t var_mask, int32_t fetch, void* stream, void* copy_stream, tfr_feed_set* next_set,
+                      void* side_stream);
+/* The same step as ONE CUDA graph of kernels only: forward + segment sums -> { table pass | delivery of the predictions ->
+ * fetch + id sort of next_set }.  The staged batch is read, and the predictions are written, by kernels over the pinned
+ * buffers (zero-copy; h_feed / h_out / h_flag must be device-mapped pinned memory, cudaHostAlloc or torch pin_memory):
+ * the shape of the device-resident stream path, whose batch assembly + sort are known to run beside the table pass.
+ * Measured on B200 (profiles/r02_feed_path.md): launched eagerly on other streams, neither the sort nor the copy of the
+ * predictions gets going before the pass has drained.
+ * early_side != 0 (small tables, where the sort is longer than the pass): the fetch + sort branch forks at the start of the
+ * step instead, and the delivery sits on the step stream in front of the pass.
+ * create: captures on the two given streams (used for nothing else; relaxed mode) and instantiates; the executable graph
+ * is bound to this (set, next_set, B, flags, var_mask, fetch) and to the tables' addresses; tfr_graph_destroy frees it.
+ * launch: set must be sorted, next_set (if the graph was created with one) staged.  The predictions are in h_out when
+ * *h_flag has reached set->deliver_seq (tfr_host_wait_flag); ev_h2d (next_set) is recorded inside the graph, ev_done (set)
+ * behind it. */
+int tfr_svd_feed_graph_create(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set, tfr_feed_set* next_set,
+                              int64_t B, int32_t flags, int32_t var_mask, int32_t fetch, int32_t early_side,
+                              void* capture_stream, void* capture_side_stream, void** graph_exec_out);
+int tfr_svd_feed_graph_launch(void* graph_exec, tfr_feed_set* set, tfr_feed_set* next_set, int32_t fetch, void* stream);
 int tfr_event_synchronize(void* event);
+/* spins (HOST) until *flag_host, a 32-bit counter in pinned memory, has reached at_least (wrap-around safe); TFR_ERR_CUDA
+ * after timeout_us. */
+int tfr_host_wait_flag(const void* flag_host, uint32_t at_least, int64_t timeout_us);
 
 /* ---- DISCRETE-branch metrics on the device: replaces the host code of svd_train_val.py:94-98,138-143 -------------------
  * out4 (device, 4 doubles) = [ sum_b sigmoid_cross_entropy(labels_b, logits_b)   (cost_nll, ops.py:125-126),

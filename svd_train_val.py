@@ -83,13 +83,21 @@ def svd(train, test, args, log=print):
 
         def feed_of(b):
             return {user_batch: b[0], item_batch: b[1], rate_batch: b[2], wins_batch: b[3], fails_batch: b[4]}
-        # session mode: this driver owns the iterator, so batch i+1 is drawn (same RandomState order as the reference's
-        # loop: one draw per step) and handed to sess.prefetch BEFORE step i is asked for -- its packing, H2D copy and id
-        # sort then overlap step i on the device
-        ahead = None
-        if not (args.mode == "stream" and not discrete) and total_steps > 0:
-            ahead = next(iter_train)
-            sess.prefetch(feed_of(ahead))
+        # session mode: this driver owns the iterator, so batches i+1 and i+2 are drawn (same RandomState order as the
+        # reference's loop: one draw per step, total_steps draws in all) and handed to sess.prefetch BEFORE step i is
+        # asked for -- i+2 is being packed and copied by the feed worker while i+1's ids are sorted under step i's pass
+        AHEAD = 2
+        drawn = []          # batches handed over, not stepped yet
+        n_drawn = 0
+
+        def draw_ahead():
+            nonlocal n_drawn
+            while len(drawn) < AHEAD + 1 and n_drawn < total_steps:
+                drawn.append(next(iter_train))
+                n_drawn += 1
+                sess.prefetch(feed_of(drawn[-1]))
+        if not (args.mode == "stream" and not discrete):
+            draw_ahead()
         while i < total_steps:
             if args.mode == "stream" and not discrete:
                 # steps i .. next report: the first report comes after one step, then every nb_batches
@@ -105,11 +113,9 @@ def svd(train, test, args, log=print):
                 if report_at % nb_batches != 0:
                     continue  # the tail after the last full epoch is trained but not reported (:106)
             else:
-                cur = ahead
+                draw_ahead()
+                cur = drawn.pop(0)
                 train_users, train_items, train_rates, train_wins, train_fails = cur
-                if i + 1 < total_steps:
-                    ahead = next(iter_train)
-                    sess.prefetch(feed_of(ahead))
                 _, train_logits, train_infer = sess.run([train_op, logits, infer], feed_dict=feed_of(cur))
                 if discrete:
                     if host_metrics:   # the reference's own host code (:94-98), kept as the cross-check

@@ -745,6 +745,57 @@ def test_host_fed_unfetched_and_prefetched_match_fetched():
     assert np.array_equal(eng_p.get_tables()["user_feat"], eng_f.get_tables()["user_feat"])
 
 
+@pytest.mark.parametrize("shape", [(3000, 2000, 64, 4096), (700, 500, 15, 1000), (50, 40, 8, 63)])
+def test_host_fed_two_ahead_graph_steps_match_plain_steps(shape):
+    """The driver's loop: batches t+1 and t+2 handed over before step t is asked for, so that every step is the graph that
+    also fetches + sorts the staged next batch (forced here: each step waits for the feed worker first).  Tables and
+    predictions are bit-identical to the plain one-call-per-step loop, with and without the graph path, and a batch
+    whose ids are out of range raises when it is stepped and trains nothing."""
+    U, I, d, B = shape
+    steps = 11
+    rng = np.random.default_rng(5)
+    batches = [tuple(c.astype(np.float64) for c in make_batch(rng, U, I, B)) for _ in range(steps)]
+    eng_a, _ = both(U, I, d, 1e-3, 0.05)
+    eng_b, _ = both(U, I, d, 1e-3, 0.05)
+    eng_c, _ = both(U, I, d, 1e-3, 0.05)
+    eng_c.feed_graphs = False
+    preds = {0: [], 1: [], 2: []}
+    for b in batches:
+        preds[0].append(eng_a.train_step_host(*b))
+    for n, eng in ((1, eng_b), (2, eng_c)):
+        for j in range(2):
+            eng.prefetch_host(*batches[j])
+        for j, b in enumerate(batches):
+            if j + 2 < steps:
+                eng.prefetch_host(*batches[j + 2])
+            for e in eng._host_state[B]["pending"]:
+                if e["fut"] is not None:
+                    e["fut"].result()
+            preds[n].append(eng.train_step_host(*b))
+    torch.cuda.synchronize()
+    assert any(k[0] == "feed" and k[3] is not None for k in eng_b._graphs if isinstance(k, tuple))   # graphs WITH a next set ran
+    ta, tb, tc = eng_a.get_tables(), eng_b.get_tables(), eng_c.get_tables()
+    for n in ta:
+        assert np.array_equal(ta[n], tb[n]), n
+        assert np.array_equal(ta[n], tc[n]), n
+    for k in range(steps):
+        for n in (1, 2):
+            assert np.array_equal(preds[0][k][0], preds[n][k][0]) and np.array_equal(preds[0][k][1], preds[n][k][1])
+    assert eng_a.global_step == eng_b.global_step == steps
+    # a bad batch handed over early: the error comes when it is stepped
+    bad = tuple(c.copy() for c in batches[0])
+    bad[0][3] = U
+    eng_b.prefetch_host(*batches[1])
+    eng_b.prefetch_host(*bad)
+    eng_b.train_step_host(*batches[1])
+    eng_a.train_step_host(*batches[1])
+    with pytest.raises(_lib.TfrError):
+        eng_b.train_step_host(*bad)
+    torch.cuda.synchronize()
+    assert np.array_equal(eng_a.get_tables()["user_feat"], eng_b.get_tables()["user_feat"])
+    assert eng_b.global_step == steps + 1
+
+
 def test_out_of_range_ids_raise():
     """ids outside the tables are an error where they enter (TF's lookup raises InvalidArgumentError on the CPU)."""
     U, I, d, B = 50, 40, 8, 64

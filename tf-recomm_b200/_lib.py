@@ -62,7 +62,8 @@ class FeedSet(C.Structure):
     """Mirror of tfr_feed_set."""
     _fields_ = [("h_feed", vp), ("d_feed", vp), ("d_out", vp), ("h_out", vp), ("workspace", vp), ("workspace_bytes", i64),
                 ("ev_h2d", vp), ("ev_sorted", vp), ("ev_pred", vp), ("ev_d2h", vp), ("ev_done", vp),
-                ("used", i32), ("copied", i32)]
+                ("used", i32), ("copied", i32), ("sorted", i32), ("staged", i32),
+                ("d_sync", vp), ("h_flag", vp), ("deliver_seq", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class FmTables(C.Structure):
@@ -105,8 +106,15 @@ _PROTOS = {
                                      C.POINTER(vp), i32, C.POINTER(vp)]),
     "tfr_svd_feed_prefetch": (C.c_int, [C.POINTER(SvdTables), vp, C.POINTER(FeedSet), vp, i32, i64, vp, i32, i64, vp, i32, i64,
                                         i64, vp]),
-    "tfr_svd_feed_step": (C.c_int, [C.POINTER(SvdTables), vp, C.POINTER(FeedSet), i64, i32, i32, i32, vp, vp]),
+    "tfr_svd_feed_stage": (C.c_int, [C.POINTER(SvdTables), C.POINTER(FeedSet), vp, i32, i64, vp, i32, i64, vp, i32, i64, i64]),
+    "tfr_svd_feed_graph_create": (C.c_int, [C.POINTER(SvdTables), vp, C.POINTER(FeedSet), C.POINTER(FeedSet), i64, i32, i32, i32,
+                                            i32, vp, vp, C.POINTER(vp)]),
+    "tfr_svd_feed_graph_launch": (C.c_int, [vp, C.POINTER(FeedSet), C.POINTER(FeedSet), i32, vp]),
+    "tfr_svd_feed_sort": (C.c_int, [C.POINTER(SvdTables), vp, C.POINTER(FeedSet), i64, vp, vp]),
+    "tfr_svd_feed_step": (C.c_int, [C.POINTER(SvdTables), vp, C.POINTER(FeedSet), i64, i32, i32, i32, vp, vp,
+                                    C.POINTER(FeedSet), vp]),
     "tfr_event_synchronize": (C.c_int, [vp]),
+    "tfr_host_wait_flag": (C.c_int, [vp, C.c_uint32, i64]),
     "tfr_binary_metrics_workspace_bytes": (i64, [i64]),
     "tfr_binary_metrics": (C.c_int, [vp, vp, i64, vp, i64, vp, vp]),
     "tfr_ktm_workspace_bytes": (i64, [i64]),

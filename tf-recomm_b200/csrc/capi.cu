@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <map>
 #include <mutex>
 
@@ -434,38 +435,141 @@ extern "C" int tfr_host_pack_feed(const void* users_host, int32_t users_dtype, i
                                     rates_host, rates_dtype, rates_stride, n, staging_host, 0, 0);
 }
 
-// ---- the feed path in two calls -------------------------------------------------------------------------------------------
+// ---- the feed path (include/tfrecomm.h: "the feed_dict step") -----------------------------------------------------------
+extern "C" int tfr_svd_feed_stage(const tfr_svd_tables* t, tfr_feed_set* set, const void* users_host, int32_t users_dtype,
+                                  int64_t users_stride, const void* items_host, int32_t items_dtype, int64_t items_stride,
+                                  const void* rates_host, int32_t rates_dtype, int64_t rates_stride, int64_t B) {
+  TFR_CHECK_ARG(t && set && B > 0 && t->dim > 0 && set->h_feed && set->ev_h2d);
+  set->sorted = 0;
+  set->staged = 0;
+  if (set->used) TFR_CUDA(cudaEventSynchronize((cudaEvent_t)set->ev_h2d));  // the previous copy out of h_feed is done
+  const int rc = tfr_host_pack_feed_checked(users_host, users_dtype, users_stride, items_host, items_dtype, items_stride,
+                                            rates_host, rates_dtype, rates_stride, B, set->h_feed, t->user_num, t->item_num);
+  if (rc) return rc;
+  set->used = 1;
+  set->staged = 1;
+  return TFR_OK;
+}
+
+// The two ends of the feed graph as kernels over zero-copy (pinned, device-mapped) host memory -- what the batch assembly is
+// to the device-resident stream path; a graph of kernel nodes only (with memcpy nodes in the side branch nothing of that
+// branch ran before the table pass had drained: profiles/r02_feed_path.md).
+// fetch: [users | items | rates] of the staged batch, 3 * B 32-bit words; four independent 128-bit loads per thread keep
+// enough PCIe reads in flight from the one CTA per SM that fits beside the table pass.
+constexpr int FETCH_UNROLL = 4;
+__global__ void __launch_bounds__(256) feed_fetch_kernel(const uint32_t* __restrict__ h_src, uint32_t* __restrict__ d_dst,
+                                                         int64_t words) {
+  const int64_t n16 = words / 4;
+  const bool vec = (((uintptr_t)h_src | (uintptr_t)d_dst) & 15) == 0;
+  if (vec) {
+    const int64_t base = (int64_t)blockIdx.x * blockDim.x * FETCH_UNROLL + threadIdx.x;
+    uint4 v[FETCH_UNROLL];
+#pragma unroll
+    for (int k = 0; k < FETCH_UNROLL; ++k) {
+      const int64_t i = base + (int64_t)k * blockDim.x;
+      if (i < n16) v[k] = reinterpret_cast<const uint4*>(h_src)[i];
+    }
+#pragma unroll
+    for (int k = 0; k < FETCH_UNROLL; ++k) {
+      const int64_t i = base + (int64_t)k * blockDim.x;
+      if (i < n16) reinterpret_cast<uint4*>(d_dst)[i] = v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (words & 3)) d_dst[n16 * 4 + threadIdx.x] = h_src[n16 * 4 + threadIdx.x];
+  } else {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < words; k += (int64_t)gridDim.x * blockDim.x)
+      d_dst[k] = h_src[k];
+  }
+}
+
+// Delivery of the predictions into the pinned (device-mapped) result buffer by a kernel; the last CTA then publishes the
+// set's delivery count in *h_flag (system-scope fences: data before flag), which tfr_host_wait_flag polls -- no event, no
+// API call on the host's critical path.
+__global__ void __launch_bounds__(256) feed_deliver_kernel(const float* __restrict__ d_src, float* __restrict__ h_dst,
+                                                           int64_t n, uint32_t* __restrict__ d_sync,
+                                                           volatile uint32_t* __restrict__ h_flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n4 = n / 4;
+  const bool vec = (((uintptr_t)d_src | (uintptr_t)h_dst) & 15) == 0;
+  if (vec) {
+    if (i < n4) reinterpret_cast<float4*>(h_dst)[i] = reinterpret_cast<const float4*>(d_src)[i];
+    const int64_t t = n4 * 4 + (i - n4);
+    if (i >= n4 && t < n) h_dst[t] = d_src[t];
+  } else {
+    for (int64_t k = i; k < n; k += (int64_t)gridDim.x * blockDim.x) h_dst[k] = d_src[k];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int arrived = atomicAdd(&d_sync[0], 1u);
+    if (arrived == gridDim.x - 1) {   // every CTA's stores are fenced and counted
+      d_sync[0] = 0u;
+      const unsigned int seq = d_sync[1] + 1u;
+      d_sync[1] = seq;
+      __threadfence_system();
+      *h_flag = seq;
+    }
+  }
+}
+
+// H2D copy of a staged set + the sort of its ids, on `side` (eager, or inside a capture: the copy's event is then recorded
+// as an external node, for the host thread that repacks h_feed)
+static int feed_copy_sort(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set, int64_t B, cudaStream_t side,
+                          bool capturing, cudaEvent_t before_sort, bool do_copy = true, bool do_sort = true) {
+  tfr_svd_step_ws ws;
+  int rc = tfr_svd_step_carve(set->workspace, set->workspace_bytes, B, t->dim, &ws);
+  if (rc) return rc;
+  if (!do_copy) {
+  } else if (capturing) {
+    const int64_t words = 3 * B;
+    TFR_PREP(feed_fetch_kernel);
+    feed_fetch_kernel<<<(unsigned)((words / 4 + 256 * FETCH_UNROLL - 1) / (256 * FETCH_UNROLL) + 1), 256, 0, side>>>(
+        static_cast<const uint32_t*>(set->h_feed), static_cast<uint32_t*>(set->d_feed), words);
+    TFR_LAUNCH_CHECK();
+    TFR_CUDA(cudaEventRecordWithFlags((cudaEvent_t)set->ev_h2d, side, cudaEventRecordExternal));
+  } else {
+    TFR_CUDA(cudaMemcpyAsync(set->d_feed, set->h_feed, 12 * (size_t)B, cudaMemcpyHostToDevice, side));
+    TFR_CUDA(cudaEventRecord((cudaEvent_t)set->ev_h2d, side));
+  }
+  if (!do_sort) return TFR_OK;
+  if (before_sort) TFR_CUDA(cudaStreamWaitEvent(side, before_sort, 0));
+  const int32_t* ids = static_cast<const int32_t*>(set->d_feed);
+  // inside the graph: the sort in its barrier-free form (one launch per phase): it runs in whatever room the table pass
+  // leaves, and a CTA that has to wait for room holds up nobody
+  return dedup_sort_pairs_impl(ids, (int64_t)t->user_num + 1, ws.su_ids, ws.su_pos, ids + B, (int64_t)t->item_num + 1,
+                               ws.si_ids, ws.si_pos, B, ws.sort_ws, ws.sort_ws_bytes, opt, side, capturing);
+}
+
+extern "C" int tfr_svd_feed_sort(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set, int64_t B,
+                                 void* side_stream, void* after_event) {
+  TFR_CHECK_ARG(t && opt && set && B > 0 && t->dim > 0 && side_stream && set->used && set->staged && !set->sorted);
+  TFR_CHECK_ARG(set->h_feed && set->d_feed && set->workspace && set->ev_h2d && set->ev_sorted && set->ev_done);
+  cudaStream_t side = (cudaStream_t)side_stream;
+  // the step that last used this set's device buffers has finished (device-side wait; a no-op before the first record)
+  TFR_CUDA(cudaStreamWaitEvent(side, (cudaEvent_t)set->ev_done, 0));
+  const int rc = feed_copy_sort(t, opt, set, B, side, false, (cudaEvent_t)after_event);
+  if (rc) return rc;
+  TFR_CUDA(cudaEventRecord((cudaEvent_t)set->ev_sorted, side));
+  set->staged = 0;
+  set->sorted = 1;
+  return TFR_OK;
+}
+
 extern "C" int tfr_svd_feed_prefetch(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set, const void* users_host,
                                      int32_t users_dtype, int64_t users_stride, const void* items_host, int32_t items_dtype,
                                      int64_t items_stride, const void* rates_host, int32_t rates_dtype, int64_t rates_stride,
                                      int64_t B, void* side_stream) {
-  TFR_CHECK_ARG(t && opt && set && B > 0 && t->dim > 0 && side_stream);
-  TFR_CHECK_ARG(set->h_feed && set->d_feed && set->workspace && set->ev_h2d && set->ev_sorted && set->ev_done);
-  tfr_svd_step_ws ws;
-  int rc = tfr_svd_step_carve(set->workspace, set->workspace_bytes, B, t->dim, &ws);
-  if (rc) return rc;
-  cudaStream_t side = (cudaStream_t)side_stream;
-  if (set->used) TFR_CUDA(cudaEventSynchronize((cudaEvent_t)set->ev_h2d));  // the previous copy out of h_feed is done
-  if ((rc = tfr_host_pack_feed_checked(users_host, users_dtype, users_stride, items_host, items_dtype, items_stride,
-                                       rates_host, rates_dtype, rates_stride, B, set->h_feed, t->user_num, t->item_num)))
-    return rc;
-  // the step that last used this set's device buffers has finished (device-side wait, the host does not block)
-  if (set->used) TFR_CUDA(cudaStreamWaitEvent(side, (cudaEvent_t)set->ev_done, 0));
-  TFR_CUDA(cudaMemcpyAsync(set->d_feed, set->h_feed, 12 * (size_t)B, cudaMemcpyHostToDevice, side));
-  TFR_CUDA(cudaEventRecord((cudaEvent_t)set->ev_h2d, side));
-  const int32_t* ids = static_cast<const int32_t*>(set->d_feed);
-  if ((rc = tfr_dedup_sort_pairs_tl(ids, (int64_t)t->user_num + 1, ws.su_ids, ws.su_pos, ids + B, (int64_t)t->item_num + 1,
-                                    ws.si_ids, ws.si_pos, B, ws.sort_ws, ws.sort_ws_bytes, opt, side)))
-    return rc;
-  TFR_CUDA(cudaEventRecord((cudaEvent_t)set->ev_sorted, side));
-  set->used = 1;
-  return TFR_OK;
+  TFR_CHECK_ARG(opt);
+  int rc = tfr_svd_feed_stage(t, set, users_host, users_dtype, users_stride, items_host, items_dtype, items_stride, rates_host,
+                              rates_dtype, rates_stride, B);
+  return rc ? rc : tfr_svd_feed_sort(t, opt, set, B, side_stream, nullptr);
 }
 
 extern "C" int tfr_svd_feed_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set, int64_t B, int32_t flags,
-                                 int32_t var_mask, int32_t fetch, void* stream, void* copy_stream) {
-  TFR_CHECK_ARG(t && opt && set && B > 0 && set->used && set->d_feed && set->d_out && fetch >= 0 && fetch <= 2);
-  TFR_CHECK_ARG(fetch == 0 || (copy_stream && set->h_out && set->ev_pred && set->ev_d2h));
+                                 int32_t var_mask, int32_t fetch, void* stream, void* copy_stream, tfr_feed_set* next_set,
+                                 void* side_stream) {
+  TFR_CHECK_ARG(t && opt && set && B > 0 && set->used && set->sorted && set->d_feed && set->d_out && set->ev_pred);
+  TFR_CHECK_ARG(fetch >= 0 && fetch <= 2 && (fetch == 0 || (copy_stream && set->h_out && set->ev_d2h)));
+  TFR_CHECK_ARG(!next_set || (next_set != set && side_stream));
   cudaStream_t s0 = (cudaStream_t)stream, sc = (cudaStream_t)copy_stream;
   TFR_CUDA(cudaStreamWaitEvent(s0, (cudaEvent_t)set->ev_sorted, 0));
   if (set->copied) TFR_CUDA(cudaStreamWaitEvent(s0, (cudaEvent_t)set->ev_d2h, 0));  // d_out is about to be overwritten
@@ -474,9 +578,13 @@ extern "C" int tfr_svd_feed_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, 
   int rc = run_step(t, opt, ids, ids + B, rates, B, set->d_out, set->d_out + B, flags, var_mask, set->workspace,
                     set->workspace_bytes, stream, nullptr, 0, nullptr, true, 1);
   if (rc) return rc;
+  // end of forward + segment sums: the table pass starts here
+  TFR_CUDA(cudaEventRecord((cudaEvent_t)set->ev_pred, s0));
+  if (next_set && next_set->staged && !next_set->sorted &&
+      (rc = tfr_svd_feed_sort(t, opt, next_set, B, side_stream, set->ev_pred)))
+    return rc;
   if (fetch) {
     // the predictions come from the PRE-update tables (A.7): they go back while the table pass runs
-    TFR_CUDA(cudaEventRecord((cudaEvent_t)set->ev_pred, s0));
     TFR_CUDA(cudaStreamWaitEvent(sc, (cudaEvent_t)set->ev_pred, 0));
     const size_t off = fetch == 1 ? (size_t)B : 0, cnt = fetch == 1 ? (size_t)B : 2 * (size_t)B;
     TFR_CUDA(cudaMemcpyAsync(set->h_out + off, set->d_out + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, sc));
@@ -487,6 +595,142 @@ extern "C" int tfr_svd_feed_step(const tfr_svd_tables* t, tfr_opt_scalars* opt, 
                      set->workspace_bytes, stream, nullptr, 0, nullptr, true, 2)))
     return rc;
   TFR_CUDA(cudaEventRecord((cudaEvent_t)set->ev_done, s0));
+  return TFR_OK;
+}
+
+// The same step as ONE graph: [H2D + id sort of the staged next batch] beside [forward + segment sums -> {copy of the
+// predictions, table pass}].  Eager launches on several streams do not run beside the table pass on this platform -- the
+// side stream's sort and even the copy engine's D2H only start when the pass has drained (tools/timeline.py eager vs graph,
+// profiles/r02_feed_path.md) -- the branches of a graph do.
+namespace {
+struct CaptureEvents {
+  cudaEvent_t e[2] = {nullptr, nullptr};
+  ~CaptureEvents() {
+    for (cudaEvent_t x : e)
+      if (x) cudaEventDestroy(x);
+  }
+};
+
+int deliver(tfr_feed_set* set, int64_t B, int32_t fetch, cudaStream_t st) {
+  const int64_t off = fetch == 1 ? B : 0, cnt = fetch == 1 ? B : 2 * B;
+  TFR_PREP(feed_deliver_kernel);
+  feed_deliver_kernel<<<(unsigned)((cnt / 4 + 255) / 256 + 1), 256, 0, st>>>(set->d_out + off, set->h_out + off, cnt,
+                                                                           set->d_sync, set->h_flag);
+  TFR_LAUNCH_CHECK();
+  return TFR_OK;
+}
+
+int feed_graph_body(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set, tfr_feed_set* next_set, int64_t B,
+                    int32_t flags, int32_t var_mask, int32_t fetch, bool early_side, cudaStream_t c0, cudaStream_t cs,
+                    CaptureEvents& ev) {
+  cudaEvent_t e_fwd = ev.e[0], e_sorted = ev.e[1];
+  const int32_t* ids = static_cast<const int32_t*>(set->d_feed);
+  const float* rates = reinterpret_cast<const float*>(ids + 2 * B);
+  int rc;
+  // ONE branch of kernels beside the table pass: delivery of the predictions -> fetch of the staged next batch -> its id
+  // sort in the barrier-free form.  (Measured, profiles/r02_feed_path.md: the one-launch sort with its grid barrier,
+  // released next to the pass, sometimes only got part of its grid resident until the pass drained -- 45 -> 250 us instead
+  // of 57 -> 125.)
+  // Small tables (early_side): the pass is a few microseconds, the sort is the longest thing in the step -- the fetch + sort
+  // branch forks at the very start, beside the forward, and the delivery sits on the step stream in front of the pass.
+  const bool side = next_set || (fetch && !early_side);
+  if (early_side && next_set) {
+    TFR_CUDA(cudaEventRecord(e_fwd, c0));
+    TFR_CUDA(cudaStreamWaitEvent(cs, e_fwd, 0));
+    if ((rc = feed_copy_sort(t, opt, next_set, B, cs, true, nullptr))) return rc;
+  }
+  if ((rc = run_step(t, opt, ids, ids + B, rates, B, set->d_out, set->d_out + B, flags, var_mask, set->workspace,
+                     set->workspace_bytes, c0, nullptr, 0, nullptr, true, 1)))
+    return rc;
+  if (early_side) {
+    if (fetch && (rc = deliver(set, B, fetch, c0))) return rc;
+  } else {
+    TFR_CUDA(cudaEventRecord(e_fwd, c0));
+    if (side) TFR_CUDA(cudaStreamWaitEvent(cs, e_fwd, 0));
+    if (fetch && (rc = deliver(set, B, fetch, cs))) return rc;
+    if (next_set && (rc = feed_copy_sort(t, opt, next_set, B, cs, true, nullptr))) return rc;
+  }
+  if (side) TFR_CUDA(cudaEventRecord(e_sorted, cs));
+  if ((rc = run_step(t, opt, ids, ids + B, rates, B, set->d_out, set->d_out + B, flags, var_mask, set->workspace,
+                     set->workspace_bytes, c0, nullptr, 0, nullptr, true, 2)))
+    return rc;
+  if (side) TFR_CUDA(cudaStreamWaitEvent(c0, e_sorted, 0));
+  return TFR_OK;
+}
+}  // namespace
+
+extern "C" int tfr_svd_feed_graph_create(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set,
+                                         tfr_feed_set* next_set, int64_t B, int32_t flags, int32_t var_mask, int32_t fetch,
+                                         int32_t early_side, void* capture_stream, void* capture_side_stream,
+                                         void** graph_exec_out) {
+  TFR_CHECK_ARG(t && opt && set && B > 0 && t->dim > 0 && graph_exec_out && capture_stream);
+  TFR_CHECK_ARG(set->d_feed && set->d_out && set->workspace && fetch >= 0 && fetch <= 2);
+  TFR_CHECK_ARG((fetch == 0 && !next_set) || capture_side_stream);
+  TFR_CHECK_ARG(fetch == 0 || (set->h_out && set->d_sync && set->h_flag));
+  TFR_CHECK_ARG(!next_set || (next_set != set && next_set->h_feed && next_set->d_feed &&
+                              next_set->workspace && next_set->ev_h2d));
+  CaptureEvents ev;
+  for (cudaEvent_t& x : ev.e) TFR_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+  cudaStream_t c0 = (cudaStream_t)capture_stream;
+  // relaxed: the feed worker thread may be inside cudaEventSynchronize while this thread captures
+  TFR_CUDA(cudaStreamBeginCapture(c0, cudaStreamCaptureModeRelaxed));
+  const int rc = feed_graph_body(t, opt, set, next_set, B, flags, var_mask, fetch, early_side != 0, c0,
+                                 (cudaStream_t)capture_side_stream, ev);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e_end = cudaStreamEndCapture(c0, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return rc;
+  }
+  if (e_end != cudaSuccess) {
+    set_error("cudaStreamEndCapture -> %s", cudaGetErrorString(e_end));
+    cudaGetLastError();
+    return TFR_ERR_CUDA;
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t e_inst = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e_inst != cudaSuccess) {
+    set_error("cudaGraphInstantiate -> %s", cudaGetErrorString(e_inst));
+    cudaGetLastError();
+    return TFR_ERR_CUDA;
+  }
+  *graph_exec_out = (void*)exec;
+  return TFR_OK;
+}
+
+extern "C" int tfr_svd_feed_graph_launch(void* graph_exec, tfr_feed_set* set, tfr_feed_set* next_set, int32_t fetch,
+                                         void* stream) {
+  TFR_CHECK_ARG(graph_exec && set && set->used && set->sorted && set->ev_sorted && set->ev_done);
+  TFR_CHECK_ARG(!next_set || (next_set != set && next_set->staged && !next_set->sorted));
+  cudaStream_t s0 = (cudaStream_t)stream;
+  // a sort of this set queued eagerly (the first steps); one inside the previous graph is ordered by the stream itself
+  TFR_CUDA(cudaStreamWaitEvent(s0, (cudaEvent_t)set->ev_sorted, 0));
+  TFR_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, s0));
+  TFR_CUDA(cudaEventRecord((cudaEvent_t)set->ev_done, s0));
+  if (fetch) set->deliver_seq += 1;   // what *h_flag reads once this launch's predictions are on the host
+  if (next_set) {
+    next_set->staged = 0;
+    next_set->sorted = 1;
+  }
+  return TFR_OK;
+}
+
+extern "C" int tfr_host_wait_flag(const void* flag_host, uint32_t at_least, int64_t timeout_us) {
+  TFR_CHECK_ARG(flag_host && timeout_us > 0);
+  const volatile uint32_t* f = static_cast<const volatile uint32_t*>(flag_host);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint64_t spins = 1; (int32_t)(*f - at_least) < 0; ++spins) {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+    if ((spins & 4095) == 0 &&
+        std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() > timeout_us) {
+      set_error("tfr_host_wait_flag: %u not reached after %lld us (flag = %u)", at_least, (long long)timeout_us, *f);
+      return TFR_ERR_CUDA;
+    }
+  }
   return TFR_OK;
 }
 

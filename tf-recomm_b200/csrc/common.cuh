@@ -39,6 +39,10 @@ void prep_kernel(const void* fn);
 // that is enough, else the smallest percentage that is (a preferred carve-out is a ceiling for occupancy: the driver
 // only guarantees that ONE CTA fits)
 void prep_kernel_carveout(const void* fn, size_t smem_per_sm);
+// tfr_dedup_sort_pairs_tl with the launch form chosen by the caller: split = one launch per phase, no grid barrier
+int dedup_sort_pairs_impl(const int32_t* ids_a, int64_t max_id_a, int32_t* sorted_ids_a, int32_t* sorted_pos_a,
+                          const int32_t* ids_b, int64_t max_id_b, int32_t* sorted_ids_b, int32_t* sorted_pos_b, int64_t n,
+                          void* workspace, int64_t workspace_bytes, const tfr_opt_scalars* opt, void* stream, bool split);
 #define TFR_PREP(kernel) tfr::prep_kernel(reinterpret_cast<const void*>(kernel))
 
 #define TFR_CHECK_ARG(cond)                                                        \

@@ -46,10 +46,17 @@ struct SortProblem {
   int64_t n;
 };
 
-__global__ void __launch_bounds__(SORT_THREADS) dedup_sort_kernel(SortProblem pa, SortProblem pb, int bpp, int n_passes,
+// SPLIT = false: the whole sort in ONE launch, the phases separated by grid barriers (every CTA must be resident).
+// SPLIT = true: ONE phase per launch -- (only_pass, only_part 0) the histograms of a pass, (only_pass, 1) its scan +
+// scatter; the kernel boundaries are the barriers, and no CTA ever waits for another: the form that runs beside a kernel
+// that fills the machine without the all-resident requirement (the host-fed step's graph, capi.cu).  Same code, same result.
+// (8 CTAs per SM = 32 registers per thread: a CTA's 8K registers are exactly what two CTAs of the table pass leave)
+template <bool SPLIT>
+__global__ void __launch_bounds__(SORT_THREADS, 8) dedup_sort_kernel(SortProblem pa, SortProblem pb, int bpp, int n_passes,
                                                                   int digit_bits, uint32_t* __restrict__ hist_g,
                                                                   const tfr_opt_scalars* __restrict__ opt,
-                                                                  unsigned int* __restrict__ barrier) {
+                                                                  unsigned int* __restrict__ barrier, int only_pass,
+                                                                  int only_part) {
   TlScope tl_scope(opt, TFR_TL_SORT);
   unsigned int epoch = 0;
   __shared__ uint32_t s_wc[SORT_WARPS][RADIX];
@@ -74,6 +81,7 @@ __global__ void __launch_bounds__(SORT_THREADS) dedup_sort_kernel(SortProblem pa
   for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_wc[0][0])[i] = 0;
 
   for (int pass = 0; pass < n_passes; ++pass) {
+    if (SPLIT && pass != only_pass) continue;
     const int shift = pass * digit_bits;
     // ping-pong so that the LAST pass lands in out_*
     const bool to_out = ((n_passes - 1 - pass) & 1) == 0;
@@ -83,18 +91,25 @@ __global__ void __launch_bounds__(SORT_THREADS) dedup_sort_kernel(SortProblem pa
     int32_t* dst_pos = to_out ? p.out_pos : p.tmp_pos;
 
     // (a) histogram of my chunk
-    for (int dg = tid; dg < RADIX; dg += SORT_THREADS) s_base[dg] = 0;
-    __syncthreads();
-    for (int64_t i0 = begin; i0 < end; i0 += SORT_THREADS) {
-      const int64_t i = i0 + tid;
-      const bool valid = i < end;
-      const uint32_t digit = valid ? (((uint32_t)src_ids[i] >> shift) & dmask) : invalid_digit;
-      const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-      if (valid && (peers & lt_mask) == 0) atomicAdd(&s_base[digit], __popc(peers));
+    if (!SPLIT || only_part == 0) {
+      for (int dg = tid; dg < RADIX; dg += SORT_THREADS) s_base[dg] = 0;
+      __syncthreads();
+      for (int64_t i0 = begin; i0 < end; i0 += SORT_THREADS) {
+        const int64_t i = i0 + tid;
+        const bool valid = i < end;
+        const uint32_t digit = valid ? (((uint32_t)src_ids[i] >> shift) & dmask) : invalid_digit;
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        if (valid && (peers & lt_mask) == 0) atomicAdd(&s_base[digit], __popc(peers));
+      }
+      __syncthreads();
+      for (int dg = tid; dg < RADIX; dg += SORT_THREADS) my_hist[dg] = s_base[dg];
     }
-    __syncthreads();
-    for (int dg = tid; dg < RADIX; dg += SORT_THREADS) my_hist[dg] = s_base[dg];
-    grid_barrier(barrier, ++epoch * gridDim.x);
+    if (SPLIT) {
+      if (only_part == 0) return;
+      __syncthreads();   // (s_wc is zeroed)
+    } else {
+      grid_barrier(barrier, ++epoch * gridDim.x);
+    }
 
     // (c) my scatter bases: exclusive scan over digits of the problem-wide totals + lower CTAs' counts.
     // Thread tid owns the DPT consecutive digits tid*DPT .. tid*DPT+DPT-1.
@@ -160,7 +175,7 @@ __global__ void __launch_bounds__(SORT_THREADS) dedup_sort_kernel(SortProblem pa
       __syncwarp();
       if (leader) s_wc[warp][digit] = 0;
     }
-    grid_barrier(barrier, ++epoch * gridDim.x);
+    if (!SPLIT) grid_barrier(barrier, ++epoch * gridDim.x);
   }
 }
 
@@ -226,13 +241,16 @@ using namespace tfr;
 // barrier needs EVERY CTA of the grid to become resident: the grid is sized against this, so a device with fewer SMs
 // (or a build that uses more shared memory) shrinks the grid instead of hanging.  CTAs that have to wait for a
 // neighbour kernel (the table pass) to leave room are fine: nothing that runs beside the sort waits on it.
+__global__ void __launch_bounds__(64) sort_header_zero_kernel(uint32_t* header) { header[threadIdx.x] = 0u; }
+
 static int sort_resident_capacity() {
   static int cached[64] = {0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
   if (cached[dev] > 0) return cached[dev];
   int per_sm = 0, sms = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dedup_sort_kernel, SORT_THREADS, 0) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dedup_sort_kernel<false>, SORT_THREADS, 0) != cudaSuccess)
+    return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
   // one CTA per SM at most: beside a persistent neighbour only that much room is certain
   cached[dev] = per_sm > 0 ? sms : 0;
@@ -264,6 +282,14 @@ extern "C" int tfr_dedup_sort_pairs_tl(const int32_t* ids_a, int64_t max_id_a, i
                                        int32_t* sorted_pos_a, const int32_t* ids_b, int64_t max_id_b,
                                        int32_t* sorted_ids_b, int32_t* sorted_pos_b, int64_t n, void* workspace,
                                        int64_t workspace_bytes, const tfr_opt_scalars* opt, void* stream) {
+  return dedup_sort_pairs_impl(ids_a, max_id_a, sorted_ids_a, sorted_pos_a, ids_b, max_id_b, sorted_ids_b, sorted_pos_b, n,
+                               workspace, workspace_bytes, opt, stream, false);
+}
+
+int tfr::dedup_sort_pairs_impl(const int32_t* ids_a, int64_t max_id_a, int32_t* sorted_ids_a, int32_t* sorted_pos_a,
+                               const int32_t* ids_b, int64_t max_id_b, int32_t* sorted_ids_b, int32_t* sorted_pos_b,
+                               int64_t n, void* workspace, int64_t workspace_bytes, const tfr_opt_scalars* opt,
+                               void* stream, bool split) {
   TFR_CHECK_ARG(n >= 0 && n < ((int64_t)1 << 31));
   if (n == 0) return TFR_OK;
   TFR_CHECK_ARG(ids_a && sorted_ids_a && sorted_pos_a && workspace && max_id_a > 0);
@@ -292,10 +318,23 @@ extern "C" int tfr_dedup_sort_pairs_tl(const int32_t* ids_a, int64_t max_id_a, i
   }
   int bpp = sort_bpp(n, capacity);
   // the whole 256-byte header: the grid barrier and the fix-up work-list counters the segment sums keep at +64
-  TFR_CUDA(cudaMemsetAsync(barrier, 0, 256, (cudaStream_t)stream));
-  TFR_PREP(dedup_sort_kernel);
-  dedup_sort_kernel<<<2 * bpp, SORT_THREADS, 0, (cudaStream_t)stream>>>(pa, pb, bpp, n_passes, digit_bits, hist, opt,
-                                                                        barrier);
+  // (a 64-thread kernel of ours with the step kernels' carve-out: a plain kernel node in the captured graphs)
+  TFR_PREP(sort_header_zero_kernel);
+  sort_header_zero_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint32_t*>(barrier));
+  TFR_LAUNCH_CHECK();
+  if (split) {
+    TFR_PREP(dedup_sort_kernel<true>);
+    for (int pass = 0; pass < n_passes; ++pass)
+      for (int part = 0; part < 2; ++part) {
+        dedup_sort_kernel<true><<<2 * bpp, SORT_THREADS, 0, (cudaStream_t)stream>>>(pa, pb, bpp, n_passes, digit_bits, hist,
+                                                                                    opt, barrier, pass, part);
+        TFR_LAUNCH_CHECK();
+      }
+    return TFR_OK;
+  }
+  TFR_PREP(dedup_sort_kernel<false>);
+  dedup_sort_kernel<false><<<2 * bpp, SORT_THREADS, 0, (cudaStream_t)stream>>>(pa, pb, bpp, n_passes, digit_bits, hist, opt,
+                                                                               barrier, -1, -1);
   TFR_LAUNCH_CHECK();
   return TFR_OK;
 }

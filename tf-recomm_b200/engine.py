@@ -5,7 +5,10 @@ Adam slots, global_step -- svd_train_val.py:47-56) as CUDA tensors, and drives l
 ctypes.  torch is plumbing here (device memory, streams, pinned staging); all arithmetic of the path is in
 the hand-written kernels.  No CPU fallback: constructing an engine without CUDA raises.
 """
+import contextlib
 import ctypes as C
+import os
+import time
 
 import numpy as np
 import torch
@@ -33,6 +36,7 @@ class SvdEngine:
         _require_cuda()
         self.L = _lib.load()
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.U, self.I, self.d = int(user_num), int(item_num), int(dim)
         self.flags, self.var_mask = int(flags), int(var_mask)
         self.sgd = bool(flags & OPT_SGD)
@@ -103,6 +107,12 @@ class SvdEngine:
         self._graphs = {}
         self._host_state = {}
         self._copy_stream = torch.cuda.Stream(device=self.device)
+        # prefetch_host runs on a worker thread (TFR_FEED_WORKER=0: in line, on the caller's thread)
+        self.feed_worker = os.environ.get("TFR_FEED_WORKER", "1") != "0"
+        self._feed_pool = None
+        self.feed_graphs = os.environ.get("TFR_FEED_GRAPHS", "1") != "0"   # 0: the host-fed step as eager launches
+        self._feed_cap = None
+        self.host_prof = None       # dict: train_step_host accumulates its host-side phases (seconds) into it
         self.data = None
         self.se_ring = None
         self.overlap = True
@@ -116,6 +126,13 @@ class SvdEngine:
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _on_device(self):
+        """torch.cuda.device(self.device), or nothing at all when that already is the current device (the context
+        manager costs several microseconds per entry: too much for the per-step path of a 30 us step)."""
+        if torch.cuda.current_device() == self._dev_index:
+            return contextlib.nullcontext()
+        return torch.cuda.device(self.device)
 
     def _fill_struct(self):
         s = SvdTables()
@@ -229,10 +246,9 @@ class SvdEngine:
         """binary_metrics of the step train_step_host issued LAST, from its device-resident logits and ratings (the
         staging set it used): the DISCRETE branch's per-step train metrics without a second pass over host arrays."""
         hs = self._host_state.get(B)
-        if hs is None:
+        if hs is None or hs["last"] is None:
             raise TfrError("no host-fed step of batch size %d has run" % B)
-        k = (hs["next"] - 1 - len(hs["pending"])) % self.N_FEED_SETS
-        st = self._host_set(B, k)
+        st = self._host_set(B, hs["last"])   # (never restaged before the next step has been issued: pending <= N_FEED_SETS - 1)
         return self.binary_metrics(st["d_out"][:B], st["d_feed"][2 * B:].view(torch.float32))
 
     # ---- all-pairs consumers fused into the GEMM epilogue ------------------------------------------------------------
@@ -333,11 +349,11 @@ class SvdEngine:
     # step's table pass.  train_step_host(batch) then issues forward + segment sums, copies the predictions (they come
     # from the PRE-update tables) back on a copy stream while the Adam pass runs, and returns as soon as the
     # predictions are on the host.  A driver that owns its iterator (svd_train_val.py) hands over batch t+1 BEFORE it
-    # asks for step t (two batches may be pending), so that its host work overlaps step t on the device; a plain
+    # asks for step t (up to three batches may be pending: one stepping, one sorting, one being packed), so that its host work overlaps step t on the device; a plain
     # sess.run(feed_dict) without a prefetch does the same work in line.  Every reuse of a staging set is ordered by
     # its events: the pinned buffer is never repacked while a copy from it is queued (also with fetch=False, which does
     # not synchronise), the device buffers never overwritten while a step still reads them.
-    N_FEED_SETS = 3
+    N_FEED_SETS = 4
 
     def _host_set(self, B, k):
         key = ("host", B, k)
@@ -348,10 +364,13 @@ class SvdEngine:
             st = dict(h_feed=torch.empty(3 * B, dtype=torch.int32).pin_memory(),
                       d_feed=torch.empty(3 * B, dtype=torch.int32, device=self.device),
                       d_out=torch.empty(2 * B, dtype=torch.float32, device=self.device),
-                      h_out=torch.empty(2 * B, dtype=torch.float32).pin_memory(), ws=ws, fs=fs, events=[])
+                      h_out=torch.empty(2 * B, dtype=torch.float32).pin_memory(), ws=ws, fs=fs, events=[],
+                      d_sync=torch.zeros(2, dtype=torch.int32, device=self.device),
+                      h_flag=torch.zeros(16, dtype=torch.int32).pin_memory())
             fs.h_feed, fs.d_feed = st["h_feed"].data_ptr(), st["d_feed"].data_ptr()
             fs.d_out, fs.h_out = st["d_out"].data_ptr(), st["h_out"].data_ptr()
             fs.workspace, fs.workspace_bytes = ws.data_ptr(), ws.numel()
+            fs.d_sync, fs.h_flag = st["d_sync"].data_ptr(), st["h_flag"].data_ptr()
             with torch.cuda.device(self.device):
                 for f in ("ev_h2d", "ev_sorted", "ev_pred", "ev_d2h", "ev_done"):
                     ev = C.c_void_p()
@@ -361,49 +380,139 @@ class SvdEngine:
             self._stage[key] = st
         return st
 
-    def prefetch_host(self, users, items, rates):
-        """Hands over a coming batch early: pack -> H2D -> id sort on the side stream, under whatever the main stream
-        is doing (normally the current step's table pass).  Up to N_FEED_SETS - 1 batches may be pending; they must be
-        stepped in the order they were handed over (train_step_host with these very arrays) -- a different batch
-        drops everything that is pending."""
+    def _stage_task(self, st, cols, B):
+        """tfr_svd_feed_stage (the host-side pack into the pinned buffer; no stream is touched) on the feed worker thread:
+        ctypes releases the GIL for the call, so the packing of a coming batch (the one piece of real host work of a
+        step) overlaps the main thread's launch / wait / copy-out.  check() runs here, on the thread that made the call:
+        the library's error text is thread-local."""
+        (ku, pu, du, su), (ki, pi, di, si), (kr, pr, dr, sr) = cols
+        with torch.cuda.device(self.device):
+            check(self.L.tfr_svd_feed_stage(C.byref(self.tables_struct), C.byref(st["fs"]), pu, du, su, pi, di, si, pr, dr,
+                                            sr, B))
+
+    def prefetch_host(self, users, items, rates, _inline=False):
+        """Hands over a coming batch early: it is packed right away (on ONE worker thread, in order); its H2D copy and id
+        sort are issued by the step before it, beside that step's forward and table pass.  Up to N_FEED_SETS - 1 batches
+        may be pending; they must be stepped in the order they were handed over (train_step_host with these very
+        arrays) -- a different batch drops everything that is pending.  Errors of a handed-over batch (ids out of range)
+        surface when that batch is stepped."""
         B = len(users)
-        hs = self._host_state.setdefault(B, dict(next=0, pending=[]))
+        hs = self._host_state.setdefault(B, dict(next=0, pending=[], last=None))
         if len(hs["pending"]) >= self.N_FEED_SETS - 1:
             raise TfrError("too many batches pending: step one before prefetching another")
         k = hs["next"]
         hs["next"] = (k + 1) % self.N_FEED_SETS
         st = self._host_set(B, k)
-        ku, pu, du, su = self._feed_col(users)
-        ki, pi, di, si = self._feed_col(items)
-        kr, pr, dr, sr = self._feed_col(rates)
+        cols = (self._feed_col(users), self._feed_col(items), self._feed_col(rates))   # (array kept alive, ptr, dtype, stride)
+        fut = None
+        if self.feed_worker and not _inline:
+            if self._feed_pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._feed_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="tfr-feed")
+            fut = self._feed_pool.submit(self._stage_task, st, cols, B)
+        else:
+            self._stage_task(st, cols, B)
+        hs["pending"].append(dict(k=k, arrays=(users, items, rates), fut=fut, cols=cols, sorted=False))
+
+    def _sort_pending(self, B, e, after_event):
+        """Queues the H2D copy + id sort of a staged batch on the side stream (once it IS staged: the worker's errors are
+        raised here)."""
+        if e["sorted"]:
+            return
+        if e["fut"] is not None:
+            e["fut"].result()
+        e["sorted"] = True
         with torch.cuda.device(self.device):
-            check(self.L.tfr_svd_feed_prefetch(C.byref(self.tables_struct), self.opt.data_ptr(), C.byref(st["fs"]), pu, du,
-                                               su, pi, di, si, pr, dr, sr, B, self.side_streams[0].cuda_stream))
-        hs["pending"].append((k, users, items, rates))
+            check(self.L.tfr_svd_feed_sort(C.byref(self.tables_struct), self.opt.data_ptr(), C.byref(self._host_set(B, e["k"])["fs"]),
+                                           B, self.side_streams[0].cuda_stream, after_event))
+
+    def _small_tables(self):
+        """The table pass is a few microseconds (the id sort is then the longest thing in a step)."""
+        if getattr(self, "prefetch_at_start", None) is not None:
+            return bool(self.prefetch_at_start)
+        return 24 * (self.U + self.I) * (self.d + 1) < 64e6
+
+    def _feed_graph(self, B, k, k_next, mode):
+        """The executable graph of one host-fed step on staging set k (+ copy and sort of the batch staged in k_next)."""
+        key = ("feed", B, k, k_next, mode, self.flags, self.var_mask, self._small_tables())
+        g = self._graphs.get(key)
+        if g is None:
+            if self._feed_cap is None:
+                self._feed_cap = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+            exe = C.c_void_p()
+            with torch.cuda.device(self.device):
+                check(self.L.tfr_svd_feed_graph_create(
+                    C.byref(self.tables_struct), self.opt.data_ptr(), C.byref(self._host_set(B, k)["fs"]),
+                    C.byref(self._host_set(B, k_next)["fs"]) if k_next is not None else None, B, self.flags, self.var_mask,
+                    mode, int(self._small_tables()), *(x.cuda_stream for x in self._feed_cap), C.byref(exe)))
+            g = self._graphs[key] = exe.value
+        return g
 
     def train_step_host(self, users, items, rates, fetch=True):
         B = len(users)
-        hs = self._host_state.setdefault(B, dict(next=0, pending=[]))
+        hs = self._host_state.setdefault(B, dict(next=0, pending=[], last=None))
         pend = hs["pending"]
-        if not pend or pend[0][1] is not users or pend[0][2] is not items or pend[0][3] is not rates:
-            pend.clear()   # not the batch that was handed over: drop what is pending
-            self.prefetch_host(users, items, rates)
-        k = pend.pop(0)[0]
-        st = self._host_set(B, k)
+        if not pend or any(x is not y for x, y in zip(pend[0]["arrays"], (users, items, rates))):
+            for e in pend:   # not the batch that was handed over: drop what is pending (after its task has run)
+                if e["fut"] is not None:
+                    e["fut"].exception()
+            pend.clear()
+            self.prefetch_host(users, items, rates, _inline=True)   # nothing to overlap with: no hand-off to the worker
+        head = pend.pop(0)
+        prof = self.host_prof
+        t0 = time.perf_counter() if prof is not None else 0.0
+        self._sort_pending(B, head, None)   # (queued by the previous step already when the batch was handed over early)
+        st = self._host_set(B, head["k"])
+        hs["last"] = head["k"]
         # the README head is the identity (infer == logits): one array goes back instead of two
         identity_head = not (self.flags & LOSS_SIGMOID_CE)
         mode = 0 if not fetch else (1 if identity_head else 2)
-        with torch.cuda.device(self.device):
-            check(self.L.tfr_svd_feed_step(C.byref(self.tables_struct), self.opt.data_ptr(), C.byref(st["fs"]), B,
-                                           self.flags, self.var_mask, mode, self._stream(), self._copy_stream.cuda_stream))
+        # The next batch's copy + id sort belong beside this step's table pass: not beside its forward + segment sums
+        # (which the sort slows), not after the pass (where they are on the critical path).  The step goes down as ONE
+        # graph that has them as a branch (tfr_svd_feed_graph_create says why eager side-stream launches do not do);
+        # a batch whose packing is still under way is copied + sorted eagerly once the predictions have arrived.
+        nxt = pend[0] if pend and not pend[0]["sorted"] else None
+        if nxt is not None and nxt["fut"] is not None and not (nxt["fut"].done() and nxt["fut"].exception() is None):
+            nxt = None   # still being packed, or failed: its own step deals with it (and raises its error)
+        if self.feed_graphs and not fetch:
+            # the worker repacks a pinned buffer on the strength of the predictions the host has SEEN (the delivery flag):
+            # a step that fetches nothing leaves the next batch's copy + sort to the eager, event-ordered path
+            nxt = None
+        if nxt is not None:
+            nxt["sorted"] = True
+        fs_next = C.byref(self._host_set(B, nxt["k"])["fs"]) if nxt is not None else None
+        with self._on_device():
+            if self.feed_graphs:
+                g = self._feed_graph(B, head["k"], nxt["k"] if nxt is not None else None, mode)
+                check(self.L.tfr_svd_feed_graph_launch(g, C.byref(st["fs"]), fs_next, mode, self._stream()))
+            else:
+                check(self.L.tfr_svd_feed_step(C.byref(self.tables_struct), self.opt.data_ptr(), C.byref(st["fs"]), B,
+                                               self.flags, self.var_mask, mode, self._stream(),
+                                               self._copy_stream.cuda_stream, fs_next, self.side_streams[0].cuda_stream))
+        t1 = time.perf_counter() if prof is not None else 0.0
         if not fetch:
             return None
-        check(self.L.tfr_event_synchronize(st["fs"].ev_d2h))
+        if self.feed_graphs:   # the delivery kernel's flag in pinned memory
+            check(self.L.tfr_host_wait_flag(st["fs"].h_flag, st["fs"].deliver_seq, 30_000_000))
+        else:
+            check(self.L.tfr_event_synchronize(st["fs"].ev_d2h))
+        t2 = time.perf_counter() if prof is not None else 0.0
+        if pend and not pend[0]["sorted"] and not (pend[0]["fut"] is not None and pend[0]["fut"].done()
+                                                     and pend[0]["fut"].exception() is not None):
+            self._sort_pending(B, pend[0], None)
+        t3 = time.perf_counter() if prof is not None else 0.0
         if identity_head:
             out = st["h_out"][B:].numpy().copy()   # one copy out of the pinned buffer
-            return out, out
-        out = st["h_out"].numpy().copy()
-        return out[:B], out[B:]
+            res = (out, out)
+        else:
+            out = st["h_out"].numpy().copy()
+            res = (out[:B], out[B:])
+        if prof is not None:   # host-side breakdown for tools/e2e_breakdown.py
+            t4 = time.perf_counter()
+            for name, dt in (("issue_step", t1 - t0), ("wait_predictions", t2 - t1), ("issue_next_sort", t3 - t2),
+                             ("copy_out", t4 - t3)):
+                prof[name] = prof.get(name, 0.0) + dt
+        return res
 
     def d2h_bytes(self, B):
         return (4 if not (self.flags & LOSS_SIGMOID_CE) else 8) * B
@@ -425,6 +534,9 @@ class SvdEngine:
 
     def close(self):
         """Releases the captured graphs (device memory goes with the tensors)."""
+        if getattr(self, "_feed_pool", None) is not None:
+            self._feed_pool.shutdown(wait=True)
+            self._feed_pool = None
         if getattr(self, "_graphs", None):
             torch.cuda.synchronize(self.device)
             self._destroy_graphs()
@@ -538,9 +650,7 @@ class SvdEngine:
         # Where to fork the next batch's assemble + sort: UNDER the table pass when that pass is long (it is
         # bandwidth-bound and barely notices them, while the latency-bound gathers of phase 1 would slow down
         # beside them); at the start of the step when the tables are small and the pass is a few microseconds.
-        small = 24 * (self.U + self.I) * (self.d + 1) < 64e6
-        if getattr(self, "prefetch_at_start", None) is not None:
-            small = bool(self.prefetch_at_start)
+        small = self._small_tables()
         if small:
             side.wait_stream(main)
             self._prefetch(B, 1 - slot, False, side.cuda_stream)

@@ -20,22 +20,143 @@ def main():
     w = bench.WORKLOADS[name]
     cols = bench.make_columns(w)
     B = w["B"]
+    if os.environ.get("TFR_FEED_SETS"):
+        SvdEngine.N_FEED_SETS = int(os.environ["TFR_FEED_SETS"])
     eng = SvdEngine(w["U"], w["I"], w["d"], bench.LR, bench.REG, device_init_seed=1)
     rng = np.random.default_rng(3)
     batches = []
     for _ in range(40):
         rows = rng.integers(0, len(cols[0]), B)
         batches.append((cols[0][rows].astype(np.float64), cols[1][rows].astype(np.float64), cols[2][rows].astype(np.float64)))
+    # the device-resident step of this box, for scale (graph replay, next batch assembled + sorted on the side stream)
+    eng.set_train_data(*cols)
+    eng.set_index_stream(rng.integers(0, len(cols[0]), 72 * B), B)
+    eng.run_stream_steps(8, use_graph=True, pipeline=True)
+    eng.set_batch_cursor(0)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    eng.run_stream_steps(64, use_graph=True, pipeline=True)
+    torch.cuda.synchronize()
+    print("%s: device-resident step %.1f us (graph replay)" % (name, (time.perf_counter() - t0) / 64 * 1e6))
     for b in batches[:5]:
         eng.train_step_host(*b)
     torch.cuda.synchronize()
-    t = dict(total=0.0)
+    n = len(batches) - 5
     t0 = time.perf_counter()
     for users, items, rates in batches[5:]:
         eng.train_step_host(users, items, rates)
-    t["total"] = time.perf_counter() - t0
-    n = len(batches) - 5
-    print(name, {k: round(v / n * 1e6, 1) for k, v in t.items()}, "us per train_step_host")
+    torch.cuda.synchronize()
+    plain = (time.perf_counter() - t0) / n * 1e6
+    print("%s feed_worker=%d: %.1f us/step unprefetched" % (name, eng.feed_worker, plain))
+    # the driver's loop: batch t+ahead handed over before step t is asked for
+    for ahead in range(1, eng.N_FEED_SETS - 1):
+        t_pre = t_step = 0.0
+        per = []
+        nb = len(batches)
+        for j in range(5, 5 + ahead):
+            eng.prefetch_host(*batches[j])
+        t0 = time.perf_counter()
+        for j in range(5, nb):
+            a = time.perf_counter()
+            if j + ahead < nb:
+                eng.prefetch_host(*batches[j + ahead])
+            b = time.perf_counter()
+            eng.train_step_host(*batches[j])
+            t_pre += b - a
+            t_step += time.perf_counter() - b
+            per.append((time.perf_counter() - a) * 1e6)
+        torch.cuda.synchronize()
+        tot = (time.perf_counter() - t0) / n * 1e6
+        print("  prefetched %d ahead: %.1f us/step (prefetch_host call %.1f us, train_step_host call %.1f us)"
+              % (ahead, tot, t_pre / n * 1e6, t_step / n * 1e6))
+        print("    per-step wall time: p10 %.0f  p50 %.0f  p90 %.0f  max %.0f us; first five: %s"
+              % (np.percentile(per, 10), np.percentile(per, 50), np.percentile(per, 90), max(per), [int(x) for x in per[:5]]))
+        eng.host_prof = {}
+        for j in range(5, 5 + ahead):
+            eng.prefetch_host(*batches[j])
+        for j in range(5, nb):
+            if j + ahead < nb:
+                eng.prefetch_host(*batches[j + ahead])
+            eng.train_step_host(*batches[j])
+        torch.cuda.synchronize()
+        print("    train_step_host:", {k: round(v / n * 1e6, 1) for k, v in eng.host_prof.items()})
+        eng.host_prof = None
+        # device side: events (made beforehand) on the step stream right before and after each step's launches
+        A = [torch.cuda.Event(enable_timing=True) for _ in range(nb)]
+        Z = [torch.cuda.Event(enable_timing=True) for _ in range(nb)]
+        for j in range(5, 5 + ahead):
+            eng.prefetch_host(*batches[j])
+        for j in range(5, nb):
+            if j + ahead < nb:
+                eng.prefetch_host(*batches[j + ahead])
+            A[j].record()
+            eng.train_step_host(*batches[j])
+            Z[j].record()
+        torch.cuda.synchronize()
+        js = range(10, nb - 3)
+        med = lambda xs: float(np.median(list(xs))) * 1e3
+        print("    step stream (events): step %.1f us, idle before the next step %.1f us"
+              % (med(A[j].elapsed_time(Z[j]) for j in js), med(Z[j].elapsed_time(A[j + 1]) for j in js)))
+    if not eng.feed_worker:
+        device_timeline(eng, batches)
+    kernel_timeline(eng, batches, eng.N_FEED_SETS - 2)
+    eng.close()
+
+
+def kernel_timeline(eng, batches, ahead):
+    """In-kernel %globaltimer stamps of ONE host-fed step in steady state: the stamps are reset on the step stream (no
+    synchronisation) before every step, so what is left after the loop belongs to the last step and to the id sort of
+    the batch handed over after it."""
+    eng.enable_timeline()
+    nb = len(batches)
+    acc = {}
+    for rep in range(7):
+        seq = batches[5:] + batches[5:5 + ahead]   # the tail is handed over (its sort is what we want to see), not stepped
+        for j in range(ahead):
+            eng.prefetch_host(*seq[j])
+        for j in range(nb - 5):
+            if j + ahead < len(seq):
+                eng.prefetch_host(*seq[j + ahead])
+            eng.reset_timeline()
+            eng.train_step_host(*seq[j])
+        torch.cuda.synchronize()
+        for k, (a, b) in eng.read_timeline().items():
+            acc.setdefault(k, []).append((a, b))
+        eng.train_step_host(*batches[0])   # drops what is pending
+        torch.cuda.synchronize()
+    print("  in-kernel timeline of a steady-state host-fed step (us from its first kernel's entry; median of 7):")
+    for k in eng.TL_NAMES:
+        if k in acc:
+            a = np.median([x[0] for x in acc[k]]); b = np.median([x[1] for x in acc[k]])
+            print("    %-12s start %7.1f  end %7.1f  dur %7.1f" % (k, a, b, b - a))
+
+
+def device_timeline(eng, batches):
+    """CUDA events around each step's launches on the main stream and around each prefetch on the side stream (in-line
+    prefetch only: the events are recorded by this thread): is the loop bound by the device or by the host?"""
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    main, side = torch.cuda.current_stream(), eng.side_streams[0]
+    A, Bm, S0, S1 = {}, {}, {}, {}
+    def pre(j):
+        S0[j] = ev(); S0[j].record(side)
+        eng.prefetch_host(*batches[j])
+        S1[j] = ev(); S1[j].record(side)
+    pre(5)
+    for j in range(5, len(batches)):
+        if j + 1 < len(batches):
+            pre(j + 1)
+        A[j] = ev(); A[j].record(main)
+        eng.train_step_host(*batches[j])
+        Bm[j] = ev(); Bm[j].record(main)
+    torch.cuda.synchronize()
+    js = range(8, len(batches) - 2)
+    med = lambda xs: float(np.median(list(xs))) * 1e3
+    print("  main stream: step span %.1f us (first launch -> pass end), idle between steps %.1f us, step period %.1f us"
+          % (med(A[j].elapsed_time(Bm[j]) for j in js), med(Bm[j].elapsed_time(A[j + 1]) for j in js),
+             med(A[j].elapsed_time(A[j + 1]) for j in js)))
+    print("  side stream: H2D + id sort of batch j+1 takes %.1f us, starts %.1f us after step j's first launch, ends %.1f us "
+          "before step j+1's first launch" % (med(S0[j + 1].elapsed_time(S1[j + 1]) for j in js),
+                                              med(A[j].elapsed_time(S0[j + 1]) for j in js),
+                                              med(S1[j + 1].elapsed_time(A[j + 1]) for j in js)))
 
 
 if __name__ == "__main__":
