@@ -282,15 +282,15 @@ def run_workload(name, args, torch, with_e2e=True, with_roofline=True, sample_cl
     if with_e2e:
         rng = np.random.default_rng(3)
         batches = []
-        for _ in range(min(args.steps, 200) + 12):
+        for _ in range(min(args.steps, 200) + 15):
             rows = rng.integers(0, n_train, B)
             batches.append((cols[0][rows].astype(np.float64), cols[1][rows].astype(np.float64),
                             cols[2][rows].astype(np.float64)))   # float64 columns: what ShuffleIterator yields
-        # the driver's loop (svd_train_val.py): batches t+1 and t+2 have been handed over when step t is asked for and
-        # returns its predictions (host) -- t+2 is packed and copied by the feed worker thread while the ids of t+1 are
-        # sorted under step t's table pass.  Every step's H2D (12 B / rating) and D2H (4 or 8 B / rating) are inside
+        # the driver's loop (svd_train_val.py): batches t+1 .. t+3 have been handed over when step t is asked for and
+        # returns its predictions (host) -- the later ones are being packed by the feed worker thread while t+1 is fetched
+        # and its ids sorted under step t's table pass.  Every step's H2D (12 B / rating) and D2H (4 or 8 B / rating) are inside
         # the timed region.
-        AHEAD, WARM = 2, 12
+        AHEAD, WARM = 3, 15
 
         def feed_loop(bs):
             for j in range(min(AHEAD, len(bs))):
@@ -309,7 +309,7 @@ def run_workload(name, args, torch, with_e2e=True, with_roofline=True, sample_cl
         n = len(batches) - WARM
         res["e2e"] = {"value": B * n / dt, "unit": "ratings/s", "h2d_bytes_per_step": eng.h2d_bytes(B),
                       "d2h_bytes_per_step": eng.d2h_bytes(B), "ms_per_step": dt / n * 1e3, "steps": n,
-                      "path": "SvdEngine.train_step_host + prefetch_host two batches ahead (what Session.run([train_op, logits, "
+                      "path": "SvdEngine.train_step_host + prefetch_host three batches ahead (what Session.run([train_op, logits, "
                               "infer], feed_dict) / Session.prefetch call; the loop of svd_train_val.py)"}
     if with_roofline and w["d"] % 4 == 0:
         res["roofline"] = kernel_roofline(eng, w, cols, min(args.steps, 20), torch, peak, peak_src)

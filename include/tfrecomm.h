@@ -411,7 +411,7 @@ int tfr_host_pack_feed(const void* users_host, int32_t users_dtype, int64_t user
 
 /* ---- the feed_dict step (what Session.prefetch / Session.run issue) -----------------------------------------------------
  * One staging set of the feed path; all memory and the five events (cudaEvent_t, tfr_event_create) are the caller's.
- * Three or four sets are used round-robin.  Every reuse is ordered by the set's events (or by the step stream itself): the
+ * Four or five sets are used round-robin.  Every reuse is ordered by the set's events (or by the step stream itself): the
  * pinned buffer is never repacked while a copy out of it is queued, the device buffers never overwritten while a step
  * still reads them. */
 typedef struct {

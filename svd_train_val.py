@@ -83,10 +83,10 @@ def svd(train, test, args, log=print):
 
         def feed_of(b):
             return {user_batch: b[0], item_batch: b[1], rate_batch: b[2], wins_batch: b[3], fails_batch: b[4]}
-        # session mode: this driver owns the iterator, so batches i+1 and i+2 are drawn (same RandomState order as the
+        # session mode: this driver owns the iterator, so batches i+1 .. i+3 are drawn (same RandomState order as the
         # reference's loop: one draw per step, total_steps draws in all) and handed to sess.prefetch BEFORE step i is
-        # asked for -- i+2 is being packed and copied by the feed worker while i+1's ids are sorted under step i's pass
-        AHEAD = 2
+        # asked for -- the later ones are being packed by the feed worker while i+1 is fetched and sorted under step i's pass
+        AHEAD = 3
         drawn = []          # batches handed over, not stepped yet
         n_drawn = 0
 

@@ -349,11 +349,12 @@ class SvdEngine:
     # step's table pass.  train_step_host(batch) then issues forward + segment sums, copies the predictions (they come
     # from the PRE-update tables) back on a copy stream while the Adam pass runs, and returns as soon as the
     # predictions are on the host.  A driver that owns its iterator (svd_train_val.py) hands over batch t+1 BEFORE it
-    # asks for step t (up to three batches may be pending: one stepping, one sorting, one being packed), so that its host work overlaps step t on the device; a plain
+    # asks for step t (up to four batches may be pending: one stepping, one sorting, two packed or being packed -- the
+    # slack that keeps a late pack from ever reaching the step stream: profiles/r02_feed_path.md), so that its host work overlaps step t on the device; a plain
     # sess.run(feed_dict) without a prefetch does the same work in line.  Every reuse of a staging set is ordered by
     # its events: the pinned buffer is never repacked while a copy from it is queued (also with fetch=False, which does
     # not synchronise), the device buffers never overwritten while a step still reads them.
-    N_FEED_SETS = 4
+    N_FEED_SETS = 5
 
     def _host_set(self, B, k):
         key = ("host", B, k)

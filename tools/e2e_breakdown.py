@@ -25,7 +25,7 @@ def main():
     eng = SvdEngine(w["U"], w["I"], w["d"], bench.LR, bench.REG, device_init_seed=1)
     rng = np.random.default_rng(3)
     batches = []
-    for _ in range(40):
+    for _ in range(int(os.environ.get("TFR_NB", "40"))):
         rows = rng.integers(0, len(cols[0]), B)
         batches.append((cols[0][rows].astype(np.float64), cols[1][rows].astype(np.float64), cols[2][rows].astype(np.float64)))
     # the device-resident step of this box, for scale (graph replay, next batch assembled + sorted on the side stream)
@@ -70,6 +70,11 @@ def main():
               % (ahead, tot, t_pre / n * 1e6, t_step / n * 1e6))
         print("    per-step wall time: p10 %.0f  p50 %.0f  p90 %.0f  max %.0f us; first five: %s"
               % (np.percentile(per, 10), np.percentile(per, 50), np.percentile(per, 90), max(per), [int(x) for x in per[:5]]))
+        if len(per) > 60:
+            tail = np.array(per[10:])
+            slow = [(i + 10, int(x)) for i, x in enumerate(tail) if x > 1.25 * np.median(tail)]
+            print("    after the first ten: mean %.1f  p50 %.1f us; %d steps > 1.25 x median: %s"
+                  % (tail.mean(), np.median(tail), len(slow), slow[:24]))
         eng.host_prof = {}
         for j in range(5, 5 + ahead):
             eng.prefetch_host(*batches[j])
