@@ -50,6 +50,8 @@ int main(void) {
   printf("%zu %zu %zu %zu\n", sizeof(tfr_feed_set), offsetof(tfr_feed_set, workspace_bytes), offsetof(tfr_feed_set, ev_done),
          offsetof(tfr_feed_set, copied));
   printf("%zu\n", offsetof(tfr_opt_scalars, prefetch_cursor));
+  printf("%zu %zu %zu %zu\n", offsetof(tfr_feed_set, staged), offsetof(tfr_feed_set, d_sync), offsetof(tfr_feed_set, h_flag),
+         offsetof(tfr_feed_set, deliver_seq));
   return 0;
 }'''
     import tempfile
@@ -65,7 +67,8 @@ int main(void) {
            _lib.OptScalars.se_ring.offset, _lib.OptScalars.timeline.offset, _lib.SvdTables.mu.offset,
            _lib.SvdTables.user_slot.offset, _lib.StepWs.sort_ws.offset, C.sizeof(_lib.FmTables),
            _lib.FmTables.w0.offset, _lib.FmTables.slot.offset, C.sizeof(_lib.FeedSet), _lib.FeedSet.workspace_bytes.offset,
-           _lib.FeedSet.ev_done.offset, _lib.FeedSet.copied.offset, _lib.OptScalars.prefetch_cursor.offset]
+           _lib.FeedSet.ev_done.offset, _lib.FeedSet.copied.offset, _lib.OptScalars.prefetch_cursor.offset,
+           _lib.FeedSet.staged.offset, _lib.FeedSet.d_sync.offset, _lib.FeedSet.h_flag.offset, _lib.FeedSet.deliver_seq.offset]
     assert got == exp
 
 
@@ -274,3 +277,63 @@ def test_tensorboard_event_file_round_trip(tmp_path):
     assert evs[0].file_version == "brain.Event:2"
     seen = [(e.step, v.tag) for e in evs[1:] for v in e.summary.value]
     assert seen == [(s, t) for s, t, _ in vals]
+
+
+def test_host_wait_flag_spins_until_the_count_is_reached_and_times_out():
+    """tfr_host_wait_flag (the host side of the feed graph's delivery flag) is plain host code: it returns once the
+    32-bit counter has reached the target -- wrap-around included -- and reports a timeout instead of hanging."""
+    import threading
+    import time
+    L = _lib.load()
+    flag = (C.c_uint32 * 16)()
+    flag[0] = 7
+    assert L.tfr_host_wait_flag(C.addressof(flag), 7, 1000) == 0        # already there
+    assert L.tfr_host_wait_flag(C.addressof(flag), 5, 1000) == 0        # past it
+    t0 = time.perf_counter()
+    assert L.tfr_host_wait_flag(C.addressof(flag), 8, 20_000) < 0      # never written: times out
+    assert 0.015 < time.perf_counter() - t0 < 2.0
+    assert b"not reached" in L.tfr_last_error()
+
+    def bump():
+        time.sleep(0.01)
+        flag[0] = 8
+    th = threading.Thread(target=bump)
+    th.start()
+    assert L.tfr_host_wait_flag(C.addressof(flag), 8, 5_000_000) == 0   # written by another thread while we spin
+    th.join()
+    flag[0] = 0xFFFFFFFE
+    assert L.tfr_host_wait_flag(C.addressof(flag), 0xFFFFFFFD, 1000) == 0
+    assert L.tfr_host_wait_flag(C.addressof(flag), 2, 5_000) < 0        # 2 is AHEAD of 0xFFFFFFFE (wrapped): not reached
+    flag[0] = 3
+    assert L.tfr_host_wait_flag(C.addressof(flag), 2, 1000) == 0
+
+
+def test_feed_stage_is_host_only():
+    """tfr_svd_feed_stage packs a handed-over batch into the set's staging buffer and touches no stream: on a fresh set
+    it runs without a GPU.  Ids out of range are refused and leave the set unstaged."""
+    L = _lib.load()
+    B, U, I = 1000, 50, 40
+    rng = np.random.default_rng(3)
+    users = rng.integers(0, U, B).astype(np.float64)
+    items = rng.integers(0, I, B).astype(np.int64)
+    rates = rng.integers(1, 6, B).astype(np.float32)
+    t = _lib.SvdTables()
+    t.user_num, t.item_num, t.dim = U, I, 8
+    staging = np.zeros(3 * B, dtype=np.int32)
+    fs = _lib.FeedSet()
+    fs.h_feed = staging.ctypes.data
+    fs.ev_h2d = 1   # (only dereferenced once the set has a history: used != 0)
+
+    def stage(u, i, r):
+        return L.tfr_svd_feed_stage(C.byref(t), C.byref(fs), u.ctypes.data, 0, u.strides[0], i.ctypes.data, 3, i.strides[0],
+                                    r.ctypes.data, 1, r.strides[0], B)
+    assert stage(users, items, rates) == 0
+    assert (fs.used, fs.staged, fs.sorted) == (1, 1, 0)
+    assert np.array_equal(staging[:B], users.astype(np.int32))
+    assert np.array_equal(staging[B:2 * B], items.astype(np.int32))
+    assert np.array_equal(staging[2 * B:].view(np.float32), rates)
+    fs.used = 0
+    bad = users.copy()
+    bad[17] = U
+    assert stage(bad, items, rates) < 0
+    assert (fs.used, fs.staged) == (0, 0)
