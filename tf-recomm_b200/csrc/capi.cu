@@ -47,6 +47,7 @@ const TuneEntry kTune[TUNE_COUNT] = {
     // programmatic dependent launch along tiles -> fix-up -> pass: no gain at the ML-25M shape (178.2 vs 177.5 us per
     // step) and a loss at the ML-1M shape (the early-resident dependents delay the side stream's id sort: 53 vs 37 us)
     {"PDL", 0},
+    {"SORT_SPLIT", 0},
 };
 std::mutex g_tune_mu;
 int g_tune_val[TUNE_COUNT];

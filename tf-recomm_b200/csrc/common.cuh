@@ -28,6 +28,7 @@ enum TuneKey {
   TUNE_AP_STAGES,         // debug: which stages of tfr_allpairs_consume's ranking run (1 sweep | 2 rescore | 4 exact rows)
   TUNE_TL_EVERY_CTA,      // debug timeline: the pass's exit stamp from every CTA instead of a sample
   TUNE_PDL,               // 1: programmatic dependent launch along the step's critical path (see pdl_wait)
+  TUNE_SORT_SPLIT,        // 1: every id sort in its one-launch-per-phase form (default: only inside the feed graph)
   TUNE_COUNT
 };
 int tune(TuneKey k);

@@ -283,7 +283,7 @@ extern "C" int tfr_dedup_sort_pairs_tl(const int32_t* ids_a, int64_t max_id_a, i
                                        int32_t* sorted_ids_b, int32_t* sorted_pos_b, int64_t n, void* workspace,
                                        int64_t workspace_bytes, const tfr_opt_scalars* opt, void* stream) {
   return dedup_sort_pairs_impl(ids_a, max_id_a, sorted_ids_a, sorted_pos_a, ids_b, max_id_b, sorted_ids_b, sorted_pos_b, n,
-                               workspace, workspace_bytes, opt, stream, false);
+                               workspace, workspace_bytes, opt, stream, tune(TUNE_SORT_SPLIT) != 0);
 }
 
 int tfr::dedup_sort_pairs_impl(const int32_t* ids_a, int64_t max_id_a, int32_t* sorted_ids_a, int32_t* sorted_pos_a,
