@@ -432,8 +432,9 @@ typedef struct {
   uint32_t reserved;
 } tfr_feed_set;
 /* tfr_svd_feed_stage: HOST ONLY -- pack (tfr_host_pack_feed_checked: value cast + range check) into h_feed.  Needs nothing of
- * the model, blocks only on ev_h2d of the set's previous use (the pinned buffer must be free to repack), touches no stream:
- * it may run on any host thread (the engine's feed worker).
+ * the model, blocks only on ev_h2d / ev_done of the set's previous use (the pinned buffer must be free to repack: its copy
+ * to the device is over, and so is the step that consumed it), touches no stream: it may run on any host thread (the
+ * engine's feed worker).
  * tfr_svd_feed_sort: H2D copy of the staged batch + the sort of its ids on side_stream, behind after_event when one is
  * given (NULL: as soon as the set's previous step has finished). */
 int tfr_svd_feed_stage(const tfr_svd_tables* t, tfr_feed_set* set, const void* users_host, int32_t users_dtype,

@@ -443,7 +443,13 @@ extern "C" int tfr_svd_feed_stage(const tfr_svd_tables* t, tfr_feed_set* set, co
   TFR_CHECK_ARG(t && set && B > 0 && t->dim > 0 && set->h_feed && set->ev_h2d);
   set->sorted = 0;
   set->staged = 0;
-  if (set->used) TFR_CUDA(cudaEventSynchronize((cudaEvent_t)set->ev_h2d));  // the previous copy out of h_feed is done
+  if (set->used) {
+    // The previous copy out of h_feed is done.  ev_h2d covers the eager path; a copy made by a step graph's fetch kernel is
+    // only known to be over when the step that CONSUMED that batch has finished (ev_done, recorded eagerly behind its
+    // graph: an event-record node inside a launched graph does not hold a host wait back before it has executed).
+    TFR_CUDA(cudaEventSynchronize((cudaEvent_t)set->ev_h2d));
+    if (set->ev_done) TFR_CUDA(cudaEventSynchronize((cudaEvent_t)set->ev_done));
+  }
   const int rc = tfr_host_pack_feed_checked(users_host, users_dtype, users_stride, items_host, items_dtype, items_stride,
                                             rates_host, rates_dtype, rates_stride, B, set->h_feed, t->user_num, t->item_num);
   if (rc) return rc;
@@ -515,12 +521,11 @@ __global__ void __launch_bounds__(256) feed_deliver_kernel(const float* __restri
 // H2D copy of a staged set + the sort of its ids, on `side` (eager, or inside a capture: the copy's event is then recorded
 // as an external node, for the host thread that repacks h_feed)
 static int feed_copy_sort(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_feed_set* set, int64_t B, cudaStream_t side,
-                          bool capturing, cudaEvent_t before_sort, bool do_copy = true, bool do_sort = true) {
+                          bool capturing, cudaEvent_t before_sort) {
   tfr_svd_step_ws ws;
   int rc = tfr_svd_step_carve(set->workspace, set->workspace_bytes, B, t->dim, &ws);
   if (rc) return rc;
-  if (!do_copy) {
-  } else if (capturing) {
+  if (capturing) {
     const int64_t words = 3 * B;
     TFR_PREP(feed_fetch_kernel);
     feed_fetch_kernel<<<(unsigned)((words / 4 + 256 * FETCH_UNROLL - 1) / (256 * FETCH_UNROLL) + 1), 256, 0, side>>>(
@@ -531,7 +536,6 @@ static int feed_copy_sort(const tfr_svd_tables* t, tfr_opt_scalars* opt, tfr_fee
     TFR_CUDA(cudaMemcpyAsync(set->d_feed, set->h_feed, 12 * (size_t)B, cudaMemcpyHostToDevice, side));
     TFR_CUDA(cudaEventRecord((cudaEvent_t)set->ev_h2d, side));
   }
-  if (!do_sort) return TFR_OK;
   if (before_sort) TFR_CUDA(cudaStreamWaitEvent(side, before_sort, 0));
   const int32_t* ids = static_cast<const int32_t*>(set->d_feed);
   // inside the graph: the sort in its barrier-free form (one launch per phase): it runs in whatever room the table pass

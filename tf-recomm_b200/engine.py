@@ -454,10 +454,14 @@ class SvdEngine:
         hs = self._host_state.setdefault(B, dict(next=0, pending=[], last=None))
         pend = hs["pending"]
         if not pend or any(x is not y for x, y in zip(pend[0]["arrays"], (users, items, rates))):
+            fetched = any(e["sorted"] for e in pend)
             for e in pend:   # not the batch that was handed over: drop what is pending (after its task has run)
                 if e["fut"] is not None:
                     e["fut"].exception()
             pend.clear()
+            if fetched:   # a step in flight is copying / sorting a dropped batch: let it finish before its set is reused
+                torch.cuda.current_stream(self.device).synchronize()
+                self.side_streams[0].synchronize()
             self.prefetch_host(users, items, rates, _inline=True)   # nothing to overlap with: no hand-off to the worker
         head = pend.pop(0)
         prof = self.host_prof
