@@ -343,17 +343,19 @@ class SvdEngine:
             a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
         return a, a.ctypes.data, self._FEED_DTYPES[a.dtype], (a.strides[0] if a.size else a.itemsize)
 
-    # The feed path is a ring of staging sets driven by two C calls (tfr_svd_feed_prefetch / tfr_svd_feed_step).
-    # prefetch_host(batch) packs the columns into a pinned staging buffer (value cast + range check in C), copies it to
-    # the device and sorts its ids on the SIDE stream -- all of which needs no table data, so it runs under the previous
-    # step's table pass.  train_step_host(batch) then issues forward + segment sums, copies the predictions (they come
-    # from the PRE-update tables) back on a copy stream while the Adam pass runs, and returns as soon as the
-    # predictions are on the host.  A driver that owns its iterator (svd_train_val.py) hands over batch t+1 BEFORE it
-    # asks for step t (up to four batches may be pending: one stepping, one sorting, two packed or being packed -- the
-    # slack that keeps a late pack from ever reaching the step stream: profiles/r02_feed_path.md), so that its host work overlaps step t on the device; a plain
-    # sess.run(feed_dict) without a prefetch does the same work in line.  Every reuse of a staging set is ordered by
-    # its events: the pinned buffer is never repacked while a copy from it is queued (also with fetch=False, which does
-    # not synchronise), the device buffers never overwritten while a step still reads them.
+    # The feed path is a ring of staging sets (include/tfrecomm.h, "the feed_dict step").  prefetch_host(batch) hands a
+    # coming batch to the feed worker thread, which packs its columns into the set's pinned buffer (value cast + range check
+    # in C; no stream is touched).  train_step_host(batch) launches the set's step GRAPH: forward + segment sums, then the
+    # table pass, and beside the pass one branch of kernels that delivers the predictions (they come from the PRE-update
+    # tables) into pinned memory, fetches the staged NEXT batch from its pinned buffer and sorts its ids; it
+    # returns as soon as the delivery flag says the predictions are on the host.  A driver that owns its iterator
+    # (svd_train_val.py) hands over batches t+1 .. t+3 BEFORE it asks for step t (up to four may be pending: one stepping,
+    # one being fetched + sorted, two packed or being packed -- the slack that keeps a late pack from ever reaching the step
+    # stream; profiles/r02_feed_path.md has the measurements behind every one of these choices).  A plain
+    # sess.run(feed_dict) without a prefetch does the same work in line: pack, eager copy + sort, the step graph without
+    # a next batch.  Every reuse of a staging set is ordered: the pinned buffer is never repacked before the step that
+    # consumed it has finished, the device buffers never overwritten while a step still reads them (stream order inside
+    # the graphs, the set's events on the eager path -- fetch=False and TFR_FEED_GRAPHS=0 use only that one).
     N_FEED_SETS = 5
 
     def _host_set(self, B, k):
