@@ -159,9 +159,11 @@ class Session(object):
         return feed[ph]
 
     def prefetch(self, feed_dict):
-        """Not in TensorFlow's API: hands the NEXT train step's feed_dict over early, so that its host packing, H2D
-        copy and id sort run under the current step's table pass (SvdEngine.prefetch_host).  The following
-        run([train_op, ...], feed_dict) must be fed the same arrays; anything else just drops the prefetched batch."""
+        """Not in TensorFlow's API: hands a COMING train step's feed_dict over early (up to four may be pending; the driver
+        hands over three ahead), so that its host packing runs on the feed worker thread and its copy to the device and
+        id sort run under the table pass of the step before it (SvdEngine.prefetch_host).  The handed-over batches must
+        then be stepped in that order -- run([train_op, ...], feed_dict) with the same arrays; anything else just drops
+        what is pending."""
         m = current_model()
         if m.engine is None:
             raise _lib.TfrError("variables are not initialised: run the initializer op first")
