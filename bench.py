@@ -282,7 +282,7 @@ def run_workload(name, args, torch, with_e2e=True, with_roofline=True, sample_cl
     if with_e2e:
         rng = np.random.default_rng(3)
         batches = []
-        for _ in range(min(args.steps, 200) + 15):
+        for _ in range(min(max(args.steps, 100), 200) + 15):   # (>= 100 timed steps: the pipeline's fill is part of the number)
             rows = rng.integers(0, n_train, B)
             batches.append((cols[0][rows].astype(np.float64), cols[1][rows].astype(np.float64),
                             cols[2][rows].astype(np.float64)))   # float64 columns: what ShuffleIterator yields
