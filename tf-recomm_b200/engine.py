@@ -451,6 +451,18 @@ class SvdEngine:
             g = self._graphs[key] = exe.value
         return g
 
+    def prepare_feed_graphs(self, B, fetch=True):
+        """Captures (without running anything) every step graph a host-fed loop of batch size B is going to launch, so that
+        no capture / instantiation falls into a timed region: per staging set the graph with the next set's fetch + sort
+        and the one without."""
+        mode = 0 if not fetch else (1 if not (self.flags & LOSS_SIGMOID_CE) else 2)
+        if not self.feed_graphs:
+            return
+        for k in range(self.N_FEED_SETS):
+            self._feed_graph(B, k, None, mode)
+            if fetch:
+                self._feed_graph(B, k, (k + 1) % self.N_FEED_SETS, mode)
+
     def train_step_host(self, users, items, rates, fetch=True):
         B = len(users)
         hs = self._host_state.setdefault(B, dict(next=0, pending=[], last=None))
