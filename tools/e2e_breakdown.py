@@ -1,5 +1,8 @@
-"""Host-side breakdown of SvdEngine.train_step_host (the Session.run feed_dict path): where the end-to-end
-microseconds go.  Usage (GPU box): python tools/e2e_breakdown.py [workload]"""
+"""Breakdown of SvdEngine.train_step_host (the Session.run feed_dict path): where the end-to-end microseconds go.
+Prints, for 1 .. N_FEED_SETS - 2 batches handed over ahead: the wall time per step (mean and percentiles), the host-side
+phases of train_step_host, the step stream's busy / idle time by CUDA events, and the in-kernel %globaltimer timeline of a
+steady-state step -- beside the device-resident step of the same box.
+Usage (GPU box): [TFR_NB=215] [TFR_FEED_SETS=n] [TFR_FEED_GRAPHS=0] [TFR_FEED_WORKER=0] python tools/e2e_breakdown.py [workload]"""
 import os
 import sys
 import time
@@ -101,8 +104,6 @@ def main():
         med = lambda xs: float(np.median(list(xs))) * 1e3
         print("    step stream (events): step %.1f us, idle before the next step %.1f us"
               % (med(A[j].elapsed_time(Z[j]) for j in js), med(Z[j].elapsed_time(A[j + 1]) for j in js)))
-    if not eng.feed_worker:
-        device_timeline(eng, batches)
     kernel_timeline(eng, batches, eng.N_FEED_SETS - 2)
     eng.close()
 
@@ -133,35 +134,6 @@ def kernel_timeline(eng, batches, ahead):
         if k in acc:
             a = np.median([x[0] for x in acc[k]]); b = np.median([x[1] for x in acc[k]])
             print("    %-12s start %7.1f  end %7.1f  dur %7.1f" % (k, a, b, b - a))
-
-
-def device_timeline(eng, batches):
-    """CUDA events around each step's launches on the main stream and around each prefetch on the side stream (in-line
-    prefetch only: the events are recorded by this thread): is the loop bound by the device or by the host?"""
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    main, side = torch.cuda.current_stream(), eng.side_streams[0]
-    A, Bm, S0, S1 = {}, {}, {}, {}
-    def pre(j):
-        S0[j] = ev(); S0[j].record(side)
-        eng.prefetch_host(*batches[j])
-        S1[j] = ev(); S1[j].record(side)
-    pre(5)
-    for j in range(5, len(batches)):
-        if j + 1 < len(batches):
-            pre(j + 1)
-        A[j] = ev(); A[j].record(main)
-        eng.train_step_host(*batches[j])
-        Bm[j] = ev(); Bm[j].record(main)
-    torch.cuda.synchronize()
-    js = range(8, len(batches) - 2)
-    med = lambda xs: float(np.median(list(xs))) * 1e3
-    print("  main stream: step span %.1f us (first launch -> pass end), idle between steps %.1f us, step period %.1f us"
-          % (med(A[j].elapsed_time(Bm[j]) for j in js), med(Bm[j].elapsed_time(A[j + 1]) for j in js),
-             med(A[j].elapsed_time(A[j + 1]) for j in js)))
-    print("  side stream: H2D + id sort of batch j+1 takes %.1f us, starts %.1f us after step j's first launch, ends %.1f us "
-          "before step j+1's first launch" % (med(S0[j + 1].elapsed_time(S1[j + 1]) for j in js),
-                                              med(A[j].elapsed_time(S0[j + 1]) for j in js),
-                                              med(S1[j + 1].elapsed_time(A[j + 1]) for j in js)))
 
 
 if __name__ == "__main__":
